@@ -1,0 +1,158 @@
+/*
+ * symphony_b200 — C ABI of the B200 (sm_100a) query-mapping kernels.
+ *
+ * Drop-in boundary for the hot path of potulabe/symphonypy:
+ *   symphonypy/tl.py:271-397   map_embedding      (project -> assign -> MoE correct)
+ *   symphonypy/tl.py:400-436   transfer_labels_kNN (brute Euclidean kNN + majority vote)
+ * The reference is pure Python (numpy / scikit-learn); it has no FFI of its own, so the
+ * entry points below are the numerical call sites of that path, one export per reference
+ * call cluster, each citing the lines it replaces.  `INTEGRATION.md` shows the ctypes
+ * binding a maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the comment says "host"
+ *   - all matrices are row-major, float32 unless stated; sizes in elements
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*),
+ *     allocates nothing, and returns 0 on success or a non-zero code
+ *     (SYM_ERR_* below, or 1000 + cudaError_t); `sym_last_error()` gives the text
+ *   - no C++ exceptions cross the boundary; no torch types appear in it
+ */
+#ifndef SYMPHONY_B200_H
+#define SYMPHONY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SYM_OK 0
+#define SYM_ERR_INVALID_ARGUMENT 1
+#define SYM_ERR_UNSUPPORTED_SHAPE 2
+#define SYM_ERR_WORKSPACE_TOO_SMALL 3
+#define SYM_ERR_CUDA_BASE 1000
+
+typedef void *sym_stream_t;
+
+/* Library version (major*10000 + minor*100 + patch). */
+int sym_version(void);
+/* Text of the last error raised on the calling host thread ("" if none). */
+const char *sym_last_error(void);
+/* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
+int64_t sym_launch_count(void);
+/* Compute capability (major*10+minor) the kernels were compiled for: 100. */
+int sym_compiled_arch(void);
+
+/* ---------------------------------------------------------------------------------------
+ * (1) project — replaces symphonypy/_utils.py:298-308 (scale, clip, GEMM with loadings).
+ *   Z[n,:] = sum_g clip((X[n,col(g)] - mu[g]) * inv_sd[g], -clip, +clip) * U[g,:]
+ *   X        [N, ldx]  query expression; column col(g) holds reference gene g
+ *   gene_col [G] or NULL   NULL: col(g) = g.  Entries < 0 mark genes absent from the query;
+ *                      together with inv_sd[g] == 0 (absent or zero-std genes,
+ *                      _utils.py:276) they contribute exactly 0 (_utils.py:240-243).
+ *   U        [G, ldu]  loadings, ldu >= d, ldu % 4 == 0, columns d..ldu-1 zero
+ *   Z        [N, ldz]  ldz >= d.   d <= 128.
+ */
+int sym_project_dense(const float *X, int64_t N, int64_t ldx, const int32_t *gene_col, int32_t G,
+                      const float *mu, const float *inv_sd, const float *U, int32_t ldu, int32_t d,
+                      float clip, float *Z, int32_t ldz, sym_stream_t stream);
+
+/* CSR query (scipy layout) — replaces _utils.py:240-243,284-285 (densify) + :298-308.
+ *   Z[n,:] = z0 + sum_{nnz j of row n, gene g=col_gene[indices[j]] >= 0}
+ *                   (clip((data[j]-mu[g])*inv_sd[g]) - clip(-mu[g]*inv_sd[g])) * U[g,:]
+ *   z0[d] = sum_g clip(-mu[g]*inv_sd[g]) * U[g,:]  is written by sym_project_csr_bias.
+ *   col_gene [n_query_cols]  reference gene index of each query column, or -1 if unused.
+ */
+int sym_project_csr_bias(const float *mu, const float *inv_sd, const float *U, int32_t ldu, int32_t G,
+                         int32_t d, float clip, float *z0, sym_stream_t stream);
+int sym_project_csr(const float *data, const int32_t *indices, const int64_t *indptr, int64_t N,
+                    const int32_t *col_gene, const float *mu, const float *inv_sd, const float *U,
+                    int32_t ldu, int32_t d, float clip, const float *z0, float *Z, int32_t ldz,
+                    sym_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (2) assign — replaces symphonypy/_utils.py:154-178.
+ *   zc = sign(max_j Z[n,j]) * Z[n,:] / ||Z[n,:]||     (signed row max: _utils.py:168-170)
+ *   R[n,k] = softmax_k( -2 (1 - Y[k,:].zc) * inv_sigma[k] )
+ *   Y [K,d] unit-norm centroids (tl.py:361-362), inv_sigma [K], R [N,K].  K <= 1024, d <= 128.
+ */
+int sym_assign(const float *Z, int32_t ldz, int64_t N, int32_t d, const float *Y, int32_t K,
+               const float *inv_sigma, float *R, sym_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (3) MoE correction — replaces symphonypy/_utils.py:181-214.  The design matrix Phi of
+ * tl.py:368-378 is one-hot per batch variable, so it is passed as integer level codes.
+ * Design column of level c of variable v is  col = 1 + var_offset[v] + c  (column 0 = intercept).
+ *
+ * sym_batch_order: counting sort of the cells by level code of ONE variable.
+ *   codes [N] in [0,B);  perm [N] cell ids grouped by level;  seg [B+1] int64 group offsets;
+ *   chunk_start [B+1] int32 prefix of ceil(group/256) (work list of the stats/apply kernels).
+ *   workspace: >= sym_batch_order_workspace(B) bytes.
+ */
+size_t sym_batch_order_workspace(int32_t B);
+int sym_batch_order(const int32_t *codes, int64_t N, int32_t B, int32_t *perm, int64_t *seg,
+                    int32_t *chunk_start, void *workspace, size_t workspace_bytes, sym_stream_t stream);
+
+/* sym_moe_stats: accumulate (+=) the sufficient statistics of _utils.py:196-204 for variable v:
+ *   gram [K,B1,B1] f64:  gram[k,c,c] += sum_{n in level} R[n,k]
+ *                         gram[k,c,c'] and gram[k,c',c] += R[n,k] for the level c' of every
+ *                         later variable v' > v of the same cell
+ *   cross[K,B1,d]  f64:  cross[k,c,:] += sum_{n in level} R[n,k] Z[n,:]
+ *   (row / column 0 and the priors Nr, C are filled in by sym_moe_solve, AFTER any
+ *    cross-GPU all-reduce of gram and cross — _utils.py:201,205 add them once, globally.)
+ *   codes [V,N] all variables;  var_offset [V] host array;  perm/seg/chunk_start: order of
+ *   variable v from sym_batch_order, or perm == NULL when variable v has a single level.
+ */
+int sym_moe_stats(const float *Z, int32_t ldz, const float *R, int64_t N, int32_t d, int32_t K,
+                  const int32_t *codes, int32_t V, const int32_t *var_offset_host, int32_t v,
+                  int32_t n_levels_v, const int32_t *perm, const int64_t *seg, const int32_t *chunk_start,
+                  int32_t B1, double *gram, double *cross, sym_stream_t stream);
+
+/* sym_moe_solve: W_k = inv(gram_k + diag(lamb)) cross_k with row 0 zeroed (_utils.py:201-209).
+ *   Builds row/column 0 (intercept) from the levels of variable 0, adds Nr[k] to gram[k,0,0] and
+ *   C[k,:] to cross[k,0,:], factorises (Cholesky, float64, in shared memory) and solves.
+ *   Requires ((B1*B1 + B1*d) * 8 bytes <= 200 KiB.
+ *   lamb [B1] f64 (lamb[0] == 0);  W [K,B1,d] f32;  info [K] int32: 0 ok, j>0 = pivot j not positive.
+ */
+int sym_moe_solve(const double *gram, const double *cross, const double *Nr, const double *C,
+                  const double *lamb, int32_t K, int32_t B1, int32_t d, int32_t n_levels_var0,
+                  float *W, int32_t *info, sym_stream_t stream);
+
+/* sym_moe_apply: Zout[n,:] = Zin[n,:] - sum_k R[n,k] W[k, 1+var_offset+code[n], :] (_utils.py:212)
+ *   for ONE variable; call once per variable, chaining Zout -> Zin (in place allowed).
+ */
+int sym_moe_apply(const float *Zin, int32_t ldzin, const float *R, int64_t N, int32_t d, int32_t K,
+                  const int32_t *codes_v, int32_t var_offset, int32_t n_levels_v, const int32_t *perm,
+                  const int64_t *seg, const int32_t *chunk_start, const float *W, int32_t B1, float *Zout,
+                  int32_t ldzout, sym_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (4) kNN + vote — replaces tl.py:425-433 (sklearn KNeighborsClassifier, brute Euclidean,
+ * uniform weights).
+ *
+ * sym_knn_fit (KNeighborsClassifier.fit): packs the reference embedding once.
+ *   Ref [M,ldr] -> packed (opaque, sym_knn_packed_bytes(M,d) bytes).
+ * sym_knn (kneighbors): idx [N,k] int32 ascending by (squared distance, index), dist2 [N,k] f32.
+ *   Candidates are selected by a float32 (or tensor-core) scan over-selecting k+pad per row and
+ *   re-ranked in float64 with sklearn's formula ||x||^2 - 2x.y + ||y||^2 clamped at 0; ties go
+ *   to the lower reference index.  k <= 120, d <= 128, k <= M.
+ *   method: 0 = auto, 1 = FP32 FFMA scan, 2 = tcgen05 scan (sm_100a tensor cores).
+ *   unsafe [N] uint8 or NULL: rows whose over-selection margin could not be certified
+ *   (tensor-core scan only; the caller re-runs those rows with method 1).
+ * sym_vote (predict / predict_proba): label[n] = lowest class code among the most frequent
+ *   codes of the k neighbours; conf[n] = winning votes / k.
+ */
+size_t sym_knn_packed_bytes(int64_t M, int32_t d);
+int sym_knn_fit(const float *Ref, int32_t ldr, int64_t M, int32_t d, void *packed, sym_stream_t stream);
+size_t sym_knn_workspace(int64_t N, int64_t M, int32_t d, int32_t k, int32_t method);
+int sym_knn(const float *Q, int32_t ldq, int64_t N, const float *Ref, int32_t ldr, int64_t M,
+            const void *packed, int32_t d, int32_t k, int32_t method, int32_t *idx, float *dist2,
+            uint8_t *unsafe, void *workspace, size_t workspace_bytes, sym_stream_t stream);
+int sym_vote(const int32_t *idx, int64_t N, int32_t k, const int32_t *ref_codes, int32_t *label,
+             float *conf, sym_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SYMPHONY_B200_H */

@@ -1,0 +1,212 @@
+"""numpy / scikit-learn restatement of the reference's query-mapping path.
+
+TEST INFRASTRUCTURE (see `oracle/__init__.py`): the checker for the CUDA path and
+the timed CPU baseline ("port") of `bench.py`.  Never imported by the product.
+
+Each function names the reference lines it follows.  Array arithmetic is kept in
+the same order and dtype as the reference so results agree to the last bit where
+numpy is deterministic, and so that timing this port is representative of timing
+the reference (the boolean-masked in-place scaling of `_utils.py:298-299` — the
+reference's slowest step — is kept as such).
+
+The kNN arithmetic of `tl.transfer_labels_kNN` is not in the reference tree: it
+is scikit-learn's `KNeighborsClassifier` (unpinned in `setup.cfg:19-22`;
+scikit-learn 1.9.0 in this image, brute force `EuclideanArgKmin64`,
+SURVEY.md App. C).  `transfer_labels_knn` calls that estimator exactly as
+`tl.py:425-436` does; `knn_vote_from_indices` restates its vote rule
+(votes/k, argmax with ties to the lowest sorted class).
+"""
+from __future__ import annotations
+
+import logging
+import warnings
+
+import numpy as np
+import pandas as pd
+from scipy.sparse import issparse
+
+logger = logging.getLogger("symphony_oracle")
+
+CLIP = 10.0  # `_utils.py:253`: max_value default, never overridden by `tl.py:350-356`
+
+
+# --------------------------------------------------------------------------- project
+def reference_genes(adata_ref, use_genes_column="highly_variable"):
+    """`_utils.py:263-274`: gene list (reference order) and their stds."""
+    if use_genes_column is None:
+        return adata_ref.var_names, np.array(adata_ref.var["std"]), None
+    hv = adata_ref.var[use_genes_column]
+    return adata_ref.var_names[hv], np.array(adata_ref.var["std"][hv]), hv
+
+
+def map_query_to_ref(adata_ref, adata_query, loadings_key="PCs", use_genes_column="highly_variable",
+                     max_value=CLIP):
+    """`_utils.py:248-308` (+ `_adjust_for_missing_genes`, `:217-245`).  Returns Z [N, d]."""
+    assert "mean" in adata_ref.var, "Gene expression means are expected to be saved in adata_ref.var"
+    assert "std" in adata_ref.var, "Gene expression stds are expected to be saved in adata_ref.var"
+    genes, sd, hv = reference_genes(adata_ref, use_genes_column)
+    present = genes.isin(adata_query.var_names) & (sd != 0)  # `:276`
+
+    if present.all():  # `:283-285`: query dtype is kept
+        block = adata_query[:, genes].X
+        t = block.toarray() if issparse(block) else block.copy()
+    else:  # `:233-243`: float64 zero buffer, present columns filled in
+        logger.warning("%i out of %i genes from the reference are missing in the query dataset or "
+                       "have zero std in the reference, their expressions in the query will be set to zero",
+                       int((~present).sum()), genes.shape[0])
+        t = np.zeros((adata_query.shape[0], genes.shape[0]))
+        block = adata_query[:, genes[present]].X
+        t[:, present] = block.toarray() if issparse(block) else block.copy()
+
+    mu_all = adata_ref.var["mean"] if hv is None else adata_ref.var["mean"][hv]
+    mu = np.array(mu_all[present])  # `:287-295`
+    sd = sd[present]  # `:296`
+    t[:, present] -= mu[None, :]  # `:298`
+    t[:, present] /= sd[None, :]  # `:299`
+    if max_value is not None:
+        t = np.clip(t, -max_value, max_value)  # `:301-302`
+    loadings = adata_ref.varm[loadings_key][adata_ref.var_names.isin(genes)]  # `:307`
+    return np.array(t @ loadings)
+
+
+# --------------------------------------------------------------------------- assign
+def assign_clusters(X, sigma, Y, K):
+    """`_utils.py:154-178`.  Returns R [K, N]."""
+    if isinstance(sigma, (int, float)):
+        sigma = np.array([sigma], dtype=np.float32)
+    else:
+        sigma = np.array(sigma, dtype=np.float32)
+        assert len(sigma) == K, \
+            "sigma paramater must be either a single float or an array of length equal to number of clusters"
+    xc = X / X.max(axis=1, keepdims=True)  # signed row max (`:168`)
+    xc /= np.linalg.norm(xc, ord=2, axis=1, keepdims=True)
+    R = -2 * (1 - Y @ xc.T) / sigma[..., None]
+    R -= R.max(axis=0)
+    R = np.exp(R)
+    R /= R.sum(axis=0, keepdims=True)
+    return R
+
+
+# --------------------------------------------------------------------------- design
+def build_design(adata_query, key, lamb):
+    """`tl.py:368-392`: Phi_ [(B+1), N] and the ridge matrix diag(0, lamb...)."""
+    if key is None:
+        batch = pd.DataFrame({"batch": ["1"] * len(adata_query)})
+    elif isinstance(key, str):
+        batch = pd.DataFrame(adata_query.obs[key]).astype(str)
+    else:
+        batch = adata_query.obs[key].astype(str)
+    phi = pd.get_dummies(batch).to_numpy().T
+    phi_ = np.concatenate([np.ones((1, phi.shape[1])), phi], axis=0)
+    levels = batch.describe().loc["unique"].to_numpy().astype(int)
+    if lamb is None:
+        lamb = np.repeat([1] * len(levels), levels)
+    elif isinstance(lamb, (float, int)):
+        lamb = np.repeat([lamb] * len(levels), levels)
+    elif len(lamb) == len(levels):
+        lamb = np.repeat([lamb], levels)
+    else:
+        assert len(lamb) == np.sum(levels), "each batch variable must have a lambda"
+    return phi_, np.diag(np.insert(lamb, 0, 0))
+
+
+# --------------------------------------------------------------------------- MoE
+def correct_query(X, phi_, R, Nr, C, lamb):
+    """`_utils.py:181-214`.  Returns X_corr [N, d]."""
+    out = X.copy().T
+    lamb[0, 0] = 0
+    for k in range(R.shape[0]):
+        pr = np.multiply(phi_, R[k, :])  # `:196`
+        gram = pr @ phi_.T  # `:199`
+        gram[0, 0] += Nr[k]
+        cross = pr @ X  # `:204`
+        cross[0, :] += C[k]
+        W = np.linalg.inv(gram + lamb) @ cross  # `:208`
+        W[0, :] = 0
+        out -= W.T @ pr  # `:212`
+    return out.T
+
+
+def moe_weights(X, phi_, R, Nr, C, lamb):
+    """The per-cluster ridge weights W [K, B+1, d] of `_utils.py:196-209` (exposed for
+    kernel-level tests; the reference never returns them)."""
+    lamb = lamb.copy()
+    lamb[0, 0] = 0
+    W = np.zeros((R.shape[0], phi_.shape[0], X.shape[1]))
+    for k in range(R.shape[0]):
+        pr = phi_ * R[k, :]
+        gram = pr @ phi_.T
+        gram[0, 0] += Nr[k]
+        cross = pr @ X
+        cross[0, :] += C[k]
+        W[k] = np.linalg.inv(gram + lamb) @ cross
+        W[k, 0, :] = 0
+    return W
+
+
+# --------------------------------------------------------------------------- map_embedding
+def map_embedding(adata_query, adata_ref, key=None, lamb=None, sigma=0.1,
+                  use_genes_column="highly_variable", transferred_adjusted_basis="X_pca_harmony",
+                  transferred_primary_basis="X_pca_reference"):
+    """`tl.py:271-397` without the out-of-scope no-Harmony fallback (`:320-335`)."""
+    assert "mean" in adata_ref.var, "Gene expression means are expected to be saved in adata_ref.var"
+    assert "std" in adata_ref.var, "Gene expression stds are expected to be saved in adata_ref.var"
+    assert "harmony" in adata_ref.uns, "oracle covers the Harmony-reference path only"
+    if use_genes_column is not None:
+        assert use_genes_column in adata_ref.var, \
+            f"Column `{use_genes_column}` not found in adata_ref.var. Set `use_genes_column` parameter properly"
+    if "log1p" not in adata_query.uns:
+        warnings.warn("Gene expressions in adata_query should be log1p-transformed")
+    h = adata_ref.uns["harmony"]
+    Z = map_query_to_ref(adata_ref, adata_query, h["ref_basis_loadings"], use_genes_column)
+    adata_query.obsm[transferred_primary_basis] = Z
+    C = h["C"]
+    Y = C / np.linalg.norm(C, ord=2, axis=1, keepdims=True)  # `:361-362`
+    R = assign_clusters(Z, sigma, Y, h["K"])
+    phi_, lam = build_design(adata_query, key, lamb)
+    adata_query.obsm[transferred_adjusted_basis] = correct_query(Z, phi_, R, h["Nr"], h["C"], lam)
+    adata_query.obsm[f"{transferred_adjusted_basis}_symphony_R"] = R.T
+
+
+# --------------------------------------------------------------------------- kNN transfer
+def transfer_labels_knn(adata_query, adata_ref, ref_labels, *knn_args, query_labels=None,
+                        ref_basis="X_pca_harmony", query_basis="X_pca_harmony", **knn_kwargs):
+    """`tl.py:400-436`: the estimator call sequence, verbatim in meaning."""
+    from sklearn.neighbors import KNeighborsClassifier
+
+    knn = KNeighborsClassifier(*knn_args, **knn_kwargs)
+    knn.fit(adata_ref.obsm[ref_basis], adata_ref.obs[ref_labels])
+    if query_labels is None:
+        query_labels = ref_labels
+    pred = knn.predict(adata_query.obsm[query_basis])
+    if isinstance(query_labels, list) and len(query_labels) == 1:
+        pred = pred.reshape(pred.shape[0], 1)
+    adata_query.obs[query_labels] = pred
+    return knn
+
+
+def knn_indices(ref_emb, query_emb, k):
+    """Neighbour indices / squared distances as sklearn's brute Euclidean ArgKmin gives
+    them (ascending distance), for index-level parity checks."""
+    from sklearn.neighbors import NearestNeighbors
+
+    nn = NearestNeighbors(n_neighbors=k, algorithm="brute").fit(ref_emb)
+    dist, idx = nn.kneighbors(query_emb)
+    return idx, dist ** 2
+
+
+def exact_sqdist(ref_emb, query_emb, idx):
+    """float64 direct-form squared distances of given (query, neighbour) pairs."""
+    diff = np.asarray(query_emb, dtype=np.float64)[:, None, :] - np.asarray(ref_emb, dtype=np.float64)[idx]
+    return np.einsum("nkd,nkd->nk", diff, diff)
+
+
+def knn_vote_from_indices(idx, ref_label_codes, n_classes):
+    """sklearn `predict_proba`/`predict` rule for uniform weights:
+    proba = votes / k; label = lowest class index among the maxima.  Returns
+    (winning class code [N], winning vote fraction [N])."""
+    votes = np.zeros((idx.shape[0], n_classes), dtype=np.int64)
+    rows = np.repeat(np.arange(idx.shape[0]), idx.shape[1])
+    np.add.at(votes, (rows, ref_label_codes[idx].ravel()), 1)
+    win = votes.argmax(axis=1)
+    return win, votes.max(axis=1) / idx.shape[1]

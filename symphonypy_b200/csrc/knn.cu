@@ -1,0 +1,500 @@
+// (4) brute-force Euclidean kNN + majority vote                  — symphonypy/tl.py:425-433
+// (sklearn KNeighborsClassifier: EuclideanArgKmin + uniform vote)
+//
+// Pipeline:   fit (pack reference once)  ->  scan (over-select kc = k + pad candidates per query
+// row, distance matrix never materialised)  ->  rerank (float64, sklearn's formula, (dist, index)
+// order, certifies the over-selection margin)  ->  vote.
+//
+// This file holds the FP32 FFMA scan (method 1) plus fit / rerank / vote, which every method
+// shares.  The tcgen05 scan (method 2) is in knn_tc.cu.
+//
+// FFMA scan: a CTA owns 128 query rows and walks the reference in 128-column tiles staged by
+// cp.async (3 stages of [32 dims x 128 refs]); each thread keeps an 8x8 register tile of
+// s = ||r||^2 - 2 q.r.  A candidate is examined further only if s <= the row's current kc-th best
+// (one compare per pair in the steady state); survivors go through a small per-row queue in
+// shared memory into the row's top-kc list (replace-the-maximum, warp cooperative).
+#include <float.h>
+
+#include "common.cuh"
+#include "knn_common.cuh"
+
+namespace sym {
+
+// ------------------------------------------------------------------------------------------ fit
+// RefT[dd][m] = Ref[m][dd] (zero padded to d4 x Mpad), norm2[m] = ||Ref[m]||^2 (NaN for padding),
+// header.rmax2 = max_m norm2[m].
+__global__ void __launch_bounds__(256)
+knn_fit_kernel(const float *__restrict__ Ref, int ldr, int64_t M, int d, KnnPacked pk) {
+    __shared__ float tile[128][33];
+    const int64_t m0 = (int64_t)blockIdx.x * 128;
+    const int tid = threadIdx.x;
+    float nrm = 0.f;  // threads 0..127 accumulate the norm of row m0 + tid
+    for (int d0 = 0; d0 < pk.d4; d0 += 32) {
+        __syncthreads();
+        for (int i = tid; i < 128 * 32; i += 256) {
+            const int r = i / 32, c = i % 32;
+            const int64_t m = m0 + r;
+            tile[r][c] = (m < M && d0 + c < d) ? Ref[m * ldr + d0 + c] : 0.f;
+        }
+        __syncthreads();
+        for (int i = tid; i < 32 * 128; i += 256) {
+            const int c = i / 128, r = i % 128;
+            if (d0 + c < pk.d4) pk.refT[(int64_t)(d0 + c) * pk.Mpad + m0 + r] = tile[r][c];
+        }
+        if (tid < 128)
+            for (int c = 0; c < 32; ++c) nrm = fmaf(tile[tid][c], tile[tid][c], nrm);
+    }
+    if (tid < 128) {
+        const bool real = m0 + tid < M;
+        pk.norm2[m0 + tid] = real ? nrm : __int_as_float(0x7fc00000);  // NaN: padding never passes a compare
+        // max over the block -> header (float atomic max through the int ordering of non-negatives)
+        float v = real ? nrm : 0.f;
+        v = warp_max(v);
+        if ((tid & 31) == 0) atomicMax(reinterpret_cast<int *>(&pk.hdr->rmax2), __float_as_int(v));
+    }
+}
+
+// ------------------------------------------------------------------------------------------ scan
+constexpr int SC_THREADS = 256;
+constexpr int SC_BQ = 128;
+constexpr int SC_BR = 128;
+constexpr int SC_DC = 32;     // dims per pipeline stage
+constexpr int SC_STAGES = 3;
+constexpr int SC_QCAP = 8;    // per-row candidate queue
+
+struct ScanSmem {
+    float *Qs;                 // [d4][SC_BQ]     (-2 q, transposed)
+    float *Rs;                 // [SC_STAGES][SC_DC][SC_BR]
+    float *rn;                 // [SC_STAGES][SC_BR]
+    float *thr_f;              // [SC_BQ]
+    unsigned long long *thr_key;   // [SC_BQ]
+    int *thr_pos;              // [SC_BQ]
+    int *cnt;                  // [SC_BQ]
+    unsigned long long *cand;  // [SC_BQ][SC_QCAP]
+    unsigned long long *top;   // [SC_BQ][kcap]  (shared memory when it fits, else global workspace)
+};
+
+__host__ __device__ inline size_t scan_smem_bytes(int d4, int kcap, bool top_in_smem) {
+    size_t b = (size_t)d4 * SC_BQ * 4 + (size_t)SC_STAGES * SC_DC * SC_BR * 4 + (size_t)SC_STAGES * SC_BR * 4;
+    b += SC_BQ * 4 + SC_BQ * 8 + SC_BQ * 4 + SC_BQ * 4 + (size_t)SC_BQ * SC_QCAP * 8;
+    if (top_in_smem) b += (size_t)SC_BQ * kcap * 8;
+    return b + 16;
+}
+
+// warp-cooperative: insert `key` into the row's list if it beats the current maximum
+__device__ __forceinline__ void topk_insert(unsigned long long *top_row, int kc, unsigned long long key,
+                                            unsigned long long &mx, int &mxpos, int lane) {
+    if (key >= mx) return;
+    if (lane == 0) top_row[mxpos] = key;
+    __syncwarp();
+    unsigned long long best = 0ull;
+    int bpos = 0;
+    for (int j = lane; j < kc; j += 32) {
+        const unsigned long long v = top_row[j];
+        if (v >= best) { best = v; bpos = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int op = __shfl_xor_sync(0xffffffffu, bpos, o);
+        if (ov > best || (ov == best && op > bpos)) { best = ov; bpos = op; }
+    }
+    mx = best;
+    mxpos = bpos;
+}
+
+__global__ void __launch_bounds__(SC_THREADS)
+knn_scan_ffma_kernel(const float *__restrict__ Q, int ldq, int64_t N, KnnPacked pk, int d, int kc, int kcap,
+                     int tiles_per_split, int top_in_smem, unsigned long long *__restrict__ top_ws,
+                     int32_t *__restrict__ cand_out, float *__restrict__ thr_out) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int d4 = pk.d4;
+    ScanSmem S;
+    {
+        unsigned char *p = smraw;
+        S.cand = (unsigned long long *)p; p += (size_t)SC_BQ * SC_QCAP * 8;
+        S.thr_key = (unsigned long long *)p; p += SC_BQ * 8;
+        if (top_in_smem) { S.top = (unsigned long long *)p; p += (size_t)SC_BQ * kcap * 8; }
+        S.Qs = (float *)p; p += (size_t)d4 * SC_BQ * 4;
+        S.Rs = (float *)p; p += (size_t)SC_STAGES * SC_DC * SC_BR * 4;
+        S.rn = (float *)p; p += SC_STAGES * SC_BR * 4;
+        S.thr_f = (float *)p; p += SC_BQ * 4;
+        S.thr_pos = (int *)p; p += SC_BQ * 4;
+        S.cnt = (int *)p;
+        if (!top_in_smem)
+            S.top = top_ws + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * SC_BQ * kcap;
+    }
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int64_t q0 = (int64_t)blockIdx.x * SC_BQ;
+    const int split = blockIdx.y, nsplit = gridDim.y;
+    const int ntiles_all = (int)(pk.Mpad / SC_BR);
+    const int t_beg = split * tiles_per_split;
+    const int t_end = min(ntiles_all, t_beg + tiles_per_split);
+    const int ntiles = max(0, t_end - t_beg);
+    const int nchunks = (d4 + SC_DC - 1) / SC_DC;
+    const int nstages = ntiles * nchunks;
+
+    // ---- init: Q tile (scaled by -2, transposed), top lists, thresholds
+    for (int i = tid; i < SC_BQ * d4; i += SC_THREADS) {
+        const int r = i / d4, c = i % d4;
+        const int64_t n = q0 + r;
+        S.Qs[c * SC_BQ + r] = (n < N && c < d) ? -2.f * Q[n * ldq + c] : 0.f;
+    }
+    for (int i = tid; i < SC_BQ * kcap; i += SC_THREADS) S.top[i] = ~0ull;
+    for (int i = tid; i < SC_BQ; i += SC_THREADS) {
+        S.thr_f[i] = INFINITY;
+        S.thr_key[i] = ~0ull;
+        S.thr_pos[i] = 0;
+        S.cnt[i] = 0;
+    }
+
+    auto issue_stage = [&](int s) {
+        if (s < nstages) {
+            const int t = t_beg + s / nchunks, ck = s % nchunks;
+            const int buf = s % SC_STAGES;
+            const int dc0 = ck * SC_DC;
+            const int len = min(SC_DC, d4 - dc0);
+            float *dst = S.Rs + (size_t)buf * SC_DC * SC_BR;
+            const float *src = pk.refT + (int64_t)dc0 * pk.Mpad + (int64_t)t * SC_BR;
+            for (int i = tid; i < len * (SC_BR / 4); i += SC_THREADS) {
+                const int r = i / (SC_BR / 4), c4 = (i % (SC_BR / 4)) * 4;
+                cp_async16(dst + r * SC_BR + c4, src + (int64_t)r * pk.Mpad + c4);
+            }
+            if (ck == 0 && tid < SC_BR / 4)
+                cp_async16(S.rn + (t % SC_STAGES) * SC_BR + tid * 4, pk.norm2 + (int64_t)t * SC_BR + tid * 4);
+        }
+        cp_async_commit();
+    };
+
+    issue_stage(0);
+    issue_stage(1);
+
+    float acc[8][8];
+    for (int s = 0; s < nstages; ++s) {
+        const int t = t_beg + s / nchunks, ck = s % nchunks;
+        cp_async_wait<SC_STAGES - 2>();
+        __syncthreads();
+        issue_stage(s + SC_STAGES - 1);
+        if (ck == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        }
+        const float *rs = S.Rs + (size_t)(s % SC_STAGES) * SC_DC * SC_BR;
+        const float *qs = S.Qs + (size_t)ck * SC_DC * SC_BQ;
+        const int len = min(SC_DC, d4 - ck * SC_DC);
+#pragma unroll 4
+        for (int kk = 0; kk < len; ++kk) {
+            const float4 qa = *reinterpret_cast<const float4 *>(qs + kk * SC_BQ + ty * 4);
+            const float4 qb = *reinterpret_cast<const float4 *>(qs + kk * SC_BQ + 64 + ty * 4);
+            const float4 ra = *reinterpret_cast<const float4 *>(rs + kk * SC_BR + tx * 4);
+            const float4 rb = *reinterpret_cast<const float4 *>(rs + kk * SC_BR + 64 + tx * 4);
+            const float q[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+            const float r[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(q[i], r[j], acc[i][j]);
+        }
+        if (ck != nchunks - 1) continue;
+
+        // ---- selection epilogue for reference tile t
+        const float *rn = S.rn + (t % SC_STAGES) * SC_BR;
+        float rnv[8];
+        {
+            const float4 a = *reinterpret_cast<const float4 *>(rn + tx * 4);
+            const float4 b = *reinterpret_cast<const float4 *>(rn + 64 + tx * 4);
+            rnv[0] = a.x; rnv[1] = a.y; rnv[2] = a.z; rnv[3] = a.w;
+            rnv[4] = b.x; rnv[5] = b.y; rnv[6] = b.z; rnv[7] = b.w;
+        }
+        unsigned long long pend = 0ull;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int row = (i < 4 ? 0 : 64) + ty * 4 + (i & 3);
+            const float th = S.thr_f[row];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                acc[i][j] += rnv[j];
+                if (acc[i][j] <= th) pend |= 1ull << (i * 8 + j);
+            }
+        }
+        while (__syncthreads_or(pend != 0ull)) {
+            unsigned long long todo = pend;
+            while (todo) {
+                const int b = __ffsll((long long)todo) - 1;
+                todo &= todo - 1;
+                const int i = b >> 3, j = b & 7;
+                const int row = (i < 4 ? 0 : 64) + ty * 4 + (i & 3);
+                // select acc[i][j] without dynamic register indexing
+                float sv = 0.f;
+#pragma unroll
+                for (int ii = 0; ii < 8; ++ii)
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj)
+                        if (ii == i && jj == j) sv = acc[ii][jj];
+                const int col = (j < 4 ? 0 : 64) + tx * 4 + (j & 3);
+                const unsigned long long key = knn_make_key(sv, (uint32_t)((int64_t)t * SC_BR + col));
+                if (key >= S.thr_key[row]) {
+                    pend &= ~(1ull << b);
+                    continue;
+                }
+                const int slot = atomicAdd(&S.cnt[row], 1);
+                if (slot < SC_QCAP) {
+                    S.cand[row * SC_QCAP + slot] = key;
+                    pend &= ~(1ull << b);
+                }
+            }
+            __syncthreads();
+            for (int row = warp; row < SC_BQ; row += SC_THREADS / 32) {
+                const int c = min(S.cnt[row], SC_QCAP);
+                if (c == 0) continue;
+                unsigned long long mx = S.thr_key[row];
+                int mxpos = S.thr_pos[row];
+                unsigned long long *top_row = S.top + (size_t)row * kcap;
+                for (int e = 0; e < c; ++e) topk_insert(top_row, kc, S.cand[row * SC_QCAP + e], mx, mxpos, lane);
+                __syncwarp();
+                if (lane == 0) {
+                    S.thr_key[row] = mx;
+                    S.thr_pos[row] = mxpos;
+                    S.thr_f[row] = knn_key_score(mx);
+                    S.cnt[row] = 0;
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+
+    // ---- write the candidate sets (unordered) and the row thresholds
+    for (int i = tid; i < SC_BQ * kc; i += SC_THREADS) {
+        const int r = i / kc, e = i % kc;
+        const int64_t n = q0 + r;
+        if (n < N) cand_out[(n * nsplit + split) * kc + e] = (int32_t)(uint32_t)(S.top[(size_t)r * kcap + e] & 0xffffffffull);
+    }
+    for (int r = tid; r < SC_BQ; r += SC_THREADS)
+        if (q0 + r < N) thr_out[(q0 + r) * nsplit + split] = S.thr_f[r];
+}
+
+// ------------------------------------------------------------------------------------------ rerank
+// One warp per query row.  Exact float64 distances of the candidates, top-k by (dist, index).
+constexpr int RR_THREADS = 256;
+constexpr int RR_MAXC = 512;  // candidates per row the shared scratch can hold
+
+__global__ void __launch_bounds__(RR_THREADS)
+knn_rerank_kernel(const float *__restrict__ Q, int ldq, int64_t N, const float *__restrict__ Ref, int ldr, int64_t M,
+                  int d, int k, const int32_t *__restrict__ cand, const float *__restrict__ thr, int ncand, int nsplit,
+                  double eps_rel, const KnnHeader *__restrict__ hdr, int32_t *__restrict__ idx_out,
+                  float *__restrict__ dist_out, uint8_t *__restrict__ unsafe) {
+    __shared__ double sd[RR_THREADS / 32][RR_MAXC];
+    __shared__ int32_t si[RR_THREADS / 32][RR_MAXC];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t n = (int64_t)blockIdx.x * (RR_THREADS / 32) + warp;
+    if (n >= N) return;
+    const float *q = Q + n * ldq;
+    double qn = 0.0;
+    for (int c = 0; c < d; ++c) {
+        const double v = (double)q[c];
+        qn = fma(v, v, qn);
+    }
+    double *wd = sd[warp];
+    int32_t *wi = si[warp];
+    for (int e = lane; e < ncand; e += 32) {
+        const int32_t id = cand[n * ncand + e];
+        double dist = INFINITY;
+        if (id >= 0 && id < M) {
+            const float *r = Ref + (int64_t)id * ldr;
+            double rn = 0.0, dot = 0.0;
+            for (int c = 0; c < d; ++c) {
+                const double rv = (double)r[c];
+                rn = fma(rv, rv, rn);
+                dot = fma((double)q[c], rv, dot);
+            }
+            dist = fmax(qn - 2.0 * dot + rn, 0.0);  // sklearn: ||x||^2 - 2 x.y + ||y||^2, clamped
+        }
+        wd[e] = dist;
+        wi[e] = (id >= 0 && id < M) ? id : 0x7fffffff;
+    }
+    __syncwarp();
+    double kth = 0.0;
+    for (int e = lane; e < ncand; e += 32) {
+        const double de = wd[e];
+        const int32_t ie = wi[e];
+        int rank = 0;
+        for (int f = 0; f < ncand; ++f) {
+            const double df = wd[f];
+            rank += (df < de) || (df == de && wi[f] < ie);
+        }
+        if (rank < k) {
+            idx_out[n * k + rank] = ie == 0x7fffffff ? -1 : ie;
+            dist_out[n * k + rank] = (float)de;
+        }
+        if (rank == k - 1) kth = de;
+    }
+    if (unsafe != nullptr) {
+        // certificate: every reference row NOT among the candidates has scan score >= thr (its
+        // split's kc-th best).  With |scan score - exact| <= eps it cannot beat the exact k-th
+        // neighbour if  kth_exact - ||q||^2 + 2 eps < thr.
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) kth = fmax(kth, __shfl_xor_sync(0xffffffffu, kth, o));
+        if (lane == 0) {
+            const double rmax = sqrt((double)hdr->rmax2), qnorm = sqrt(qn);
+            const double eps = eps_rel * (2.0 * qnorm * rmax + (double)hdr->rmax2);
+            double tmin = INFINITY;
+            for (int s = 0; s < nsplit; ++s) tmin = fmin(tmin, (double)thr[n * nsplit + s]);
+            unsafe[n] = (kth - qn + 2.0 * eps < tmin) ? 0 : 1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ vote
+// One thread per query row: label = most frequent code among the k neighbours, ties to the lowest
+// code (sklearn: classes_ sorted, argmax takes the first maximum); conf = votes / k.
+constexpr int VT_KMAX = 128;
+__global__ void __launch_bounds__(128)
+knn_vote_kernel(const int32_t *__restrict__ idx, int64_t N, int k, const int32_t *__restrict__ ref_codes,
+                int32_t *__restrict__ label, float *__restrict__ conf) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    int32_t code[VT_KMAX];
+    for (int j = 0; j < k; ++j) {
+        const int32_t id = idx[n * k + j];
+        code[j] = id >= 0 ? ref_codes[id] : -1;
+    }
+    int best = -1, bestc = 0;
+    for (int j = 0; j < k; ++j) {
+        const int32_t cj = code[j];
+        if (cj < 0) continue;
+        int cnt = 0;
+        for (int l = 0; l < k; ++l) cnt += code[l] == cj;
+        if (cnt > bestc || (cnt == bestc && cj < best)) { bestc = cnt; best = cj; }
+    }
+    label[n] = best;
+    if (conf) conf[n] = (float)bestc / (float)k;
+}
+
+}  // namespace sym
+
+// ============================================================================================
+using namespace sym;
+
+extern "C" size_t sym_knn_packed_bytes(int64_t M, int32_t d) { return knn_packed_layout(nullptr, M, d).total; }
+
+extern "C" int sym_knn_fit(const float *Ref, int32_t ldr, int64_t M, int32_t d, void *packed, sym_stream_t stream) {
+    SYM_REQUIRE(M > 0 && d > 0 && ldr >= d, SYM_ERR_INVALID_ARGUMENT, "sym_knn_fit: bad sizes");
+    SYM_REQUIRE(d <= 128, SYM_ERR_UNSUPPORTED_SHAPE, "sym_knn_fit: d=%d > 128", d);
+    SYM_REQUIRE(M < (1ll << 31) - 256, SYM_ERR_UNSUPPORTED_SHAPE, "sym_knn_fit: M too large");
+    SYM_REQUIRE(((uintptr_t)packed & 255) == 0, SYM_ERR_INVALID_ARGUMENT, "sym_knn_fit: packed must be 256-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    KnnPacked pk = knn_packed_layout(packed, M, d);
+    SYM_CUDA(cudaMemsetAsync(pk.hdr, 0, sizeof(KnnHeader), st));
+    knn_fit_kernel<<<(unsigned)(pk.Mpad / 128), 256, 0, st>>>(Ref, ldr, M, d, pk);
+    SYM_LAUNCH_CHECK("knn_fit_kernel");
+    return knn_tc_fit(Ref, ldr, M, d, pk, st);
+}
+
+namespace {
+struct ScanPlan {
+    int kc, kcap, nsplit, tiles_per_split, top_in_smem;
+    int64_t qtiles;
+    size_t smem, cand_bytes, thr_bytes, top_bytes;
+};
+
+int plan_scan(int64_t N, int64_t M, int d, int k, ScanPlan &p) {
+    const int64_t Mpad = knn_mpad(M);
+    const int d4 = (d + 3) & ~3;
+    int kc = k + 8;
+    if (kc > M) kc = (int)M;
+    p.kc = kc;
+    p.kcap = kc <= 16 ? 16 : kc <= 32 ? 32 : kc <= 64 ? 64 : 128;
+    p.top_in_smem = p.kcap <= 64;
+    p.smem = scan_smem_bytes(d4, p.kcap, p.top_in_smem);
+    p.qtiles = ceil_div(N, SC_BQ);
+    const int ntiles = (int)(Mpad / SC_BR);
+    // split the reference across CTAs only when the query alone cannot fill the GPU
+    int nsplit = 1;
+    if (p.qtiles < 2 * kNumSMs) {
+        nsplit = (int)ceil_div(2 * kNumSMs, p.qtiles);
+        const int by_work = ntiles / 8 > 0 ? ntiles / 8 : 1;   // keep >= 8 tiles per split
+        const int by_rerank = RR_MAXC / kc > 0 ? RR_MAXC / kc : 1;
+        nsplit = nsplit < by_work ? nsplit : by_work;
+        nsplit = nsplit < by_rerank ? nsplit : by_rerank;
+        if (nsplit < 1) nsplit = 1;
+    }
+    p.tiles_per_split = (int)ceil_div(ntiles, nsplit);
+    p.nsplit = (int)ceil_div(ntiles, p.tiles_per_split);
+    p.cand_bytes = ((size_t)N * p.nsplit * kc * sizeof(int32_t) + 255) & ~(size_t)255;
+    p.thr_bytes = ((size_t)N * p.nsplit * sizeof(float) + 255) & ~(size_t)255;
+    p.top_bytes = p.top_in_smem ? 0 : (size_t)p.qtiles * p.nsplit * SC_BQ * p.kcap * 8;
+    return SYM_OK;
+}
+}  // namespace
+
+extern "C" size_t sym_knn_workspace(int64_t N, int64_t M, int32_t d, int32_t k, int32_t method) {
+    if (N <= 0 || M <= 0 || d <= 0 || k <= 0) return 256;
+    ScanPlan p;
+    plan_scan(N, M, d, k, p);
+    size_t ffma = p.cand_bytes + p.thr_bytes + p.top_bytes + 256;
+    size_t tc = knn_tc_workspace(N, M, d, k);
+    (void)method;
+    return ffma > tc ? ffma : tc;
+}
+
+extern "C" int sym_knn(const float *Q, int32_t ldq, int64_t N, const float *Ref, int32_t ldr, int64_t M,
+                       const void *packed, int32_t d, int32_t k, int32_t method, int32_t *idx, float *dist2,
+                       uint8_t *unsafe, void *workspace, size_t workspace_bytes, sym_stream_t stream) {
+    SYM_REQUIRE(N >= 0 && M > 0 && d > 0 && ldq >= d && ldr >= d, SYM_ERR_INVALID_ARGUMENT, "sym_knn: bad sizes");
+    SYM_REQUIRE(k >= 1 && k <= M, SYM_ERR_INVALID_ARGUMENT,
+                "sym_knn: Expected n_neighbors <= n_samples_fit, but n_neighbors = %d, n_samples_fit = %lld", k,
+                (long long)M);
+    SYM_REQUIRE(k <= 120 && d <= 128, SYM_ERR_UNSUPPORTED_SHAPE, "sym_knn: k=%d (<=120) d=%d (<=128) unsupported", k, d);
+    SYM_REQUIRE(method >= 0 && method <= 2, SYM_ERR_INVALID_ARGUMENT, "sym_knn: unknown method %d", method);
+    SYM_REQUIRE(workspace_bytes >= sym_knn_workspace(N, M, d, k, method), SYM_ERR_WORKSPACE_TOO_SMALL,
+                "sym_knn: workspace too small");
+    SYM_REQUIRE(((uintptr_t)workspace & 255) == 0, SYM_ERR_INVALID_ARGUMENT, "sym_knn: workspace must be 256-byte aligned");
+    if (N == 0) return SYM_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    KnnPacked pk = knn_packed_layout(const_cast<void *>(packed), M, d);
+    if (method == 0) method = knn_tc_supported(N, M, d, k) ? 2 : 1;
+
+    int ncand = 0, nsplit = 1;
+    double eps_rel = 0.0;
+    const int32_t *cand = nullptr;
+    const float *thr = nullptr;
+    if (method == 2) {
+        SYM_REQUIRE(knn_tc_supported(N, M, d, k), SYM_ERR_UNSUPPORTED_SHAPE, "sym_knn: tcgen05 scan does not support this shape");
+        int rc = knn_tc_scan(Q, ldq, N, pk, M, d, k, workspace, workspace_bytes, st, &cand, &thr, &ncand, &nsplit, &eps_rel);
+        if (rc != SYM_OK) return rc;
+    } else {
+        ScanPlan p;
+        plan_scan(N, M, d, k, p);
+        unsigned char *w = (unsigned char *)workspace;
+        int32_t *cand_w = (int32_t *)w; w += p.cand_bytes;
+        float *thr_w = (float *)w; w += p.thr_bytes;
+        unsigned long long *top_w = (unsigned long long *)w;
+        SYM_REQUIRE(p.smem <= 227 * 1024, SYM_ERR_UNSUPPORTED_SHAPE, "sym_knn: d=%d k=%d needs %zu B of shared memory", d, k, p.smem);
+        SYM_CUDA(cudaFuncSetAttribute(knn_scan_ffma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+        dim3 grid((unsigned)p.qtiles, (unsigned)p.nsplit);
+        knn_scan_ffma_kernel<<<grid, SC_THREADS, p.smem, st>>>(Q, ldq, N, pk, d, p.kc, p.kcap, p.tiles_per_split,
+                                                               p.top_in_smem, top_w, cand_w, thr_w);
+        SYM_LAUNCH_CHECK("knn_scan_ffma_kernel");
+        cand = cand_w; thr = thr_w; ncand = p.nsplit * p.kc; nsplit = p.nsplit;
+        // FP32 dot product of d terms, accumulated by fmaf, plus the rounding of ||r||^2 and the sum
+        eps_rel = (double)(d + 4) * 5.97e-8;
+    }
+    SYM_REQUIRE(ncand <= RR_MAXC, SYM_ERR_UNSUPPORTED_SHAPE, "sym_knn: internal: %d candidates per row", ncand);
+    knn_rerank_kernel<<<(unsigned)ceil_div(N, RR_THREADS / 32), RR_THREADS, 0, st>>>(
+        Q, ldq, N, Ref, ldr, M, d, k, cand, thr, ncand, nsplit, eps_rel, pk.hdr, idx, dist2, unsafe);
+    SYM_LAUNCH_CHECK("knn_rerank_kernel");
+    return SYM_OK;
+}
+
+extern "C" int sym_vote(const int32_t *idx, int64_t N, int32_t k, const int32_t *ref_codes, int32_t *label,
+                        float *conf, sym_stream_t stream) {
+    SYM_REQUIRE(N >= 0 && k >= 1 && k <= VT_KMAX, SYM_ERR_INVALID_ARGUMENT, "sym_vote: bad sizes (k <= %d)", VT_KMAX);
+    if (N == 0) return SYM_OK;
+    knn_vote_kernel<<<(unsigned)ceil_div(N, 128), 128, 0, (cudaStream_t)stream>>>(idx, N, k, ref_codes, label, conf);
+    SYM_LAUNCH_CHECK("knn_vote_kernel");
+    return SYM_OK;
+}

@@ -1,0 +1,76 @@
+// Shared between the FFMA scan (knn.cu) and the tcgen05 scan (knn_tc.cu).
+#pragma once
+#include "common.cuh"
+
+namespace sym {
+
+struct KnnHeader {
+    float rmax2;       // max ||ref||^2 (written by fit with an integer atomicMax: values are >= 0)
+    int32_t tc_ready;  // 1 once the tensor-core operand section has been packed
+    int32_t pad[62];
+};
+
+// Layout of the opaque "packed reference" buffer produced by sym_knn_fit:
+//   [KnnHeader | norm2 f32[Mpad] | refT f32[d4][Mpad] | tensor-core section]
+struct KnnPacked {
+    KnnHeader *hdr;
+    float *norm2;
+    float *refT;
+    unsigned char *tc;  // tensor-core operand section (layout private to knn_tc.cu)
+    int64_t Mpad;
+    int d4;
+    size_t total;
+};
+
+__host__ __device__ inline int64_t knn_mpad(int64_t M) { return (M + 255) / 256 * 256; }
+
+size_t knn_tc_packed_bytes(int64_t M, int d);
+
+inline KnnPacked knn_packed_layout(void *base, int64_t M, int d) {
+    KnnPacked p;
+    p.Mpad = knn_mpad(M);
+    p.d4 = (d + 3) & ~3;
+    unsigned char *b = (unsigned char *)base;
+    size_t off = 0;
+    p.hdr = (KnnHeader *)(b + off);
+    off += sizeof(KnnHeader);
+    p.norm2 = (float *)(b + off);
+    off += (size_t)p.Mpad * sizeof(float);
+    p.refT = (float *)(b + off);
+    off += (size_t)p.d4 * p.Mpad * sizeof(float);
+    off = (off + 1023) & ~(size_t)1023;
+    p.tc = b + off;
+    off += knn_tc_packed_bytes(M, d);
+    p.total = off;
+    return p;
+}
+
+// Order-preserving map float -> uint32, packed with the reference index: comparing keys compares
+// (score, index) lexicographically, which makes selection independent of arrival order and sends
+// exact distance ties to the lower reference index.
+__host__ __device__ __forceinline__ unsigned long long knn_make_key(float s, uint32_t idx) {
+#ifdef __CUDA_ARCH__
+    uint32_t u = __float_as_uint(s);
+#else
+    uint32_t u;
+    memcpy(&u, &s, 4);
+#endif
+    u ^= (u & 0x80000000u) ? 0xffffffffu : 0x80000000u;
+    return ((unsigned long long)u << 32) | idx;
+}
+__device__ __forceinline__ float knn_key_score(unsigned long long key) {
+    if (key == ~0ull) return INFINITY;  // empty slot
+    uint32_t u = (uint32_t)(key >> 32);
+    u ^= (u & 0x80000000u) ? 0x80000000u : 0xffffffffu;
+    return __uint_as_float(u);
+}
+
+// tcgen05 scan entry points (knn_tc.cu)
+bool knn_tc_supported(int64_t N, int64_t M, int d, int k);
+size_t knn_tc_workspace(int64_t N, int64_t M, int d, int k);
+int knn_tc_fit(const float *Ref, int ldr, int64_t M, int d, KnnPacked pk, cudaStream_t st);
+int knn_tc_scan(const float *Q, int ldq, int64_t N, KnnPacked pk, int64_t M, int d, int k, void *workspace,
+                size_t workspace_bytes, cudaStream_t st, const int32_t **cand, const float **thr, int *ncand,
+                int *nsplit, double *eps_rel);
+
+}  // namespace sym

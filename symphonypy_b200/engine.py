@@ -1,0 +1,271 @@
+"""Device-side pipeline: torch tensors in HBM -> C-ABI kernels -> torch tensors in HBM.
+
+PyTorch is used for device memory, streams and (in `_dist.py`) the NCCL
+all-reduce; every arithmetic step of the hot path is a call into
+`libsymphony_b200.so`.  All functions take CUDA tensors and run on the current
+torch stream of the tensor's device.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _lib
+
+CLIP = 10.0  # `symphonypy/_utils.py:253`: max_value, fixed by the reference API
+KNN_AUTO, KNN_FFMA, KNN_TCGEN05 = 0, 1, 2
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
+
+
+def require_cuda(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise _lib.SymphonyLibraryError(
+            "symphonypy_b200 needs a CUDA device (B200, sm_100a); there is no CPU path.")
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+# ------------------------------------------------------------------------------------- project
+@dataclass
+class Loadings:
+    """Replicated reference-side operands of the projection (device resident)."""
+
+    mu: torch.Tensor       # [G] f32
+    inv_sd: torch.Tensor   # [G] f32, 0 for genes that contribute nothing
+    U: torch.Tensor        # [G, ldu] f32, zero padded, ldu % 4 == 0
+    d: int
+    z0: torch.Tensor | None = None  # CSR bias, filled lazily
+
+    @property
+    def G(self) -> int:
+        return self.mu.shape[0]
+
+
+def make_loadings(mean, std, U, present, device) -> Loadings:
+    """mean/std/U: host arrays over the G reference genes in use; present: bool [G]
+    (`_utils.py:276`: in the query and std != 0)."""
+    mean = np.asarray(mean, dtype=np.float64)
+    std = np.asarray(std, dtype=np.float64)
+    ok = np.asarray(present, dtype=bool) & (std != 0)
+    inv = np.zeros_like(std)
+    inv[ok] = 1.0 / std[ok]
+    U = np.asarray(U, dtype=np.float32)
+    G, d = U.shape
+    ldu = (d + 3) // 4 * 4
+    Up = np.zeros((G, ldu), dtype=np.float32)
+    Up[:, :d] = U
+    return Loadings(mu=torch.from_numpy(np.where(ok, mean, 0.0).astype(np.float32)).to(device),
+                    inv_sd=torch.from_numpy(inv.astype(np.float32)).to(device),
+                    U=torch.from_numpy(Up).to(device), d=d)
+
+
+def project_dense(X: torch.Tensor, ld: Loadings, gene_col: torch.Tensor | None = None,
+                  out: torch.Tensor | None = None) -> torch.Tensor:
+    """Z = clip((X[:, col] - mu) * inv_sd, +-10) @ U   (`_utils.py:298-308`)."""
+    lib = _lib.load()
+    assert X.is_cuda and X.dim() == 2 and X.dtype == torch.float32 and X.stride(1) == 1
+    N = X.shape[0]
+    if gene_col is None:
+        assert X.shape[1] >= ld.G
+    Z = out if out is not None else torch.empty((N, ld.d), device=X.device, dtype=torch.float32)
+    _lib.check(lib.sym_project_dense(X.data_ptr(), N, X.stride(0), _ptr(gene_col), ld.G, ld.mu.data_ptr(),
+                                     ld.inv_sd.data_ptr(), ld.U.data_ptr(), ld.U.stride(0), ld.d, CLIP,
+                                     Z.data_ptr(), Z.stride(0), _stream(X.device)), "sym_project_dense")
+    return Z
+
+
+def project_csr(data: torch.Tensor, indices: torch.Tensor, indptr: torch.Tensor, N: int, col_gene: torch.Tensor,
+                ld: Loadings, out: torch.Tensor | None = None) -> torch.Tensor:
+    """CSR form of the same projection; the dense matrix of `_utils.py:240-243` is never built."""
+    lib = _lib.load()
+    dev = data.device
+    assert data.dtype == torch.float32 and indices.dtype == torch.int32 and indptr.dtype == torch.int64
+    if ld.z0 is None:
+        ld.z0 = torch.empty(ld.d, device=dev, dtype=torch.float32)
+        _lib.check(lib.sym_project_csr_bias(ld.mu.data_ptr(), ld.inv_sd.data_ptr(), ld.U.data_ptr(), ld.U.stride(0),
+                                            ld.G, ld.d, CLIP, ld.z0.data_ptr(), _stream(dev)), "sym_project_csr_bias")
+    Z = out if out is not None else torch.empty((N, ld.d), device=dev, dtype=torch.float32)
+    _lib.check(lib.sym_project_csr(data.data_ptr(), indices.data_ptr(), indptr.data_ptr(), N, col_gene.data_ptr(),
+                                   ld.mu.data_ptr(), ld.inv_sd.data_ptr(), ld.U.data_ptr(), ld.U.stride(0), ld.d,
+                                   CLIP, ld.z0.data_ptr(), Z.data_ptr(), Z.stride(0), _stream(dev)), "sym_project_csr")
+    return Z
+
+
+# ------------------------------------------------------------------------------------- assign
+def assign(Z: torch.Tensor, Y: torch.Tensor, inv_sigma: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """R [N, K] = softmax_k(-2 (1 - cos(z, Y_k)) / sigma_k)   (`_utils.py:154-178`)."""
+    lib = _lib.load()
+    N, d = Z.shape
+    K = Y.shape[0]
+    assert Y.shape[1] == d and Y.is_contiguous() and inv_sigma.numel() == K and Z.stride(1) == 1
+    R = out if out is not None else torch.empty((N, K), device=Z.device, dtype=torch.float32)
+    _lib.check(lib.sym_assign(Z.data_ptr(), Z.stride(0), N, d, Y.data_ptr(), K, inv_sigma.data_ptr(), R.data_ptr(),
+                              _stream(Z.device)), "sym_assign")
+    return R
+
+
+# ------------------------------------------------------------------------------------- MoE
+@dataclass
+class BatchOrder:
+    perm: torch.Tensor | None
+    seg: torch.Tensor | None
+    chunk_start: torch.Tensor | None
+
+
+def batch_order(codes_v: torch.Tensor, n_levels: int) -> BatchOrder:
+    """Counting sort of the cells by level of one batch variable (None when it has one level)."""
+    if n_levels == 1:
+        return BatchOrder(None, None, None)
+    lib = _lib.load()
+    dev = codes_v.device
+    N = codes_v.shape[0]
+    perm = torch.empty(N, device=dev, dtype=torch.int32)
+    seg = torch.empty(n_levels + 1, device=dev, dtype=torch.int64)
+    chunk_start = torch.empty(n_levels + 1, device=dev, dtype=torch.int32)
+    ws_bytes = int(lib.sym_batch_order_workspace(n_levels))
+    ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+    _lib.check(lib.sym_batch_order(codes_v.data_ptr(), N, n_levels, perm.data_ptr(), seg.data_ptr(),
+                                   chunk_start.data_ptr(), ws.data_ptr(), ws_bytes, _stream(dev)), "sym_batch_order")
+    return BatchOrder(perm, seg, chunk_start)
+
+
+def moe_stats(Z, R, codes, levels, orders):
+    """Sufficient statistics gram [K,B1,B1], cross [K,B1,d] (float64) of `_utils.py:196-204`,
+    WITHOUT the priors Nr / C and without the intercept row (both added by `moe_solve`)."""
+    lib = _lib.load()
+    dev = Z.device
+    N, d = Z.shape
+    K = R.shape[1]
+    V = len(levels)
+    B1 = 1 + int(sum(levels))
+    offs = np.concatenate([[0], np.cumsum(levels)[:-1]]).astype(np.int32)
+    gram = torch.zeros((K, B1, B1), device=dev, dtype=torch.float64)
+    cross = torch.zeros((K, B1, d), device=dev, dtype=torch.float64)
+    assert codes.dtype == torch.int32 and codes.shape == (V, N) and codes.is_contiguous()
+    for v in range(V):
+        o = orders[v]
+        _lib.check(lib.sym_moe_stats(Z.data_ptr(), Z.stride(0), R.data_ptr(), N, d, K, codes.data_ptr(), V,
+                                     offs.ctypes.data, v, int(levels[v]), _ptr(o.perm), _ptr(o.seg),
+                                     _ptr(o.chunk_start), B1, gram.data_ptr(), cross.data_ptr(), _stream(dev)),
+                   "sym_moe_stats")
+    return gram, cross
+
+
+def moe_solve(gram, cross, Nr, C, lamb_diag, n_levels_var0):
+    """W [K,B1,d] f32 = inv(gram + prior + diag(lamb)) @ (cross + prior), row 0 zeroed (`_utils.py:201-209`)."""
+    lib = _lib.load()
+    dev = gram.device
+    K, B1, _ = gram.shape
+    d = cross.shape[2]
+    W = torch.empty((K, B1, d), device=dev, dtype=torch.float32)
+    info = torch.empty(K, device=dev, dtype=torch.int32)
+    _lib.check(lib.sym_moe_solve(gram.data_ptr(), cross.data_ptr(), Nr.data_ptr(), C.data_ptr(), lamb_diag.data_ptr(),
+                                 K, B1, d, int(n_levels_var0), W.data_ptr(), info.data_ptr(), _stream(dev)),
+               "sym_moe_solve")
+    return W, info
+
+
+def moe_apply(Z, R, codes, levels, orders, W, out=None):
+    """Zcorr = Z - sum_k R_k W_k^T Phi   (`_utils.py:212`), one pass per batch variable."""
+    lib = _lib.load()
+    dev = Z.device
+    N, d = Z.shape
+    K = R.shape[1]
+    B1 = W.shape[1]
+    Zc = out if out is not None else torch.empty_like(Z)
+    src = Z
+    off = 0
+    for v, lv in enumerate(levels):
+        o = orders[v]
+        _lib.check(lib.sym_moe_apply(src.data_ptr(), src.stride(0), R.data_ptr(), N, d, K, codes[v].data_ptr(), off,
+                                     int(lv), _ptr(o.perm), _ptr(o.seg), _ptr(o.chunk_start), W.data_ptr(), B1,
+                                     Zc.data_ptr(), Zc.stride(0), _stream(dev)), "sym_moe_apply")
+        src = Zc
+        off += int(lv)
+    return Zc
+
+
+# ------------------------------------------------------------------------------------- kNN
+@dataclass
+class KnnIndex:
+    """`KNeighborsClassifier.fit` result: the reference embedding, packed for the scan kernels."""
+
+    ref: torch.Tensor      # [M, d] f32
+    packed: torch.Tensor   # opaque bytes
+    M: int
+    d: int
+    workspace: dict = field(default_factory=dict)
+
+
+def knn_fit(ref: torch.Tensor) -> KnnIndex:
+    lib = _lib.load()
+    ref = _f32c(ref)
+    M, d = ref.shape
+    nbytes = int(lib.sym_knn_packed_bytes(M, d))
+    packed = torch.empty(nbytes, device=ref.device, dtype=torch.uint8)
+    assert packed.data_ptr() % 256 == 0
+    _lib.check(lib.sym_knn_fit(ref.data_ptr(), ref.stride(0), M, d, packed.data_ptr(), _stream(ref.device)),
+               "sym_knn_fit")
+    return KnnIndex(ref=ref, packed=packed, M=M, d=d)
+
+
+def knn_search(index: KnnIndex, Q: torch.Tensor, k: int, method: int = KNN_AUTO, want_unsafe: bool = True):
+    """idx [N,k] int32 (ascending by (distance, index)), dist2 [N,k] f32, unsafe [N] uint8 | None."""
+    lib = _lib.load()
+    Q = _f32c(Q)
+    N, d = Q.shape
+    assert d == index.d, f"query has {d} dims, reference has {index.d}"
+    dev = Q.device
+    idx = torch.empty((N, k), device=dev, dtype=torch.int32)
+    dist2 = torch.empty((N, k), device=dev, dtype=torch.float32)
+    unsafe = torch.empty(N, device=dev, dtype=torch.uint8) if want_unsafe else None
+    ws_bytes = int(lib.sym_knn_workspace(N, index.M, d, k, method))
+    key = "ws"
+    ws = index.workspace.get(key)
+    if ws is None or ws.numel() < ws_bytes or ws.device != dev:
+        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        index.workspace[key] = ws
+    _lib.check(lib.sym_knn(Q.data_ptr(), Q.stride(0), N, index.ref.data_ptr(), index.ref.stride(0), index.M,
+                           index.packed.data_ptr(), d, k, method, idx.data_ptr(), dist2.data_ptr(), _ptr(unsafe),
+                           ws.data_ptr(), ws.numel(), _stream(dev)), "sym_knn")
+    return idx, dist2, unsafe
+
+
+def knn_search_certified(index: KnnIndex, Q: torch.Tensor, k: int, method: int = KNN_AUTO):
+    """`knn_search` plus the repair pass: rows whose over-selection margin could not be certified
+    (possible with the reduced-precision tensor-core scan, or with many exactly tied neighbours) are
+    re-run with the FP32 FFMA scan.  Returns (idx, dist2, n_repaired)."""
+    idx, dist2, unsafe = knn_search(index, Q, k, method)
+    n_bad = int(unsafe.sum().item())
+    if n_bad:
+        rows = torch.nonzero(unsafe, as_tuple=False).flatten()
+        i2, d2, _ = knn_search(index, Q[rows].contiguous(), k, KNN_FFMA)
+        idx[rows] = i2
+        dist2[rows] = d2
+    return idx, dist2, n_bad
+
+
+def vote(idx: torch.Tensor, ref_codes: torch.Tensor, want_conf: bool = True):
+    """Majority vote with sklearn's tie rule (lowest class code); conf = winning fraction."""
+    lib = _lib.load()
+    N, k = idx.shape
+    dev = idx.device
+    label = torch.empty(N, device=dev, dtype=torch.int32)
+    conf = torch.empty(N, device=dev, dtype=torch.float32) if want_conf else None
+    assert ref_codes.dtype == torch.int32 and idx.is_contiguous()
+    _lib.check(lib.sym_vote(idx.data_ptr(), N, k, ref_codes.data_ptr(), label.data_ptr(), _ptr(conf), _stream(dev)),
+               "sym_vote")
+    return label, conf

@@ -1,0 +1,420 @@
+"""Drop-in `tl` namespace: `map_embedding` and `transfer_labels_kNN` on B200.
+
+Mirrors `symphonypy/tl.py:271-436` — same signatures, defaults, `obsm` / `obs` keys,
+assertion messages, warnings and logger name — with the numerics of
+`symphonypy/_utils.py:154-308` and scikit-learn's brute-force `KNeighborsClassifier`
+replaced by the CUDA kernels behind `include/symphony_b200.h`.
+
+Differences a user can observe (all documented in DESIGN.md):
+  * arrays written to `obsm` are float32 (the kernels compute in FP32; tolerance 1e-4
+    relative against the reference's float64);
+  * the no-Harmony fallback (`tl.py:320-335`, reference *building*) is out of scope and
+    raises `NotImplementedError`;
+  * kNN options that change the arithmetic (non-Euclidean metric, non-uniform weights)
+    raise `NotImplementedError` — there is no CPU fallback;
+  * opt-in extras (keyword only): `confidence_key=` / `neighbors_key=` on
+    `transfer_labels_kNN`;
+  * under `torch.distributed` (one process per GPU) every rank passes its own shard of
+    the query; the MoE statistics are all-reduced so results equal the single-process run.
+"""
+from __future__ import annotations
+
+import logging
+import numbers
+import warnings
+import weakref
+from collections import OrderedDict
+
+import numpy as np
+import pandas as pd
+import torch
+from scipy.sparse import issparse
+
+from . import _design, _dist, engine
+
+logger = logging.getLogger("symphonypy")
+
+
+class settings:
+    """Process-wide knobs of the B200 backend."""
+
+    device = None                  # torch device; default: current CUDA device (LOCAL_RANK under torchrun)
+    h2d_chunk_bytes = 256 << 20    # rows of X are streamed to the GPU in chunks of about this size
+    knn_method = engine.KNN_AUTO   # 0 auto, 1 FP32 FFMA scan, 2 tcgen05 scan
+    keep_on_device = True          # remember device copies of the arrays written to obsm
+    store_R = True                 # write obsm[f"{basis}_symphony_R"] (N x K) as the reference does
+
+
+# ----------------------------------------------------------------------------- device caches
+_DEV_CACHE: "OrderedDict[int, tuple]" = OrderedDict()   # id(ndarray) -> (weakref, cuda tensor)
+_REF_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
+
+
+def _remember(arr: np.ndarray, t: torch.Tensor) -> None:
+    if not settings.keep_on_device:
+        return
+    key = id(arr)
+    _DEV_CACHE[key] = (weakref.ref(arr, lambda _r, k=key: _DEV_CACHE.pop(k, None)), t)
+    while len(_DEV_CACHE) > 8:
+        _DEV_CACHE.popitem(last=False)
+
+
+def _device_copy(arr, dev) -> torch.Tensor:
+    """Device float32 copy of an obsm entry (cache hit when this module wrote it)."""
+    if isinstance(arr, torch.Tensor):
+        return arr.to(dev, torch.float32)
+    hit = _DEV_CACHE.get(id(arr))
+    if hit is not None and hit[0]() is arr and hit[1].device == dev:
+        return hit[1]
+    a = np.ascontiguousarray(np.asarray(arr))
+    return torch.from_numpy(a).to(dev).float()
+
+
+def _cached(key, owner, build):
+    hit = _REF_CACHE.get(key)
+    if hit is not None and hit[0]() is owner:
+        _REF_CACHE.move_to_end(key)
+        return hit[1]
+    val = build()
+    try:
+        ref = weakref.ref(owner)
+    except TypeError:
+        return val
+    _REF_CACHE[key] = (ref, val)
+    while len(_REF_CACHE) > 8:
+        _REF_CACHE.popitem(last=False)
+    return val
+
+
+def clear_caches() -> None:
+    _DEV_CACHE.clear()
+    _REF_CACHE.clear()
+
+
+# ----------------------------------------------------------------------------- project
+_PIN_BUFS: dict = {}
+
+
+def _pinned_stage(nbytes: int, slot: int) -> torch.Tensor:
+    buf = _PIN_BUFS.get(slot)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        _PIN_BUFS[slot] = buf
+    return buf
+
+
+def _project_host_dense(Xh: torch.Tensor, ld: engine.Loadings, gene_col, Z: torch.Tensor) -> None:
+    """Stream a host matrix through the GPU: H2D of chunk i+1 overlaps the projection of chunk i."""
+    dev = Z.device
+    N, C = Xh.shape
+    if N == 0:
+        return
+    row_bytes = C * Xh.element_size()
+    rows = int(max(1, min(N, settings.h2d_chunk_bytes // max(1, row_bytes))))
+    pinned = Xh.is_pinned()
+    compute = torch.cuda.current_stream(dev)
+    copy = torch.cuda.Stream(dev)
+    bufs = [torch.empty((rows, C), dtype=Xh.dtype, device=dev) for _ in range(2 if N > rows else 1)]
+    ready = [torch.cuda.Event() for _ in bufs]
+    free = [torch.cuda.Event() for _ in bufs]
+    copy.wait_stream(compute)
+    for i, s in enumerate(range(0, N, rows)):
+        b = i % len(bufs)
+        e = min(N, s + rows)
+        src = Xh[s:e]
+        with torch.cuda.stream(copy):
+            if i >= len(bufs):
+                copy.wait_event(free[b])
+            if not pinned:
+                if i >= len(bufs):
+                    ready[b].synchronize()  # the previous H2D out of this staging buffer has finished
+                stage = _pinned_stage(rows * row_bytes, b)[: (e - s) * row_bytes].view(Xh.dtype).view(e - s, C)
+                stage.copy_(src)
+                src = stage
+            bufs[b][: e - s].copy_(src, non_blocking=True)
+            ready[b].record(copy)
+        compute.wait_event(ready[b])
+        xb = bufs[b][: e - s]
+        if xb.dtype != torch.float32:
+            xb = xb.float()
+        engine.project_dense(xb, ld, gene_col, out=Z[s:e])
+        free[b].record(compute)
+
+
+def _project(adata_query, adata_ref, loadings_key, use_genes_column, dev) -> torch.Tensor:
+    """`_map_query_to_ref` (`_utils.py:248-308`): returns Z [N, d] on the device."""
+    assert "mean" in adata_ref.var, "Gene expression means are expected to be saved in adata_ref.var"
+    assert "std" in adata_ref.var, "Gene expression stds are expected to be saved in adata_ref.var"
+    if use_genes_column is None:
+        hv = None
+        genes = adata_ref.var_names
+        stds = np.array(adata_ref.var["std"])
+    else:
+        hv = np.asarray(adata_ref.var[use_genes_column]).astype(bool)
+        genes = adata_ref.var_names[hv]
+        stds = np.array(adata_ref.var["std"])[hv]
+    q_names = adata_query.var_names
+    q_idx = q_names.get_indexer(genes)
+    present = (q_idx >= 0) & (stds != 0)  # `_utils.py:276`
+    if not present.all():  # same message as `_utils.py:233-239`
+        logger.warning(
+            "%i out of %i genes from the reference are missing in the query dataset or have zero std in the reference, "
+            "their expressions in the query will be set to zero", int((~present).sum()), genes.shape[0])
+
+    def build():
+        means = np.array(adata_ref.var["mean"]) if hv is None else np.array(adata_ref.var["mean"])[hv]
+        pcs = np.asarray(adata_ref.varm[loadings_key])
+        U = pcs if hv is None else pcs[np.asarray(adata_ref.var_names.isin(genes))]  # `_utils.py:307`
+        return engine.make_loadings(means, stds, U, present, dev)
+
+    ld = _cached(("loadings", id(adata_ref), loadings_key, use_genes_column, str(dev), present.tobytes()),
+                 adata_ref, build)
+    G = ld.G
+    X = adata_query.X
+    N = X.shape[0]
+    Z = torch.empty((N, ld.d), device=dev, dtype=torch.float32)
+    identity = bool((q_idx == np.arange(G)).all())
+
+    if issparse(X):
+        Xc = X.tocsr()
+        if not Xc.has_canonical_format:
+            Xc = Xc.copy()
+            Xc.sum_duplicates()
+        col_gene = np.full(X.shape[1], -1, dtype=np.int32)
+        ok = q_idx >= 0
+        col_gene[q_idx[ok]] = np.arange(G, dtype=np.int32)[ok]
+        data = torch.from_numpy(np.ascontiguousarray(Xc.data)).to(dev, non_blocking=True).float()
+        indices = torch.from_numpy(np.ascontiguousarray(Xc.indices)).to(dev, non_blocking=True).int()
+        indptr = torch.from_numpy(np.ascontiguousarray(Xc.indptr)).to(dev, non_blocking=True).long()
+        engine.project_csr(data, indices, indptr, N, torch.from_numpy(col_gene).to(dev), ld, out=Z)
+        return Z
+
+    gene_col = None if identity else torch.from_numpy(q_idx.astype(np.int32)).to(dev)
+    if isinstance(X, torch.Tensor):
+        if X.is_cuda:
+            xd = X if (X.dtype == torch.float32 and X.stride(1) == 1) else X.float().contiguous()
+            engine.project_dense(xd, ld, gene_col, out=Z)
+            return Z
+        Xh = X if X.is_contiguous() else X.contiguous()
+    else:
+        Xn = np.asarray(X)
+        if not Xn.flags.c_contiguous:
+            Xn = np.ascontiguousarray(Xn)
+        if not Xn.flags.writeable:  # torch.from_numpy warns on read-only memory; we never write to it
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                Xh = torch.from_numpy(Xn)
+        else:
+            Xh = torch.from_numpy(Xn)
+    _project_host_dense(Xh, ld, gene_col, Z)
+    return Z
+
+
+# ----------------------------------------------------------------------------- map_embedding
+def _inv_sigma(sigma, K: int, dev) -> torch.Tensor:
+    """`_utils.py:158-164`: sigma is cast to float32 first (so 0.1 is float32(0.1))."""
+    if np.ndim(sigma) == 0:
+        s = np.full(K, np.float32(sigma), dtype=np.float32)
+    else:
+        s = np.array(sigma, dtype=np.float32)
+        assert len(s) == K, \
+            "sigma paramater must be either a single float or an array of length equal to number of clusters"
+    return torch.from_numpy((1.0 / s.astype(np.float64)).astype(np.float32)).to(dev)
+
+
+def _to_host(t: torch.Tensor) -> np.ndarray:
+    out = torch.empty(t.shape, dtype=t.dtype, device="cpu")
+    out.copy_(t)  # D2H on the current stream, synchronous for pageable destinations
+    return out.numpy()
+
+
+def map_embedding(
+    adata_query,
+    adata_ref,
+    key: list[str] | str | None = None,
+    lamb: float | np.ndarray | None = None,
+    sigma: float | np.ndarray = 0.1,
+    use_genes_column: str | None = "highly_variable",
+    transferred_adjusted_basis: str = "X_pca_harmony",
+    transferred_primary_basis: str = "X_pca_reference",
+    ref_basis_loadings: str = "PCs",
+    K: int | None = None,
+    reference_primary_basis: str = "X_pca",
+) -> None:
+    """Symphony query mapping (`symphonypy/tl.py:271-397`) on the GPU.
+
+    Writes `adata_query.obsm[transferred_primary_basis]` (projection onto the reference PCs),
+    `obsm[transferred_adjusted_basis]` (after the mixture-of-experts correction) and
+    `obsm[transferred_adjusted_basis + "_symphony_R"]` (soft cluster memberships, N x K).
+
+    `sigma` is the soft-assignment temperature and `lamb` the ridge penalty per batch level
+    (the reference's docstring swaps the two descriptions, `tl.py:295-298`; the behaviour is kept).
+    """
+    assert "mean" in adata_ref.var, "Gene expression means are expected to be saved in adata_ref.var"
+    assert "std" in adata_ref.var, "Gene expression stds are expected to be saved in adata_ref.var"
+    if "harmony" not in adata_ref.uns:
+        raise NotImplementedError(
+            "adata_ref.uns['harmony'] not found. The k-means fallback of symphonypy (tl.py:320-335) builds a "
+            "reference and is outside this package's scope: run symphonypy.pp.harmony_integrate (or "
+            "symphonypy's own map_embedding once) on the reference first.")
+    if use_genes_column is not None:
+        assert use_genes_column in adata_ref.var, \
+            f"Column `{use_genes_column}` not found in adata_ref.var. Set `use_genes_column` parameter properly"
+    if "log1p" not in adata_query.uns:
+        warnings.warn("Gene expressions in adata_query should be log1p-transformed")
+
+    dev = engine.require_cuda(settings.device)
+    harmony_ref = adata_ref.uns["harmony"]
+    ref_basis_loadings = harmony_ref["ref_basis_loadings"]  # `tl.py:347` overrides the keyword
+
+    with torch.cuda.device(dev):
+        # 1. project
+        Z = _project(adata_query, adata_ref, ref_basis_loadings, use_genes_column, dev)
+        N, d = Z.shape
+
+        # 2. soft assignment against the reference centroids
+        Kc = int(harmony_ref["K"])
+        Cn = np.asarray(harmony_ref["C"], dtype=np.float64)
+        Y = Cn / np.linalg.norm(Cn, ord=2, axis=1, keepdims=True)  # `tl.py:361-362`
+        inv_sig = _inv_sigma(sigma, Kc, dev)
+        Yd = torch.from_numpy(np.ascontiguousarray(Y, dtype=np.float32)).to(dev)
+        assert Yd.shape == (Kc, d), "harmony C must be [K, n_components]"
+        R = engine.assign(Z, Yd, inv_sig)
+
+        # 3. mixture-of-experts correction
+        codes_h, levels = _design.batch_codes(adata_query, key)
+        n_levels = [len(lv) for lv in levels]
+        lam = _design.ridge_diagonal(lamb, n_levels)
+        codes = torch.from_numpy(codes_h).to(dev)
+        orders = [engine.batch_order(codes[v], n_levels[v]) for v in range(len(n_levels))]
+        gram, cross = engine.moe_stats(Z, R, codes, n_levels, orders)
+        _dist.allreduce_stats(gram, cross)  # the only cross-GPU exchange of the path
+        Nr = torch.from_numpy(np.ascontiguousarray(harmony_ref["Nr"], dtype=np.float64)).to(dev)
+        Cd = torch.from_numpy(np.ascontiguousarray(Cn)).to(dev)
+        W, info = engine.moe_solve(gram, cross, Nr, Cd, torch.from_numpy(lam).to(dev), n_levels[0])
+        Zc = engine.moe_apply(Z, R, codes, n_levels, orders, W)
+        if int(info.abs().max().item()) != 0:
+            raise np.linalg.LinAlgError("Singular matrix")  # what `np.linalg.inv` raises at `_utils.py:208`
+
+        # 4. results back into the AnnData, as the reference does (`tl.py:394-397`, `_utils.py:306`)
+        z_h, zc_h = _to_host(Z), _to_host(Zc)
+        adata_query.obsm[transferred_primary_basis] = z_h
+        adata_query.obsm[transferred_adjusted_basis] = zc_h
+        _remember(z_h, Z)
+        _remember(zc_h, Zc)
+        if settings.store_R:
+            r_h = _to_host(R)
+            adata_query.obsm[f"{transferred_adjusted_basis}_symphony_R"] = r_h
+            _remember(r_h, R)
+
+
+# ----------------------------------------------------------------------------- kNN transfer
+_KNN_DEFAULTS = dict(n_neighbors=5, weights="uniform", algorithm="auto", leaf_size=30, p=2, metric="minkowski",
+                     metric_params=None, n_jobs=None)
+_KNN_ORDER = list(_KNN_DEFAULTS)
+
+
+def _knn_params(args, kwargs) -> dict:
+    """Accepts the `KNeighborsClassifier(*args, **kwargs)` surface of `tl.py:425` and rejects what the
+    kernels do not implement instead of silently computing something else."""
+    if len(args) > 1:
+        # sklearn's estimator takes n_neighbors positionally and everything else by keyword
+        raise TypeError(f"KNeighborsClassifier.__init__() takes from 1 to 2 positional arguments but "
+                        f"{len(args) + 1} were given")
+    p = dict(_KNN_DEFAULTS)
+    if args:
+        p["n_neighbors"] = args[0]
+    for k, v in kwargs.items():
+        if k not in p:
+            raise TypeError(f"KNeighborsClassifier.__init__() got an unexpected keyword argument '{k}'")
+        p[k] = v
+    k = p["n_neighbors"]
+    if not isinstance(k, numbers.Integral) or isinstance(k, bool) or k < 1:
+        raise ValueError(f"The 'n_neighbors' parameter of KNeighborsClassifier must be an int in the range "
+                         f"[1, inf) or None. Got {k!r} instead.")
+    if p["weights"] not in ("uniform", None):
+        raise NotImplementedError("symphonypy_b200 implements weights='uniform' only (no CPU fallback)")
+    if p["algorithm"] not in ("auto", "brute", "kd_tree", "ball_tree"):
+        raise ValueError(f"The 'algorithm' parameter of KNeighborsClassifier must be a str among "
+                         f"{{'auto', 'ball_tree', 'brute', 'kd_tree'}}. Got {p['algorithm']!r} instead.")
+    metric, pw = p["metric"], p["p"]
+    euclid = metric in ("euclidean", "l2") or (metric == "minkowski" and pw == 2)
+    if not euclid or p["metric_params"] is not None:
+        raise NotImplementedError("symphonypy_b200 implements the Euclidean metric only (no CPU fallback)")
+    return p
+
+
+def _label_columns(adata_ref, ref_labels):
+    y = adata_ref.obs[ref_labels]
+    if isinstance(y, pd.DataFrame):
+        cols = [np.asarray(y[c]) for c in y.columns]
+        two_d = True
+    else:
+        cols = [np.asarray(y)]
+        two_d = False
+    return cols, two_d
+
+
+def transfer_labels_kNN(
+    adata_query,
+    adata_ref,
+    ref_labels: list[str] | str,
+    *kNN_args,
+    query_labels: list[str] | str | None = None,
+    ref_basis: str = "X_pca_harmony",
+    query_basis: str = "X_pca_harmony",
+    confidence_key: list[str] | str | None = None,
+    neighbors_key: str | None = None,
+    **kNN_kwargs,
+) -> None:
+    """kNN label transfer (`symphonypy/tl.py:400-436`) on the GPU.
+
+    `*kNN_args` / `**kNN_kwargs` are the `sklearn.neighbors.KNeighborsClassifier` arguments the
+    reference forwards (`tl.py:425`); brute-force Euclidean search with a uniform vote is what every
+    accepted combination computes (sklearn picks brute force itself for d > 15).  Ties in the vote go
+    to the lowest label in sorted order, distance ties to the lower reference index.
+
+    Extras (not in the reference, off by default): `confidence_key` names `obs` column(s) that receive
+    the winning vote fraction (`predict_proba(...).max(1)`, the TODO at `tl.py:432`); `neighbors_key`
+    stores neighbour indices / squared distances in `obsm[key + "_indices" / "_sqdist"]`.
+    """
+    params = _knn_params(kNN_args, kNN_kwargs)
+    k = int(params["n_neighbors"])
+    dev = engine.require_cuda(settings.device)
+    ref_emb = adata_ref.obsm[ref_basis]
+    label_cols, two_d = _label_columns(adata_ref, ref_labels)
+    M = ref_emb.shape[0]
+    if k > M:  # sklearn's message at kneighbors()
+        raise ValueError(f"Expected n_neighbors <= n_samples_fit, but n_neighbors = {k}, n_samples_fit = {M}, "
+                         f"n_samples = {adata_query.obsm[query_basis].shape[0]}")
+    if query_labels is None:
+        query_labels = ref_labels
+
+    with torch.cuda.device(dev):
+        index = _cached(("knn", id(ref_emb), str(dev)), ref_emb if not isinstance(ref_emb, torch.Tensor) else adata_ref,
+                        lambda: engine.knn_fit(_device_copy(ref_emb, dev)))
+        Q = _device_copy(adata_query.obsm[query_basis], dev)
+        idx, dist2, n_repaired = engine.knn_search_certified(index, Q, k, settings.knn_method)
+        if n_repaired:
+            logger.debug("kNN: %d query rows re-run with the FP32 scan", n_repaired)
+        preds, confs = [], []
+        for col in label_cols:
+            classes, inv = np.unique(col, return_inverse=True)  # sklearn: classes_ = sorted unique labels
+            codes = torch.from_numpy(inv.astype(np.int32)).to(dev)
+            lab, conf = engine.vote(idx, codes, want_conf=confidence_key is not None)
+            preds.append(classes[lab.cpu().numpy()])
+            if conf is not None:
+                confs.append(conf.cpu().numpy())
+        if neighbors_key is not None:
+            adata_query.obsm[neighbors_key + "_indices"] = idx.cpu().numpy()
+            adata_query.obsm[neighbors_key + "_sqdist"] = dist2.cpu().numpy()
+
+    labels_pred = np.stack(preds, axis=1) if two_d and len(preds) > 1 else preds[0]
+    if isinstance(query_labels, list) and len(query_labels) == 1:  # `tl.py:434-435`
+        labels_pred = labels_pred.reshape(labels_pred.shape[0], 1)
+    adata_query.obs[query_labels] = labels_pred
+    if confidence_key is not None:
+        keys = [confidence_key] if isinstance(confidence_key, str) else list(confidence_key)
+        assert len(keys) == len(confs), "confidence_key needs one name per label column"
+        for kname, c in zip(keys, confs):
+            adata_query.obs[kname] = c

@@ -1,0 +1,132 @@
+"""CPU tests of the host-side mirror of the reference interface (no kernels involved)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import symphony_oracle as so
+from symphonypy_b200 import _design, _lib, synth, tl
+from symphonypy_b200.anndata_lite import AnnDataLite
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _query_with_obs(n=200, seed=0):
+    rng = np.random.default_rng(seed)
+    obs = pd.DataFrame({
+        "donor": rng.choice(["b_10", "b_2", "b_9", "a"], n),   # string order != numeric order
+        "chem": rng.choice([3, 10, 1], n),                      # ints are str()-ed by the reference
+        "site": pd.Categorical(rng.choice(["x", "y"], n)),
+    })
+    return AnnDataLite(np.zeros((n, 3), dtype=np.float32), obs=obs)
+
+
+@pytest.mark.parametrize("key", [None, "donor", ["donor"], ["chem", "donor", "site"]])
+def test_design_codes_match_get_dummies(key):
+    q = _query_with_obs()
+    codes, levels = _design.batch_codes(q, key)
+    phi_, lam = so.build_design(q, key, None)
+    n_levels = [len(lv) for lv in levels]
+    assert phi_.shape[0] == 1 + sum(n_levels)
+    # rebuild the one-hot matrix from the codes: must equal the reference's Phi_ row for row
+    mine = np.zeros_like(phi_)
+    mine[0] = 1
+    off = 1
+    for v, lv in enumerate(n_levels):
+        mine[off + codes[v], np.arange(codes.shape[1])] = 1
+        off += lv
+    np.testing.assert_array_equal(mine, phi_)
+    np.testing.assert_array_equal(np.diag(lam), _design.ridge_diagonal(None, n_levels))
+
+
+@pytest.mark.parametrize("lamb", [None, 0.5, 2, [0.5, 2.0, 3.0], list(np.arange(1, 10) / 4)])
+def test_ridge_diagonal_matches_reference(lamb):
+    q = _query_with_obs()
+    key = ["chem", "donor", "site"]  # 3 + 4 + 2 = 9 levels
+    _, levels = _design.batch_codes(q, key)
+    _, lam = so.build_design(q, key, lamb if lamb is None or np.ndim(lamb) == 0 else list(lamb))
+    np.testing.assert_allclose(np.diag(lam), _design.ridge_diagonal(lamb, [len(l) for l in levels]))
+
+
+def test_ridge_diagonal_bad_length():
+    with pytest.raises(AssertionError, match="each batch variable must have a lambda"):
+        _design.ridge_diagonal([1.0, 2.0], [3, 4, 2])
+
+
+def test_knn_params_surface():
+    assert tl._knn_params((), {})["n_neighbors"] == 5
+    assert tl._knn_params((7,), {"algorithm": "kd_tree", "n_jobs": 4})["n_neighbors"] == 7
+    assert tl._knn_params((), {"metric": "euclidean", "n_neighbors": 3})["n_neighbors"] == 3
+    with pytest.raises(NotImplementedError):
+        tl._knn_params((), {"weights": "distance"})
+    with pytest.raises(NotImplementedError):
+        tl._knn_params((), {"metric": "cosine"})
+    with pytest.raises(NotImplementedError):
+        tl._knn_params((), {"p": 1})
+    with pytest.raises(ValueError):
+        tl._knn_params((0,), {})
+    with pytest.raises(TypeError):
+        tl._knn_params((), {"neighbours": 3})
+
+
+def test_map_embedding_asserts_like_reference():
+    q, r = synth.small_case(N=20, M=50, G=32, d=20, K=4, L=3, seed=1)
+    bad = AnnDataLite(r.X, obs=r.obs, var=r.var.drop(columns=["mean"]), obsm=r.obsm, varm=r.varm, uns=r.uns)
+    with pytest.raises(AssertionError, match="Gene expression means"):
+        tl.map_embedding(q, bad)
+    with pytest.raises(AssertionError, match="not found in adata_ref.var"):
+        tl.map_embedding(q, r, use_genes_column="nope")
+    no_h = AnnDataLite(r.X, obs=r.obs, var=r.var, obsm=r.obsm, varm=r.varm, uns={})
+    with pytest.raises(NotImplementedError):
+        tl.map_embedding(q, no_h)
+
+
+def test_no_cpu_fallback(monkeypatch):
+    """Without a CUDA device the product path refuses to run; it never routes through the oracle."""
+    import torch
+
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: False)
+    q, r = synth.small_case(N=20, M=50, G=32, d=20, K=4, L=3, seed=1)
+    with pytest.raises(_lib.SymphonyLibraryError, match="no CPU path"):
+        tl.map_embedding(q, r)
+    with pytest.raises(_lib.SymphonyLibraryError, match="no CPU path"):
+        tl.transfer_labels_kNN(q, r, "cell_type")
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "symphonypy_b200")
+    for name in os.listdir(pkg):
+        if name.endswith(".py"):
+            src = open(os.path.join(pkg, name)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), name
+
+
+def test_library_exports_every_declared_symbol(built_library):
+    header = open(os.path.join(ROOT, "include", "symphony_b200.h")).read()
+    declared = set(re.findall(r"\b(sym_[a-z0-9_]+)\s*\(", header))
+    declared -= {"sym_stream_t"}
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = ctypes.CDLL(built_library)
+    for name in declared:
+        assert hasattr(lib, name), name
+    loaded = _lib.load()
+    assert loaded.sym_version() == 100 and loaded.sym_compiled_arch() == 100
+    assert loaded.sym_last_error() == b""
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.SymphonyLibraryError, match="no CPU fallback"):
+        _lib.load()
+
+
+def test_anndata_lite_gene_indexing():
+    X = np.arange(12, dtype=np.float32).reshape(3, 4)
+    a = AnnDataLite(X, var=pd.DataFrame(index=pd.Index(["a", "b", "c", "d"])))
+    sub = a[:, pd.Index(["d", "b"])]
+    np.testing.assert_array_equal(sub.X, X[:, [3, 1]])
+    assert list(sub.var_names) == ["d", "b"] and len(a) == 3

@@ -1,0 +1,93 @@
+"""The numpy oracle against (a) golden vectors produced by the unmodified reference and
+(b) the reference itself, live, when /root/reference is present (build container only)."""
+import copy
+import glob
+import logging
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import golden_io, ref_loader, symphony_oracle as so
+from symphonypy_b200 import synth
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def _run_oracle(query, ref, call):
+    q = copy.deepcopy(query)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        so.map_embedding(q, ref, **copy.deepcopy(call["map_embedding"]))
+        kw = dict(call["transfer"])
+        so.transfer_labels_knn(q, ref, kw.pop("ref_labels"), **kw)
+    return q
+
+
+def test_golden_present():
+    assert len(GOLDEN) >= 3
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_oracle_matches_golden(path):
+    logging.getLogger("symphony_oracle").setLevel(logging.ERROR)
+    query, ref, call, out = golden_io.unpack(path)
+    q = _run_oracle(query, ref, call)
+    # the oracle repeats the reference's float64 numpy arithmetic: agreement is to rounding noise of BLAS
+    np.testing.assert_allclose(q.obsm["X_pca_reference"], out["X_pca_reference"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(q.obsm["X_pca_harmony"], out["X_pca_harmony"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(q.obsm["X_pca_harmony_symphony_R"], out["R"], rtol=0, atol=1e-12)
+    for k, v in out.items():
+        if k.startswith("label__"):
+            assert (np.asarray(q.obs[k[7:]], dtype=str) == v).all()
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("case", [
+    dict(kw=dict(N=400, M=900, G=256, d=20, K=20, L=6, levels=(1,), seed=21), key=None, lamb=None),
+    dict(kw=dict(N=300, M=800, G=200, d=25, K=12, L=5, levels=(5, 3, 2), seed=22, missing_frac=0.2,
+                 sparse=True, extra_query_genes=17), key=["batch0", "batch1", "batch2"], lamb=[1.0, 0.5, 3.0]),
+    dict(kw=dict(N=150, M=400, G=128, d=20, K=8, L=4, levels=(2,), seed=23, dtype64=False), key="batch0",
+         lamb=[0.7, 1.3]),
+])
+def test_oracle_matches_live_reference(case):
+    tl, _ = ref_loader.load()
+    logging.getLogger("symphonypy").setLevel(logging.ERROR)
+    logging.getLogger("symphony_oracle").setLevel(logging.ERROR)
+    query, ref = synth.small_case(second_label=True, **case["kw"])
+    qa, qb = copy.deepcopy(query), copy.deepcopy(query)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        tl.map_embedding(qa, ref, key=case["key"], lamb=copy.deepcopy(case["lamb"]))
+        so.map_embedding(qb, ref, key=case["key"], lamb=copy.deepcopy(case["lamb"]))
+        tl.transfer_labels_kNN(qa, ref, ["cell_type", "lineage"], n_neighbors=9)
+        so.transfer_labels_knn(qb, ref, ["cell_type", "lineage"], n_neighbors=9)
+    for key in ("X_pca_reference", "X_pca_harmony", "X_pca_harmony_symphony_R"):
+        assert qa.obsm[key].dtype == qb.obsm[key].dtype
+        np.testing.assert_array_equal(qa.obsm[key], qb.obsm[key])
+    for c in ("cell_type", "lineage"):
+        assert (qa.obs[c] == qb.obs[c]).all()
+
+
+def test_vote_rule_matches_sklearn():
+    """`knn_vote_from_indices` restates sklearn's predict / predict_proba (ties -> lowest class)."""
+    from sklearn.neighbors import KNeighborsClassifier
+
+    rng = np.random.default_rng(0)
+    ref = rng.normal(size=(500, 20))
+    q = rng.normal(size=(300, 20))
+    y = rng.integers(0, 5, 500)
+    knn = KNeighborsClassifier(n_neighbors=10).fit(ref, y)
+    idx, _ = so.knn_indices(ref, q, 10)
+    win, frac = so.knn_vote_from_indices(idx, y, 5)
+    assert (win == knn.predict(q)).all()
+    np.testing.assert_allclose(frac, knn.predict_proba(q).max(axis=1))
+
+
+def test_assign_sign_flip_quirk():
+    """Rows whose entries are all negative are flipped by the signed row max (`_utils.py:168`)."""
+    X = np.array([[-1.0, -2.0, -3.0], [1.0, 2.0, 3.0]])
+    Y = np.eye(3)
+    R = so.assign_clusters(X, 0.1, Y, 3)
+    np.testing.assert_allclose(R[:, 0], R[:, 1])
