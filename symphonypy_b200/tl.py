@@ -30,7 +30,7 @@ import pandas as pd
 import torch
 from scipy.sparse import issparse
 
-from . import _design, _dist, engine
+from . import _design, engine, pipeline
 
 logger = logging.getLogger("symphonypy")
 
@@ -279,22 +279,17 @@ def map_embedding(
         inv_sig = _inv_sigma(sigma, Kc, dev)
         Yd = torch.from_numpy(np.ascontiguousarray(Y, dtype=np.float32)).to(dev)
         assert Yd.shape == (Kc, d), "harmony C must be [K, n_components]"
-        R = engine.assign(Z, Yd, inv_sig)
 
         # 3. mixture-of-experts correction
         codes_h, levels = _design.batch_codes(adata_query, key)
         n_levels = [len(lv) for lv in levels]
         lam = _design.ridge_diagonal(lamb, n_levels)
         codes = torch.from_numpy(codes_h).to(dev)
-        orders = [engine.batch_order(codes[v], n_levels[v]) for v in range(len(n_levels))]
-        gram, cross = engine.moe_stats(Z, R, codes, n_levels, orders)
-        _dist.allreduce_stats(gram, cross)  # the only cross-GPU exchange of the path
         Nr = torch.from_numpy(np.ascontiguousarray(harmony_ref["Nr"], dtype=np.float64)).to(dev)
         Cd = torch.from_numpy(np.ascontiguousarray(Cn)).to(dev)
-        W, info = engine.moe_solve(gram, cross, Nr, Cd, torch.from_numpy(lam).to(dev), n_levels[0])
-        Zc = engine.moe_apply(Z, R, codes, n_levels, orders, W)
-        if int(info.abs().max().item()) != 0:
-            raise np.linalg.LinAlgError("Singular matrix")  # what `np.linalg.inv` raises at `_utils.py:208`
+        R, Zc, info = pipeline.soft_assign_and_correct(Z, Yd, inv_sig, codes, n_levels, torch.from_numpy(lam).to(dev),
+                                                       Nr, Cd)
+        pipeline.check_solve(info)
 
         # 4. results back into the AnnData, as the reference does (`tl.py:394-397`, `_utils.py:306`)
         z_h, zc_h = _to_host(Z), _to_host(Zc)

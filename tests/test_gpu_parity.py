@@ -1,0 +1,354 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle.  Run with `-m gpu` on a B200.
+
+Tolerances (north_star): embeddings within 1e-4 relative of the reference's float64 result
+(row-relative L2 error), R within 1e-5 absolute, neighbour indices identical except where the
+distance gap to the k-th boundary is below 1e-5 relative, labels >= 99.9 % identical.
+"""
+import copy
+import glob
+import logging
+import os
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import golden_io, symphony_oracle as so
+from symphonypy_b200 import engine, synth, tl
+
+pytestmark = pytest.mark.gpu
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+EMB_TOL = 1e-4
+R_TOL = 1e-5
+
+
+def row_rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float((np.linalg.norm(a - b, axis=1) / np.maximum(np.linalg.norm(b, axis=1), 1e-30)).max())
+
+
+def quiet():
+    logging.getLogger("symphonypy").setLevel(logging.ERROR)
+    logging.getLogger("symphony_oracle").setLevel(logging.ERROR)
+
+
+# ------------------------------------------------------------------------------ golden fixtures, end to end
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_api_matches_reference_golden(cuda_device, path):
+    quiet()
+    query, ref, call, out = golden_io.unpack(path)
+    tl.clear_caches()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        tl.map_embedding(query, ref, **copy.deepcopy(call["map_embedding"]))
+        kw = dict(call["transfer"])
+        tl.transfer_labels_kNN(query, ref, kw.pop("ref_labels"), **kw)
+    assert row_rel_err(query.obsm["X_pca_reference"], out["X_pca_reference"]) < EMB_TOL
+    assert row_rel_err(query.obsm["X_pca_harmony"], out["X_pca_harmony"]) < EMB_TOL
+    assert np.abs(query.obsm["X_pca_harmony_symphony_R"] - out["R"]).max() < R_TOL
+    for k, v in out.items():
+        if k.startswith("label__"):
+            same = (np.asarray(query.obs[k[7:]], dtype=str) == v).mean()
+            assert same >= 0.999, (k, same)
+
+
+# ------------------------------------------------------------------------------ config 1, oracle side by side
+@pytest.mark.parametrize("variant", ["dense", "csr_missing", "gather"])
+def test_config1_against_oracle(cuda_device, variant):
+    quiet()
+    kw = dict(N=3000, M=10000, G=2000, d=20, K=100, L=12, levels=(1,), seed=0)
+    if variant == "csr_missing":
+        kw.update(missing_frac=0.15, zero_std_frac=0.01, sparse=True, extra_query_genes=300)
+    if variant == "gather":
+        kw.update(missing_frac=0.05, extra_query_genes=100, extra_ref_genes=200)
+    query, ref = synth.small_case(**kw)
+    qo = copy.deepcopy(query)
+    tl.clear_caches()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        so.map_embedding(qo, ref, key=None)
+        so.transfer_labels_knn(qo, ref, "cell_type", n_neighbors=10)
+        tl.map_embedding(query, ref, key=None)
+        tl.transfer_labels_kNN(query, ref, "cell_type", n_neighbors=10, confidence_key="conf")
+    assert row_rel_err(query.obsm["X_pca_reference"], qo.obsm["X_pca_reference"]) < EMB_TOL
+    assert row_rel_err(query.obsm["X_pca_harmony"], qo.obsm["X_pca_harmony"]) < EMB_TOL
+    assert np.abs(query.obsm["X_pca_harmony_symphony_R"] - qo.obsm["X_pca_harmony_symphony_R"]).max() < R_TOL
+    assert (query.obs["cell_type"] == qo.obs["cell_type"]).mean() >= 0.999
+    assert query.obs["conf"].between(0.1, 1.0).all()
+
+
+# ------------------------------------------------------------------------------ kernel level: project
+@pytest.mark.parametrize("N,G,d", [(1, 5, 3), (257, 2000, 20), (1000, 333, 30), (130, 96, 50), (64, 40, 100)])
+def test_project_dense_kernel(cuda_device, N, G, d):
+    rng = np.random.default_rng(N + G)
+    X = (rng.gamma(2.0, 0.8, (N, G)) * (rng.random((N, G)) < 0.3)).astype(np.float32)
+    X[0, 0] = 500.0  # exercises the clip
+    mu, sd = rng.gamma(2.0, 0.15, G), rng.gamma(2.0, 0.2, G) + 0.05
+    sd[rng.choice(G, max(1, G // 20), replace=False)] = 0.0
+    U = rng.normal(size=(G, d))
+    present = rng.random(G) > 0.1
+    ok = present & (sd != 0)
+    t = np.zeros((N, G))
+    t[:, ok] = np.clip((X[:, ok].astype(np.float64) - mu[ok]) / sd[ok], -10, 10)
+    want = t @ U
+    ld = engine.make_loadings(mu, sd, U, present, cuda_device)
+    Z = engine.project_dense(torch.from_numpy(X).to(cuda_device), ld)
+    assert row_rel_err(Z.cpu().numpy(), want) < 2e-5
+    # gather path: same matrix with shuffled columns plus an index
+    perm = rng.permutation(G)
+    Xs = np.ascontiguousarray(X[:, perm])
+    col = np.empty(G, dtype=np.int32)
+    col[perm] = np.arange(G)
+    col[~present] = -1
+    Z2 = engine.project_dense(torch.from_numpy(Xs).to(cuda_device), ld, torch.from_numpy(col).to(cuda_device))
+    assert row_rel_err(Z2.cpu().numpy(), want) < 2e-5
+
+
+def test_project_csr_kernel(cuda_device):
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(5)
+    N, G, d, extra = 700, 500, 30, 60
+    X = sp.random(N, G + extra, density=0.08, format="csr", random_state=1, dtype=np.float32)
+    X.data = (rng.gamma(2.0, 0.8, X.nnz)).astype(np.float32)
+    X[3] = 0  # an empty row
+    X.eliminate_zeros()
+    mu, sd = rng.gamma(2.0, 0.15, G), rng.gamma(2.0, 0.2, G) + 0.05
+    sd[:7] = 0
+    U = rng.normal(size=(G, d))
+    cols = rng.permutation(G + extra)[:G]  # query column of each reference gene
+    present = rng.random(G) > 0.1
+    ok = present & (sd != 0)
+    dense = X.toarray()[:, cols].astype(np.float64)
+    t = np.zeros((N, G))
+    t[:, ok] = np.clip((dense[:, ok] - mu[ok]) / sd[ok], -10, 10)
+    want = t @ U
+    col_gene = np.full(G + extra, -1, dtype=np.int32)
+    col_gene[cols[present]] = np.arange(G, dtype=np.int32)[present]
+    ld = engine.make_loadings(mu, sd, U, present, cuda_device)
+    dev = cuda_device
+    Z = engine.project_csr(torch.from_numpy(X.data).to(dev), torch.from_numpy(X.indices.astype(np.int32)).to(dev),
+                           torch.from_numpy(X.indptr.astype(np.int64)).to(dev), N,
+                           torch.from_numpy(col_gene).to(dev), ld)
+    assert row_rel_err(Z.cpu().numpy(), want) < 2e-5
+
+
+# ------------------------------------------------------------------------------ kernel level: assign
+@pytest.mark.parametrize("N,d,K", [(1, 20, 100), (1001, 30, 100), (513, 50, 200), (77, 20, 7), (300, 24, 300),
+                                   (64, 20, 600)])
+def test_assign_kernel(cuda_device, N, d, K):
+    rng = np.random.default_rng(K)
+    Z = rng.normal(size=(N, d)) * 3
+    Z[0] = -np.abs(Z[0])  # all-negative row: flipped by the signed row max
+    C = rng.normal(size=(K, d))
+    Y = C / np.linalg.norm(C, axis=1, keepdims=True)
+    sigma = list(rng.uniform(0.08, 0.3, K)) if K % 2 else 0.1
+    want = so.assign_clusters(Z.astype(np.float32).astype(np.float64), sigma, Y.astype(np.float32).astype(np.float64), K).T
+    inv = tl._inv_sigma(sigma, K, cuda_device)
+    R = engine.assign(torch.from_numpy(Z.astype(np.float32)).to(cuda_device),
+                      torch.from_numpy(Y.astype(np.float32)).to(cuda_device), inv)
+    got = R.cpu().numpy()
+    assert np.abs(got - want).max() < R_TOL
+    np.testing.assert_allclose(got.sum(1), 1.0, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------ kernel level: MoE
+def _moe_case(N, d, K, levels, seed):
+    rng = np.random.default_rng(seed)
+    Z = rng.normal(size=(N, d)).astype(np.float32)
+    logits = rng.normal(size=(N, K)) * 2
+    R = np.exp(logits - logits.max(1, keepdims=True))
+    R = (R / R.sum(1, keepdims=True)).astype(np.float32)
+    codes = np.stack([rng.integers(0, lv, N) for lv in levels]).astype(np.int32)
+    for v, lv in enumerate(levels):  # every level occupied, very uneven sizes
+        codes[v, :lv] = np.arange(lv)
+    Nr = rng.uniform(5, 50, K)
+    C = rng.normal(size=(K, d)) * Nr[:, None]
+    lam = np.insert(rng.uniform(0.5, 2.0, sum(levels)), 0, 0.0)
+    B1 = 1 + sum(levels)
+    phi = np.zeros((B1, N))
+    phi[0] = 1
+    off = 1
+    for v, lv in enumerate(levels):
+        phi[off + codes[v], np.arange(N)] = 1
+        off += lv
+    return Z, R, codes, Nr, C, lam, phi
+
+
+@pytest.mark.parametrize("N,d,K,levels", [(1000, 20, 100, [1]), (5000, 30, 100, [7]), (3000, 50, 200, [3, 4]),
+                                          (20000, 30, 100, [100]), (4000, 24, 36, [5, 2, 6, 3]), (300, 20, 10, [2])])
+def test_moe_kernels(cuda_device, N, d, K, levels):
+    Z, R, codes, Nr, C, lam, phi = _moe_case(N, d, K, levels, N + K)
+    Z64, R64 = Z.astype(np.float64), R.astype(np.float64)
+    want = so.correct_query(Z64, phi, R64.T, Nr, C, np.diag(lam))
+    Wwant = so.moe_weights(Z64, phi, R64.T, Nr, C, np.diag(lam))
+    dev = cuda_device
+    Zd, Rd, cd = torch.from_numpy(Z).to(dev), torch.from_numpy(R).to(dev), torch.from_numpy(codes).to(dev)
+    orders = [engine.batch_order(cd[v], levels[v]) for v in range(len(levels))]
+    for v, o in enumerate(orders):  # the counting sort is a permutation grouped by level
+        if o.perm is not None:
+            p = o.perm.cpu().numpy()
+            seg = o.seg.cpu().numpy()
+            assert np.array_equal(np.sort(p), np.arange(N))
+            assert np.array_equal(np.bincount(codes[v], minlength=levels[v]), np.diff(seg))
+            assert (np.diff(codes[v][p]) >= 0).all()
+    gram, cross = engine.moe_stats(Zd, Rd, cd, levels, orders)
+    # statistics against the dense formulation (rows/cols >= 1; row 0 is built in the solve)
+    g_want = np.einsum("bn,nk,cn->kbc", phi, R64, phi)
+    h_want = np.einsum("bn,nk,nd->kbd", phi, R64, Z64)
+    np.testing.assert_allclose(gram.cpu().numpy()[:, 1:, 1:], g_want[:, 1:, 1:], rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(cross.cpu().numpy()[:, 1:], h_want[:, 1:], rtol=2e-4, atol=2e-4)
+    W, info = engine.moe_solve(gram, cross, torch.from_numpy(Nr).to(dev), torch.from_numpy(C).to(dev),
+                               torch.from_numpy(lam).to(dev), levels[0])
+    assert int(info.abs().max()) == 0
+    scale = np.abs(Wwant).max()
+    assert np.abs(W.cpu().numpy() - Wwant).max() < 2e-4 * max(scale, 1.0)
+    Zc = engine.moe_apply(Zd, Rd, cd, levels, orders, W)
+    assert row_rel_err(Zc.cpu().numpy(), want) < EMB_TOL
+
+
+def test_moe_singular_reports(cuda_device):
+    """lamb = 0 with key=None makes Phi Phi^T singular; numpy raises LinAlgError, so do we."""
+    query, ref = synth.small_case(N=200, M=300, G=64, d=20, K=5, L=3, seed=4)
+    ref.uns["harmony"]["Nr"] = np.zeros(5)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        with pytest.raises(np.linalg.LinAlgError):
+            tl.map_embedding(query, ref, key=None, lamb=0.0)
+
+
+# ------------------------------------------------------------------------------ kernel level: kNN + vote
+def _check_knn(idx, dist2, ref, q, k, gap_tol=1e-5):
+    want_idx, _ = so.knn_indices(ref.astype(np.float64), q.astype(np.float64), min(k + 1, ref.shape[0]))
+    exact = so.exact_sqdist(ref, q, want_idx)
+    got_exact = so.exact_sqdist(ref, q, idx)
+    n_bad = 0
+    for n in range(q.shape[0]):
+        if np.array_equal(idx[n], want_idx[n, :k]):
+            continue
+        # allowed only where distances tie within tolerance: the sorted exact distances must agree
+        a, b = np.sort(got_exact[n]), np.sort(exact[n, :k])
+        if not np.allclose(a, b, rtol=gap_tol, atol=1e-9):
+            n_bad += 1
+    assert n_bad == 0, f"{n_bad} rows with wrong neighbours"
+    assert (np.diff(got_exact, axis=1) >= -1e-9 * np.abs(got_exact[:, 1:])).all(), "not sorted by distance"
+    np.testing.assert_allclose(dist2, got_exact, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("method", [engine.KNN_FFMA, engine.KNN_AUTO])
+@pytest.mark.parametrize("N,M,d,k", [(3000, 10000, 20, 10), (1, 5, 20, 5), (130, 129, 30, 1), (500, 70000, 50, 30),
+                                     (257, 2000, 50, 50), (300, 900, 100, 7), (100, 400, 3, 4),
+                                     (40, 3000, 30, 120)])
+def test_knn_matches_sklearn(cuda_device, N, M, d, k, method):
+    rng = np.random.default_rng(M + k)
+    centres = rng.normal(size=(8, d)) * 4
+    ref = (centres[rng.integers(0, 8, M)] + rng.normal(size=(M, d))).astype(np.float32)
+    q = (centres[rng.integers(0, 8, N)] + rng.normal(size=(N, d))).astype(np.float32)
+    index = engine.knn_fit(torch.from_numpy(ref).to(cuda_device))
+    idx, dist2, unsafe = engine.knn_search(index, torch.from_numpy(q).to(cuda_device), k, method)
+    assert int(unsafe.sum()) == 0
+    _check_knn(idx.cpu().numpy(), dist2.cpu().numpy(), ref, q, k)
+
+
+def test_knn_duplicates_tie_to_lower_index(cuda_device):
+    rng = np.random.default_rng(3)
+    base = rng.normal(size=(50, 20)).astype(np.float32)
+    ref = np.concatenate([base, base, base])  # every point three times: indices i, i+50, i+100
+    index = engine.knn_fit(torch.from_numpy(ref).to(cuda_device))
+    idx, dist2, _ = engine.knn_search(index, torch.from_numpy(base).to(cuda_device), 2, engine.KNN_FFMA)
+    idx = idx.cpu().numpy()
+    assert (idx[:, 0] == np.arange(50)).all() and (idx[:, 1] == np.arange(50) + 50).all()
+    assert np.abs(dist2.cpu().numpy()).max() < 1e-6
+
+
+def test_knn_k_larger_than_reference(cuda_device):
+    query, ref = synth.small_case(N=50, M=30, G=64, d=20, K=5, L=3, seed=4)
+    query.obsm["X_pca_harmony"] = np.zeros((50, 20), dtype=np.float32)
+    with pytest.raises(ValueError, match="Expected n_neighbors <= n_samples_fit"):
+        tl.transfer_labels_kNN(query, ref, "cell_type", n_neighbors=31)
+
+
+def test_vote_kernel_ties(cuda_device):
+    rng = np.random.default_rng(1)
+    M, N, k, L = 400, 1000, 10, 5
+    codes = rng.integers(0, L, M).astype(np.int32)
+    idx = np.stack([rng.choice(M, k, replace=False) for _ in range(N)]).astype(np.int32)
+    want, frac = so.knn_vote_from_indices(idx, codes, L)
+    ties = (np.sort(np.stack([(codes[idx] == c).sum(1) for c in range(L)], 1), 1)[:, -1] ==
+            np.sort(np.stack([(codes[idx] == c).sum(1) for c in range(L)], 1), 1)[:, -2]).sum()
+    assert ties > 50  # the tie rule is actually exercised
+    lab, conf = engine.vote(torch.from_numpy(idx).to(cuda_device), torch.from_numpy(codes).to(cuda_device))
+    assert (lab.cpu().numpy() == want).all()
+    np.testing.assert_allclose(conf.cpu().numpy(), frac, rtol=1e-6)
+
+
+def test_multilabel_and_neighbors_output(cuda_device):
+    quiet()
+    query, ref = synth.small_case(N=500, M=2000, G=256, d=20, K=20, L=6, levels=(3,), seed=8, second_label=True)
+    qo = copy.deepcopy(query)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        so.map_embedding(qo, ref, key="batch0")
+        tl.map_embedding(query, ref, key="batch0")
+        # same embedding for both so that only the kNN differs
+        qo.obsm["X_pca_harmony"] = query.obsm["X_pca_harmony"].astype(np.float64)
+        so.transfer_labels_knn(qo, ref, ["cell_type", "lineage"], 15, query_labels=["ct", "lin"])
+        tl.transfer_labels_kNN(query, ref, ["cell_type", "lineage"], 15, query_labels=["ct", "lin"],
+                               confidence_key=["ct_conf", "lin_conf"], neighbors_key="knn")
+    assert (query.obs["ct"] == qo.obs["ct"]).all() and (query.obs["lin"] == qo.obs["lin"]).all()
+    assert query.obsm["knn_indices"].shape == (500, 15)
+    # list-of-one keeps the reference's [N, 1] assignment path
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        tl.transfer_labels_kNN(query, ref, ["cell_type"], n_neighbors=15, query_labels=["only"])
+    assert (query.obs["only"] == qo.obs["ct"]).all()
+
+
+# ------------------------------------------------------------------------------ full-size properties
+def test_fullsize_properties_config2(cuda_device):
+    """BASELINE config 2 shapes (1M x 500k would need minutes of sklearn; use size-independent
+    properties instead): (a) a query row that IS a reference row finds itself first at distance 0,
+    (b) kNN distances are sorted and indices unique, (c) R rows sum to 1, (d) the MoE correction
+    is invariant to the order of the cells (permutation equivariance of the whole map)."""
+    dev = cuda_device
+    d, K, k = 30, 100, 10
+    M, N = 500_000, 200_000
+    model = synth.make_model(2000, d, 16, 0, dev)
+    Zref, comp, C, Nr = synth.make_reference(model, M, K, 0)
+    index = engine.knn_fit(Zref)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1)
+    pick = torch.randint(0, M, (N,), generator=g, device=dev)
+    Q = Zref[pick].contiguous()
+    idx, dist2, n_rep = engine.knn_search_certified(index, Q, k)
+    assert (dist2[:, 0] == 0).all()
+    # the first neighbour is the row itself unless an exact duplicate with a lower index exists
+    first = idx[:, 0].long()
+    assert bool(((first == pick) | ((Zref[first] == Q).all(1) & (first < pick))).all())
+    assert bool((dist2[:, 1:] >= dist2[:, :-1]).all())
+    srt = idx.sort(dim=1).values
+    assert bool((srt[:, 1:] != srt[:, :-1]).all())
+
+    X, codes, _ = synth.make_query(model, 50_000, [3], 0)
+    ld = engine.Loadings(mu=model.mean, inv_sd=1.0 / model.std, U=torch.nn.functional.pad(model.U, (0, 2)), d=d)
+    Z = engine.project_dense(X, ld)
+    Y = (C / C.norm(dim=1, keepdim=True)).float().contiguous()
+    inv = torch.full((K,), 10.0, device=dev)
+    R = engine.assign(Z, Y, inv)
+    assert torch.allclose(R.sum(1), torch.ones(50_000, device=dev), atol=1e-5)
+
+    def correct(Z, R, codes):
+        orders = [engine.batch_order(codes[0], 3)]
+        gram, cross = engine.moe_stats(Z, R, codes, [3], orders)
+        lam = torch.tensor([0.0, 1.0, 1.0, 1.0], dtype=torch.float64, device=dev)
+        W, info = engine.moe_solve(gram, cross, Nr, C, lam, 3)
+        assert int(info.abs().max()) == 0
+        return engine.moe_apply(Z, R, codes, [3], orders, W)
+
+    Zc = correct(Z, R, codes)
+    p = torch.randperm(50_000, device=dev)
+    Zc_p = correct(Z[p].contiguous(), R[p].contiguous(), codes[:, p].contiguous())
+    rel = ((Zc_p - Zc[p]).norm(dim=1) / Zc[p].norm(dim=1)).max().item()
+    assert rel < 1e-5
