@@ -104,7 +104,7 @@ __device__ __forceinline__ void topk_insert(unsigned long long *top_row, int kc,
 }
 
 __global__ void __launch_bounds__(SC_THREADS)
-knn_scan_ffma_kernel(const float *__restrict__ Q, int ldq, int64_t N, KnnPacked pk, int d, int kc, int kcap,
+knn_scan_ffma_kernel(const float *__restrict__ Q, int ldq, int64_t N, int64_t M, KnnPacked pk, int d, int kc, int kcap,
                      int tiles_per_split, int top_in_smem, unsigned long long *__restrict__ top_ws,
                      int32_t *__restrict__ cand_out, float *__restrict__ thr_out) {
     extern __shared__ __align__(16) unsigned char smraw[];
@@ -273,8 +273,10 @@ knn_scan_ffma_kernel(const float *__restrict__ Q, int ldq, int64_t N, KnnPacked 
         const int64_t n = q0 + r;
         if (n < N) cand_out[(n * nsplit + split) * kc + e] = (int32_t)(uint32_t)(S.top[(size_t)r * kcap + e] & 0xffffffffull);
     }
+    // a split with no more than kc reference rows hands all of them over: nothing was left out
+    const int64_t split_refs = min(M, (int64_t)t_end * SC_BR) - (int64_t)t_beg * SC_BR;
     for (int r = tid; r < SC_BQ; r += SC_THREADS)
-        if (q0 + r < N) thr_out[(q0 + r) * nsplit + split] = S.thr_f[r];
+        if (q0 + r < N) thr_out[(q0 + r) * nsplit + split] = split_refs <= kc ? INFINITY : S.thr_f[r];
 }
 
 // ------------------------------------------------------------------------------------------ rerank
@@ -476,7 +478,7 @@ extern "C" int sym_knn(const float *Q, int32_t ldq, int64_t N, const float *Ref,
         SYM_REQUIRE(p.smem <= 227 * 1024, SYM_ERR_UNSUPPORTED_SHAPE, "sym_knn: d=%d k=%d needs %zu B of shared memory", d, k, p.smem);
         SYM_CUDA(cudaFuncSetAttribute(knn_scan_ffma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
         dim3 grid((unsigned)p.qtiles, (unsigned)p.nsplit);
-        knn_scan_ffma_kernel<<<grid, SC_THREADS, p.smem, st>>>(Q, ldq, N, pk, d, p.kc, p.kcap, p.tiles_per_split,
+        knn_scan_ffma_kernel<<<grid, SC_THREADS, p.smem, st>>>(Q, ldq, N, M, pk, d, p.kc, p.kcap, p.tiles_per_split,
                                                                p.top_in_smem, top_w, cand_w, thr_w);
         SYM_LAUNCH_CHECK("knn_scan_ffma_kernel");
         cand = cand_w; thr = thr_w; ncand = p.nsplit * p.kc; nsplit = p.nsplit;

@@ -253,10 +253,12 @@ moe_solve_kernel(const double *__restrict__ gram, const double *__restrict__ cro
     // intercept row / column: Phi row 0 is all ones and variable 0 partitions the cells, so
     //   G[0,0] = sum_{levels c of var 0} G[c,c],  G[0,c] = G[c,0] = G[c,c]   (_utils.py:199)
     //   H[0,:] = sum_{levels c of var 0} H[c,:]                              (_utils.py:204)
+    __shared__ double A0;
     if (tid == 0) {
         double s = 0.0;
         for (int c = 1; c <= n_lev0; ++c) s += A[c * B1 + c];
-        A[0] = s + Nr[k] + lamb[0];  // _utils.py:201; the reference forces lamb[0,0] = 0 (:191)
+        A0 = s + Nr[k];
+        A[0] = A0 + lamb[0];  // _utils.py:201; the reference forces lamb[0,0] = 0 (:191)
     }
     for (int c = tid; c < d; c += SV_THREADS) {
         double h0 = C[(int64_t)k * d + c];  // _utils.py:205
@@ -272,10 +274,12 @@ moe_solve_kernel(const double *__restrict__ gram, const double *__restrict__ cro
     }
     __syncthreads();
 
-    // right-looking Cholesky on the lower triangle: A = L L^T
+    // right-looking Cholesky on the lower triangle: A = L L^T.  A pivot that cancels to rounding
+    // noise of its original diagonal entry means the ridge system is singular (np.linalg.inv raises).
     for (int j = 0; j < B1; ++j) {
         const double piv = A[j * B1 + j];
-        if (!(piv > 0.0)) {  // uniform: every thread reads the same value
+        const double d0 = Ag[j * B1 + j] + lamb[j] + (j == 0 ? A0 : 0.0);
+        if (!(piv > 1e-13 * d0)) {  // uniform: every thread reads the same value
             if (tid == 0) bad = j + 1;
             break;
         }
