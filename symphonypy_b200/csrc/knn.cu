@@ -106,7 +106,7 @@ __device__ __forceinline__ void topk_insert(unsigned long long *top_row, int kc,
 __global__ void __launch_bounds__(SC_THREADS)
 knn_scan_ffma_kernel(const float *__restrict__ Q, int ldq, int64_t N, int64_t M, KnnPacked pk, int d, int kc, int kcap,
                      int tiles_per_split, int top_in_smem, unsigned long long *__restrict__ top_ws,
-                     int32_t *__restrict__ cand_out, float *__restrict__ thr_out) {
+                     unsigned long long *__restrict__ cand_out, float *__restrict__ thr_out) {
     extern __shared__ __align__(16) unsigned char smraw[];
     const int d4 = pk.d4;
     ScanSmem S;
@@ -271,7 +271,7 @@ knn_scan_ffma_kernel(const float *__restrict__ Q, int ldq, int64_t N, int64_t M,
     for (int i = tid; i < SC_BQ * kc; i += SC_THREADS) {
         const int r = i / kc, e = i % kc;
         const int64_t n = q0 + r;
-        if (n < N) cand_out[(n * nsplit + split) * kc + e] = (int32_t)(uint32_t)(S.top[(size_t)r * kcap + e] & 0xffffffffull);
+        if (n < N) cand_out[(n * nsplit + split) * kc + e] = S.top[(size_t)r * kcap + e];
     }
     // a split with no more than kc reference rows hands all of them over: nothing was left out
     const int64_t split_refs = min(M, (int64_t)t_end * SC_BR) - (int64_t)t_beg * SC_BR;
@@ -286,7 +286,7 @@ constexpr int RR_MAXC = 512;  // candidates per row the shared scratch can hold
 
 __global__ void __launch_bounds__(RR_THREADS)
 knn_rerank_kernel(const float *__restrict__ Q, int ldq, int64_t N, const float *__restrict__ Ref, int ldr, int64_t M,
-                  int d, int k, const int32_t *__restrict__ cand, const float *__restrict__ thr, int ncand, int nsplit,
+                  int d, int k, const unsigned long long *__restrict__ cand, const float *__restrict__ thr, int ncand, int nsplit,
                   double eps_rel, const KnnHeader *__restrict__ hdr, int32_t *__restrict__ idx_out,
                   float *__restrict__ dist_out, uint8_t *__restrict__ unsafe) {
     __shared__ double sd[RR_THREADS / 32][RR_MAXC];
@@ -302,10 +302,15 @@ knn_rerank_kernel(const float *__restrict__ Q, int ldq, int64_t N, const float *
     }
     double *wd = sd[warp];
     int32_t *wi = si[warp];
+    const double rmax2 = (double)hdr->rmax2;
+    const double eps = eps_rel * (2.0 * sqrt(qn) * sqrt(rmax2) + rmax2);
+    int bad = 0;  // a recorded scan score further than eps from the exact score voids the certificate
     for (int e = lane; e < ncand; e += 32) {
-        const int32_t id = cand[n * ncand + e];
+        const unsigned long long key = cand[n * ncand + e];
+        const uint32_t id = (uint32_t)(key & 0xffffffffull);
         double dist = INFINITY;
-        if (id >= 0 && id < M) {
+        const bool valid = key != ~0ull && (int64_t)id < M;
+        if (valid) {
             const float *r = Ref + (int64_t)id * ldr;
             double rn = 0.0, dot = 0.0;
             for (int c = 0; c < d; ++c) {
@@ -313,10 +318,12 @@ knn_rerank_kernel(const float *__restrict__ Q, int ldq, int64_t N, const float *
                 rn = fma(rv, rv, rn);
                 dot = fma((double)q[c], rv, dot);
             }
-            dist = fmax(qn - 2.0 * dot + rn, 0.0);  // sklearn: ||x||^2 - 2 x.y + ||y||^2, clamped
+            const double s_exact = rn - 2.0 * dot;
+            bad |= !(fabs((double)knn_key_score(key) - s_exact) <= eps);
+            dist = fmax(qn + s_exact, 0.0);  // sklearn: ||x||^2 - 2 x.y + ||y||^2, clamped at 0
         }
         wd[e] = dist;
-        wi[e] = (id >= 0 && id < M) ? id : 0x7fffffff;
+        wi[e] = valid ? (int32_t)id : 0x7fffffff;
     }
     __syncwarp();
     double kth = 0.0;
@@ -340,12 +347,11 @@ knn_rerank_kernel(const float *__restrict__ Q, int ldq, int64_t N, const float *
         // neighbour if  kth_exact - ||q||^2 + 2 eps < thr.
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) kth = fmax(kth, __shfl_xor_sync(0xffffffffu, kth, o));
+        bad = __any_sync(0xffffffffu, bad);
         if (lane == 0) {
-            const double rmax = sqrt((double)hdr->rmax2), qnorm = sqrt(qn);
-            const double eps = eps_rel * (2.0 * qnorm * rmax + (double)hdr->rmax2);
             double tmin = INFINITY;
             for (int s = 0; s < nsplit; ++s) tmin = fmin(tmin, (double)thr[n * nsplit + s]);
-            unsafe[n] = (kth - qn + 2.0 * eps < tmin) ? 0 : 1;
+            unsafe[n] = (!bad && kth - qn + 2.0 * eps < tmin) ? 0 : 1;
         }
     }
 }
@@ -426,7 +432,7 @@ int plan_scan(int64_t N, int64_t M, int d, int k, ScanPlan &p) {
     }
     p.tiles_per_split = (int)ceil_div(ntiles, nsplit);
     p.nsplit = (int)ceil_div(ntiles, p.tiles_per_split);
-    p.cand_bytes = ((size_t)N * p.nsplit * kc * sizeof(int32_t) + 255) & ~(size_t)255;
+    p.cand_bytes = ((size_t)N * p.nsplit * kc * sizeof(unsigned long long) + 255) & ~(size_t)255;
     p.thr_bytes = ((size_t)N * p.nsplit * sizeof(float) + 255) & ~(size_t)255;
     p.top_bytes = p.top_in_smem ? 0 : (size_t)p.qtiles * p.nsplit * SC_BQ * p.kcap * 8;
     return SYM_OK;
@@ -462,7 +468,7 @@ extern "C" int sym_knn(const float *Q, int32_t ldq, int64_t N, const float *Ref,
 
     int ncand = 0, nsplit = 1;
     double eps_rel = 0.0;
-    const int32_t *cand = nullptr;
+    const unsigned long long *cand = nullptr;
     const float *thr = nullptr;
     if (method == 2) {
         SYM_REQUIRE(knn_tc_supported(N, M, d, k), SYM_ERR_UNSUPPORTED_SHAPE, "sym_knn: tcgen05 scan does not support this shape");
@@ -472,7 +478,7 @@ extern "C" int sym_knn(const float *Q, int32_t ldq, int64_t N, const float *Ref,
         ScanPlan p;
         plan_scan(N, M, d, k, p);
         unsigned char *w = (unsigned char *)workspace;
-        int32_t *cand_w = (int32_t *)w; w += p.cand_bytes;
+        unsigned long long *cand_w = (unsigned long long *)w; w += p.cand_bytes;
         float *thr_w = (float *)w; w += p.thr_bytes;
         unsigned long long *top_w = (unsigned long long *)w;
         SYM_REQUIRE(p.smem <= 227 * 1024, SYM_ERR_UNSUPPORTED_SHAPE, "sym_knn: d=%d k=%d needs %zu B of shared memory", d, k, p.smem);

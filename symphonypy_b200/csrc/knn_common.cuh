@@ -70,7 +70,7 @@ bool knn_tc_supported(int64_t N, int64_t M, int d, int k);
 size_t knn_tc_workspace(int64_t N, int64_t M, int d, int k);
 int knn_tc_fit(const float *Ref, int ldr, int64_t M, int d, KnnPacked pk, cudaStream_t st);
 int knn_tc_scan(const float *Q, int ldq, int64_t N, KnnPacked pk, int64_t M, int d, int k, void *workspace,
-                size_t workspace_bytes, cudaStream_t st, const int32_t **cand, const float **thr, int *ncand,
+                size_t workspace_bytes, cudaStream_t st, const unsigned long long **cand, const float **thr, int *ncand,
                 int *nsplit, double *eps_rel);
 
 }  // namespace sym

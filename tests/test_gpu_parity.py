@@ -352,3 +352,46 @@ def test_fullsize_properties_config2(cuda_device):
     Zc_p = correct(Z[p].contiguous(), R[p].contiguous(), codes[:, p].contiguous())
     rel = ((Zc_p - Zc[p]).norm(dim=1) / Zc[p].norm(dim=1)).max().item()
     assert rel < 1e-5
+
+
+# ------------------------------------------------------------------------------ tcgen05 scan
+def test_tc_score_tile(cuda_device, built_library):
+    """The BF16x3 tcgen05 score tile ||r||^2 - 2 q.r against float64 (packing, descriptors, MMA chain)."""
+    import ctypes
+
+    lib = ctypes.CDLL(built_library)
+    rng = np.random.default_rng(0)
+    for d in (20, 30, 50, 7):
+        q = (rng.normal(size=(100, d)) * 3).astype(np.float32)
+        r = (rng.normal(size=(128, d)) * 3).astype(np.float32)
+        Q, R = torch.from_numpy(q).to(cuda_device), torch.from_numpy(r).to(cuda_device)
+        out = torch.zeros((128, 128), device=cuda_device)
+        scratch = torch.zeros(2 * 256 * 256 + 1024, dtype=torch.uint8, device=cuda_device)
+        rc = lib.sym_debug_tc_scores(ctypes.c_void_p(Q.data_ptr()), 100, ctypes.c_void_p(R.data_ptr()), 128, d,
+                                     ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(scratch.data_ptr()), None)
+        assert rc == 0
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()[:100]
+        want = (r.astype(np.float64) ** 2).sum(1)[None, :] - 2.0 * q.astype(np.float64) @ r.astype(np.float64).T
+        scale = 2 * np.linalg.norm(q, axis=1)[:, None] * np.linalg.norm(r, axis=1)[None, :] + (r ** 2).sum(1)[None, :]
+        err = np.abs(got - want) / scale
+        assert err.max() < 6e-5, (d, err.max())
+        assert (out.cpu().numpy()[100:] == (r.astype(np.float32) ** 2).sum(1)[None, :]).mean() > 0.9  # zero query rows
+
+
+@pytest.mark.parametrize("N,M,d,k", [(3000, 10000, 20, 10), (1, 5, 20, 5), (130, 129, 30, 1), (500, 70000, 50, 30),
+                                     (257, 2000, 50, 50), (100, 400, 3, 4), (20000, 50000, 30, 10)])
+def test_knn_tcgen05_matches_sklearn(cuda_device, N, M, d, k):
+    rng = np.random.default_rng(M + k)
+    centres = rng.normal(size=(8, d)) * 4
+    ref = (centres[rng.integers(0, 8, M)] + rng.normal(size=(M, d))).astype(np.float32)
+    q = (centres[rng.integers(0, 8, N)] + rng.normal(size=(N, d))).astype(np.float32)
+    index = engine.knn_fit(torch.from_numpy(ref).to(cuda_device))
+    idx, dist2, unsafe = engine.knn_search(index, torch.from_numpy(q).to(cuda_device), k, engine.KNN_TCGEN05)
+    n_unsafe = int(unsafe.sum())
+    assert n_unsafe <= max(1, N // 100), n_unsafe   # the certificate rarely fails on separated data
+    ok = (unsafe == 0).cpu().numpy()
+    _check_knn(idx.cpu().numpy()[ok], dist2.cpu().numpy()[ok], ref, q[ok], k)
+    # and the certified wrapper repairs whatever was flagged
+    idx2, dist22, _ = engine.knn_search_certified(index, torch.from_numpy(q).to(cuda_device), k, engine.KNN_TCGEN05)
+    _check_knn(idx2.cpu().numpy(), dist22.cpu().numpy(), ref, q, k)
