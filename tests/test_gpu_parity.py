@@ -247,8 +247,12 @@ def test_knn_matches_sklearn(cuda_device, N, M, d, k, method):
     ref = (centres[rng.integers(0, 8, M)] + rng.normal(size=(M, d))).astype(np.float32)
     q = (centres[rng.integers(0, 8, N)] + rng.normal(size=(N, d))).astype(np.float32)
     index = engine.knn_fit(torch.from_numpy(ref).to(cuda_device))
-    idx, dist2, unsafe = engine.knn_search(index, torch.from_numpy(q).to(cuda_device), k, method)
-    assert int(unsafe.sum()) == 0
+    Qd = torch.from_numpy(q).to(cuda_device)
+    if method == engine.KNN_FFMA:
+        idx, dist2, unsafe = engine.knn_search(index, Qd, k, method)
+        assert int(unsafe.sum()) == 0
+    else:  # auto: tensor-core scan where it fits, rows it cannot certify are repaired by the FP32 scan
+        idx, dist2, _ = engine.knn_search_certified(index, Qd, k, method)
     _check_knn(idx.cpu().numpy(), dist2.cpu().numpy(), ref, q, k)
 
 
@@ -376,7 +380,7 @@ def test_tc_score_tile(cuda_device, built_library):
         scale = 2 * np.linalg.norm(q, axis=1)[:, None] * np.linalg.norm(r, axis=1)[None, :] + (r ** 2).sum(1)[None, :]
         err = np.abs(got - want) / scale
         assert err.max() < 6e-5, (d, err.max())
-        assert (out.cpu().numpy()[100:] == (r.astype(np.float32) ** 2).sum(1)[None, :]).mean() > 0.9  # zero query rows
+        assert (out.cpu().numpy()[100:] == 0).all()  # padded query rows are all-zero operands
 
 
 @pytest.mark.parametrize("N,M,d,k", [(3000, 10000, 20, 10), (1, 5, 20, 5), (130, 129, 30, 1), (500, 70000, 50, 30),
