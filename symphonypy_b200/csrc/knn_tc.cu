@@ -28,8 +28,8 @@ namespace sym {
 
 constexpr int TC_BM = 128;        // query rows per CTA (UMMA M)
 constexpr int TC_BN = 128;        // reference rows per tile (UMMA N)
-constexpr int TC_THREADS = 192;
-constexpr int TC_ACC = 4;         // TMEM accumulator buffers (4 x 128 columns)
+// query tiles per CTA: QT = 2 (256 rows share every reference tile) when shared memory allows, else 1;
+// TMEM accumulator buffers per query tile: 4 / QT  (QT * ACC * 128 = 512 columns)
 constexpr int TC_MAX_STAGES = 4;
 constexpr int TC_PAD = 8;         // over-selection: kc = k + TC_PAD
 
@@ -178,43 +178,86 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
 constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((TC_BN >> 3) << 17) | ((TC_BM >> 4) << 24);
 
 // ------------------------------------------------------------------------------------------ scan kernel
-struct RowTop {
-    float thr;                    // score of the current kc-th best (+inf while the list is not full)
-    unsigned long long thr_key;   // its (score, index) key
-    int pos;                      // its slot
-};
+// A CTA owns TC_QT query tiles (256 rows) and streams the reference tiles once for both.
+//   warp 0       : producer (cp.async.bulk of one packed tile per stage)
+//   warp 1       : TMEM owner + MMA issuer (TC_QT chains of kp/16 tcgen05.mma per reference tile)
+//   warps 2..9   : selection; warp w serves query tile (w-2)/4, TMEM lane quadrant w%4, thread <-> query row
+// TMEM: accumulator (query tile q, buffer b) lives at columns (q*TC_ACC + b)*128.
+//
+// Selection, per 32-column chunk: tcgen05.ld (issued one chunk ahead), four independent 3-input-min
+// chains over groups of 8, one compare against the row's kc-th best.  Only groups in which some lane
+// of the warp has a hit are walked, and a hit calls the (single, out-of-line) list update.
 
-// per-thread: replace the row's current maximum with `key` and find the new maximum
-__device__ __noinline__ void tc_insert(unsigned long long *top_row /* stride TC_BM */, int kc, unsigned long long key,
-                                       RowTop &st) {
-    top_row[st.pos * TC_BM] = key;
-    unsigned long long best = 0ull;
-    int pos = 0;
+// Replace the slot holding the row's current maximum `thr` by (s, id); returns the new maximum.
+// Scores / indices are stored [slot][row] (stride TC_BM) so the 32 rows of a warp never bank-conflict.
+__device__ __noinline__ float tc_insert(float *sc_row, uint32_t *idx_row, int kc, float s, uint32_t id, float thr) {
+    int pos = -1;
+    float rest = -INFINITY;  // maximum of the slots that stay
+#pragma unroll 8
     for (int e = 0; e < kc; ++e) {
-        const unsigned long long v = top_row[e * TC_BM];
-        if (v > best) { best = v; pos = e; }
+        const float v = sc_row[e * TC_BM];
+        const bool take = (pos < 0) && (v == thr);
+        pos = take ? e : pos;
+        rest = take ? rest : fmaxf(rest, v);
     }
-    st.thr_key = best;
-    st.pos = pos;
-    st.thr = knn_key_score(best);
+    if (pos < 0) return thr;  // cannot happen: thr is the maximum of the list
+    sc_row[pos * TC_BM] = s;
+    idx_row[pos * TC_BM] = id;
+    return fmaxf(rest, s);
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+#define TC_WALK8(G)                                                                                   \
+    if (__any_sync(0xffffffffu, g##G < thr)) {                                                        \
+        _Pragma("unroll") for (int j = 0; j < 8; ++j) {                                               \
+            const float sv = __uint_as_float(v[(G) * 8 + j]);                                         \
+            if (sv < thr) {                                                                           \
+                const int64_t id = ref0 + (G) * 8 + j;                                                \
+                if (id < M) thr = tc_insert(sc_row, idx_row, kc, sv, (uint32_t)id, thr);              \
+            }                                                                                         \
+        }                                                                                             \
+    }
+
+__device__ __forceinline__ float tc_min8(const uint32_t *v) {
+    float m = fmin3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
+    m = fmin3(m, __uint_as_float(v[3]), __uint_as_float(v[4]));
+    m = fmin3(m, __uint_as_float(v[5]), __uint_as_float(v[6]));
+    return fminf(m, __uint_as_float(v[7]));
+}
+
+// one 32-column chunk of one row against the row's threshold
+__device__ __forceinline__ float tc_select32(const uint32_t (&v)[32], float thr, int64_t ref0, int64_t M, float *sc_row,
+                                             uint32_t *idx_row, int kc) {
+    const float g0 = tc_min8(v), g1 = tc_min8(v + 8), g2 = tc_min8(v + 16), g3 = tc_min8(v + 24);
+    const float m = fminf(fmin3(g0, g1, g2), g3);
+    if (__any_sync(0xffffffffu, m < thr)) {
+        TC_WALK8(0)
+        TC_WALK8(1)
+        TC_WALK8(2)
+        TC_WALK8(3)
+    }
+    return thr;
+}
+
+template <int TC_QT>
+__global__ void __launch_bounds__(64 + 128 * TC_QT, 1)
 knn_scan_tc_kernel(const unsigned char *__restrict__ qpack, const unsigned char *__restrict__ rpack, int64_t N,
                    int64_t M, int kp, int kc, int stages, int tiles_per_split, int ntiles_all,
                    unsigned long long *__restrict__ cand_out, float *__restrict__ thr_out) {
+    constexpr int TC_ACC = 4 / TC_QT;
+    constexpr int TC_SEL_WARPS = 4 * TC_QT;
     extern __shared__ __align__(1024) unsigned char smraw[];
     const uint32_t tile_bytes = (uint32_t)tc_tile_bytes(kp);
-    unsigned char *q_s = smraw;                                   // [tile_bytes]
-    unsigned char *r_s = smraw + tile_bytes;                      // [stages][tile_bytes]
-    unsigned long long *top_s = (unsigned long long *)(r_s + (size_t)stages * tile_bytes);  // [kc][TC_BM]
-    uint64_t *bars = (uint64_t *)(top_s + (size_t)kc * TC_BM);
-    uint64_t *q_full = bars;                   // 1
-    uint64_t *r_full = bars + 1;               // [TC_MAX_STAGES]
-    uint64_t *r_empty = r_full + TC_MAX_STAGES;
-    uint64_t *t_full = r_empty + TC_MAX_STAGES;   // [TC_ACC]
-    uint64_t *t_empty = t_full + TC_ACC;
-    uint32_t *tmem_slot = (uint32_t *)(t_empty + TC_ACC);
+    unsigned char *q_s = smraw;                                        // [TC_QT][tile_bytes]
+    unsigned char *r_s = q_s + (size_t)TC_QT * tile_bytes;             // [stages][tile_bytes]
+    float *sc_s = (float *)(r_s + (size_t)stages * tile_bytes);        // [TC_QT][kc][TC_BM]
+    uint32_t *idx_s = (uint32_t *)(sc_s + (size_t)TC_QT * kc * TC_BM); // [TC_QT][kc][TC_BM]
+    uint64_t *bars = (uint64_t *)(idx_s + (size_t)TC_QT * kc * TC_BM);
+    uint64_t *q_full = bars;                      // 1
+    uint64_t *r_full = bars + 1;                  // [TC_MAX_STAGES]
+    uint64_t *r_empty = r_full + TC_MAX_STAGES;   // [TC_MAX_STAGES]
+    uint64_t *t_full = r_empty + TC_MAX_STAGES;   // [4]
+    uint64_t *t_empty = t_full + 4;               // [4]
+    uint32_t *tmem_slot = (uint32_t *)(t_empty + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int split = blockIdx.y, nsplit = gridDim.y;
@@ -225,7 +268,7 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qpack, const unsigned char 
     if (threadIdx.x == 0) {
         mbar_init(q_full, 1);
         for (int i = 0; i < TC_MAX_STAGES; ++i) { mbar_init(&r_full[i], 1); mbar_init(&r_empty[i], 1); }
-        for (int i = 0; i < TC_ACC; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+        for (int i = 0; i < TC_ACC; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], TC_SEL_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {  // TMEM: all 512 columns, owned by this warp
@@ -234,10 +277,12 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qpack, const unsigned char 
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // selection threads initialise their row's list
-    if (warp >= 2) {
-        const int row = (warp & 3) * 32 + lane;
-        for (int e = 0; e < kc; ++e) top_s[e * TC_BM + row] = ~0ull;
+    if (warp >= 2) {  // selection threads initialise their row's list
+        const int qt = (warp - 2) >> 2, row = (warp & 3) * 32 + lane;
+        for (int e = 0; e < kc; ++e) {
+            sc_s[((size_t)qt * kc + e) * TC_BM + row] = INFINITY;
+            idx_s[((size_t)qt * kc + e) * TC_BM + row] = 0xffffffffu;
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -245,10 +290,12 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qpack, const unsigned char 
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===== producer: one bulk copy per tile =====
+        // ===== producer =====
         if (lane == 0) {
-            mbar_arrive_expect_tx(q_full, tile_bytes);
-            bulk_g2s(q_s, qpack + (size_t)blockIdx.x * tile_bytes, tile_bytes, q_full);
+            mbar_arrive_expect_tx(q_full, TC_QT * tile_bytes);
+            for (int q = 0; q < TC_QT; ++q)
+                bulk_g2s(q_s + (size_t)q * tile_bytes, qpack + ((size_t)blockIdx.x * TC_QT + q) * tile_bytes, tile_bytes,
+                         q_full);
             for (int i = 0; i < ntiles; ++i) {
                 const int s = i % stages;
                 mbar_wait(&r_empty[s], ((i / stages) & 1) ^ 1);
@@ -257,7 +304,7 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qpack, const unsigned char 
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: one thread, kp/16 instructions per tile =====
+        // ===== MMA issuer =====
         if (lane == 0) {
             mbar_wait(q_full, 0);
             const uint32_t q_addr = smem_u32(q_s);
@@ -267,60 +314,62 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qpack, const unsigned char 
                 mbar_wait(&r_full[s], (i / stages) & 1);
                 tc_fence_after();
                 const uint32_t r_addr = smem_u32(r_s + (size_t)s * tile_bytes);
-                const uint32_t d_tmem = tmem_base + (uint32_t)(b * TC_BN);
-                for (int k = 0; k < kp / 16; ++k)
-                    tc_mma_bf16(d_tmem, umma_desc(q_addr + k * 4096), umma_desc(r_addr + k * 4096), TC_IDESC, k > 0);
+#pragma unroll
+                for (int q = 0; q < TC_QT; ++q) {
+                    const uint32_t d_tmem = tmem_base + (uint32_t)((q * TC_ACC + b) * TC_BN);
+                    for (int k = 0; k < kp / 16; ++k)
+                        tc_mma_bf16(d_tmem, umma_desc(q_addr + q * tile_bytes + k * 4096), umma_desc(r_addr + k * 4096),
+                                    TC_IDESC, k > 0);
+                }
                 tc_commit(&r_empty[s]);   // smem stage reusable once these MMAs have read it
-                tc_commit(&t_full[b]);    // accumulator complete
+                tc_commit(&t_full[b]);    // both accumulators of buffer b complete
             }
         }
     } else {
-        // ===== selection: thread <-> query row <-> TMEM lane =====
-        const int quad = warp & 3;
+        // ===== selection =====
+        const int qt = (warp - 2) >> 2, quad = warp & 3;
         const int row = quad * 32 + lane;
-        unsigned long long *top_row = top_s + row;
-        RowTop st;
-        st.thr = INFINITY;
-        st.thr_key = ~0ull;
-        st.pos = 0;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+        float *sc_row = sc_s + (size_t)qt * kc * TC_BM + row;
+        uint32_t *idx_row = idx_s + (size_t)qt * kc * TC_BM + row;
+        float thr = INFINITY;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(qt * TC_ACC * TC_BN);
         for (int i = 0; i < ntiles; ++i) {
             const int b = i % TC_ACC;
             mbar_wait(&t_full[b], (i / TC_ACC) & 1);
             tc_fence_after();
             const int64_t ref0 = (int64_t)(t_beg + i) * TC_BN;
-#pragma unroll 1
-            for (int c = 0; c < TC_BN / 32; ++c) {
-                uint32_t v[32];
-                __syncwarp();
-                tc_ld32(lane_base + (uint32_t)(b * TC_BN + c * 32), v);
-                tc_wait_ld();
-                float m = fmin3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
-#pragma unroll
-                for (int j = 3; j + 1 < 32; j += 2) m = fmin3(m, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
-                m = fminf(m, __uint_as_float(v[31]));
-                if (m <= st.thr) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float sv = __uint_as_float(v[j]);
-                        if (sv <= st.thr) {
-                            const int64_t id = ref0 + c * 32 + j;
-                            const unsigned long long key = knn_make_key(sv, (uint32_t)id);
-                            if (id < M && key < st.thr_key) tc_insert(top_row, kc, key, st);
-                        }
-                    }
-                }
-            }
-            tc_fence_before();
+            const uint32_t acc = lane_base + (uint32_t)(b * TC_BN);
+            uint32_t va[32], vb[32];
+            tc_ld32(acc, va);
+            tc_wait_ld();
+            tc_ld32(acc + 32, vb);                       // in flight while chunk 0 is examined
+            thr = tc_select32(va, thr, ref0, M, sc_row, idx_row, kc);
             __syncwarp();
+            tc_wait_ld();
+            tc_ld32(acc + 64, va);
+            thr = tc_select32(vb, thr, ref0 + 32, M, sc_row, idx_row, kc);
+            __syncwarp();
+            tc_wait_ld();
+            tc_ld32(acc + 96, vb);
+            thr = tc_select32(va, thr, ref0 + 64, M, sc_row, idx_row, kc);
+            __syncwarp();
+            tc_wait_ld();
+            // every score of this accumulator is in registers: hand the TMEM buffer back early
+            tc_fence_before();
             if (lane == 0) mbar_arrive(&t_empty[b]);
+            thr = tc_select32(vb, thr, ref0 + 96, M, sc_row, idx_row, kc);
+            __syncwarp();
         }
-        // results: the row's candidate keys (unordered) and its final threshold
-        const int64_t n = (int64_t)blockIdx.x * TC_BM + row;
+        // results: the row's candidates as (score, index) keys (unordered) and its final threshold
+        const int64_t n = ((int64_t)blockIdx.x * TC_QT + qt) * TC_BM + row;
         if (n < N) {
-            for (int e = 0; e < kc; ++e) cand_out[(n * nsplit + split) * kc + e] = top_row[e * TC_BM];
+            for (int e = 0; e < kc; ++e) {
+                const uint32_t id = idx_row[e * TC_BM];
+                cand_out[(n * nsplit + split) * kc + e] =
+                    id == 0xffffffffu ? ~0ull : knn_make_key(sc_row[e * TC_BM], id);
+            }
             const int64_t split_refs = min(M, (int64_t)t_end * TC_BN) - (int64_t)t_beg * TC_BN;
-            thr_out[n * nsplit + split] = split_refs <= kc ? INFINITY : st.thr;
+            thr_out[n * nsplit + split] = split_refs <= kc ? INFINITY : thr;
         }
     }
     tc_fence_before();
@@ -390,7 +439,7 @@ tc_debug_kernel(const unsigned char *__restrict__ qpack, const unsigned char *__
 // ------------------------------------------------------------------------------------------ host side
 namespace {
 struct TcPlan {
-    int kp, kc, stages, nsplit, tiles_per_split, ntiles;
+    int kp, kc, qt, stages, nsplit, tiles_per_split, ntiles;
     int64_t qtiles;
     size_t smem, qpack_bytes, cand_bytes, thr_bytes;
     bool ok;
@@ -403,16 +452,21 @@ TcPlan tc_plan(int64_t N, int64_t M, int d, int k) {
     if (kc > M) kc = (int)M;
     p.kc = kc;
     const size_t tile = tc_tile_bytes(p.kp);
-    const size_t fixed = tile + (size_t)kc * TC_BM * 8 + 256 /* barriers */ + 1024 /* alignment slack */;
     const size_t budget = 227 * 1024;
+    size_t fixed = 0;
     int stages = 0;
-    if (budget > fixed) stages = (int)((budget - fixed) / tile);
-    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+    for (int qt = 2; qt >= 1; --qt) {
+        fixed = qt * tile + (size_t)qt * kc * TC_BM * 8 + 256 /* barriers */ + 1024 /* alignment slack */;
+        stages = budget > fixed ? (int)((budget - fixed) / tile) : 0;
+        if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+        p.qt = qt;
+        if (stages >= 2) break;
+    }
     p.stages = stages;
     p.ok = stages >= 2 && p.kp <= 256 && d <= 84;
     p.smem = fixed + (size_t)(stages > 0 ? stages : 0) * tile;
     if (p.smem < 120 * 1024) p.smem = 120 * 1024;  // one CTA per SM: a CTA owns all 512 TMEM columns
-    p.qtiles = ceil_div(N, TC_BM);
+    p.qtiles = ceil_div(N, TC_BM * p.qt);  // CTAs along the query
     p.ntiles = (int)(knn_mpad(M) / TC_BN);
     int nsplit = 1;
     if (p.qtiles < kNumSMs) {
@@ -425,7 +479,7 @@ TcPlan tc_plan(int64_t N, int64_t M, int d, int k) {
     }
     p.tiles_per_split = (int)ceil_div(p.ntiles, nsplit);
     p.nsplit = (int)ceil_div(p.ntiles, p.tiles_per_split);
-    p.qpack_bytes = (size_t)p.qtiles * tile;
+    p.qpack_bytes = (size_t)p.qtiles * p.qt * tile;
     p.cand_bytes = ((size_t)N * p.nsplit * kc * 8 + 255) & ~(size_t)255;
     p.thr_bytes = ((size_t)N * p.nsplit * 4 + 255) & ~(size_t)255;
     return p;
@@ -470,15 +524,21 @@ int knn_tc_scan(const float *Q, int ldq, int64_t N, KnnPacked pk, int64_t M, int
     unsigned long long *cand_w = (unsigned long long *)w; w += p.cand_bytes;
     float *thr_w = (float *)w;
     {
-        const int64_t rows_pad = p.qtiles * TC_BM;
+        const int64_t rows_pad = p.qtiles * p.qt * TC_BM;
         dim3 grid((unsigned)ceil_div(rows_pad, 256), (unsigned)(p.kp / 8));
         tc_pack_kernel<<<grid, 256, 0, st>>>(Q, ldq, N, rows_pad, d, p.kp, 1, qpack);
         SYM_LAUNCH_CHECK("tc_pack_kernel(query)");
     }
-    SYM_CUDA(cudaFuncSetAttribute(knn_scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     dim3 grid((unsigned)p.qtiles, (unsigned)p.nsplit);
-    knn_scan_tc_kernel<<<grid, TC_THREADS, p.smem, st>>>(qpack, pk.tc, N, M, p.kp, p.kc, p.stages, p.tiles_per_split,
-                                                         p.ntiles, cand_w, thr_w);
+    if (p.qt == 2) {
+        SYM_CUDA(cudaFuncSetAttribute(knn_scan_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+        knn_scan_tc_kernel<2><<<grid, 64 + 128 * 2, p.smem, st>>>(qpack, pk.tc, N, M, p.kp, p.kc, p.stages,
+                                                                  p.tiles_per_split, p.ntiles, cand_w, thr_w);
+    } else {
+        SYM_CUDA(cudaFuncSetAttribute(knn_scan_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+        knn_scan_tc_kernel<1><<<grid, 64 + 128 * 1, p.smem, st>>>(qpack, pk.tc, N, M, p.kp, p.kc, p.stages,
+                                                                  p.tiles_per_split, p.ntiles, cand_w, thr_w);
+    }
     SYM_LAUNCH_CHECK("knn_scan_tc_kernel");
     *cand = cand_w;
     *thr = thr_w;
