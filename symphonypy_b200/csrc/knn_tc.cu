@@ -106,16 +106,32 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+// Busy-poll (mbarrier.test_wait): the hand-offs between the MMA issuer and the selection warps sit on the
+// critical path of every tile, and the suspending form (try_wait -> NANOSLEEP.SYNCS) was measured to add
+// microseconds per hand-off (profiles/r1d).  Only ~10 warps live on the SM, so polling costs nothing.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
         ".reg .pred P1;\n\t"
         "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
         "@P1 bra WAIT_DONE;\n\t"
         "bra WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+// Suspending wait for the producer, which runs far ahead and is never on the critical path.
+__device__ __forceinline__ void mbar_wait_sleepy(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity)
         : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
@@ -129,6 +145,19 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint3
                      smem_u32(smem_dst)),
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+// one lane of a converged warp (elect.sync): keeps the surrounding control flow warp-uniform, so that
+// tcgen05.mma / commit operands stay in uniform registers instead of being re-uniformised per instruction
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -188,24 +217,27 @@ constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((TC_BN >> 3)
 // chains over groups of 8, one compare against the row's kc-th best.  Only groups in which some lane
 // of the warp has a hit are walked, and a hit calls the (single, out-of-line) list update.
 
-// Replace the slot holding the row's current maximum `thr` by (s, id); returns the new maximum.
-// Scores / indices are stored [slot][row] (stride TC_BM) so the 32 rows of a warp never bank-conflict.
+// Replace the slot holding the row's current maximum `thr` by (s, id); returns the new maximum.  Every lane
+// updates ITS OWN row (lanes run in lock-step when several rows hit at once).  Row stride `ks` is odd, so the
+// 32 rows of a warp never bank-conflict.  (A warp-cooperative variant — one row at a time, REDUX for the
+// maximum — was measured 2x slower end to end: its votes/shuffles serialise on the critical path.)
 __device__ __noinline__ float tc_insert(float *sc_row, uint32_t *idx_row, int kc, float s, uint32_t id, float thr) {
     int pos = -1;
     float rest = -INFINITY;  // maximum of the slots that stay
 #pragma unroll 8
     for (int e = 0; e < kc; ++e) {
-        const float v = sc_row[e * TC_BM];
+        const float v = sc_row[e];
         const bool take = (pos < 0) && (v == thr);
         pos = take ? e : pos;
         rest = take ? rest : fmaxf(rest, v);
     }
     if (pos < 0) return thr;  // cannot happen: thr is the maximum of the list
-    sc_row[pos * TC_BM] = s;
-    idx_row[pos * TC_BM] = id;
+    sc_row[pos] = s;
+    idx_row[pos] = id;
     return fmaxf(rest, s);
 }
 
+// walk one group of 8 scores, only if some lane of the warp has a hit in it
 #define TC_WALK8(G)                                                                                   \
     if (__any_sync(0xffffffffu, g##G < thr)) {                                                        \
         _Pragma("unroll") for (int j = 0; j < 8; ++j) {                                               \
@@ -224,17 +256,21 @@ __device__ __forceinline__ float tc_min8(const uint32_t *v) {
     return fminf(m, __uint_as_float(v[7]));
 }
 
-// one 32-column chunk of one row against the row's threshold
+// one 32-column chunk of the warp's 32 rows against the rows' thresholds
 __device__ __forceinline__ float tc_select32(const uint32_t (&v)[32], float thr, int64_t ref0, int64_t M, float *sc_row,
                                              uint32_t *idx_row, int kc) {
     const float g0 = tc_min8(v), g1 = tc_min8(v + 8), g2 = tc_min8(v + 16), g3 = tc_min8(v + 24);
     const float m = fminf(fmin3(g0, g1, g2), g3);
+#ifndef TC_EXPERIMENT_NO_WALK
     if (__any_sync(0xffffffffu, m < thr)) {
         TC_WALK8(0)
         TC_WALK8(1)
         TC_WALK8(2)
         TC_WALK8(3)
     }
+#else
+    if (m < -1e30f) thr = m;
+#endif
     return thr;
 }
 
@@ -249,9 +285,10 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qpack, const unsigned char 
     const uint32_t tile_bytes = (uint32_t)tc_tile_bytes(kp);
     unsigned char *q_s = smraw;                                        // [TC_QT][tile_bytes]
     unsigned char *r_s = q_s + (size_t)TC_QT * tile_bytes;             // [stages][tile_bytes]
-    float *sc_s = (float *)(r_s + (size_t)stages * tile_bytes);        // [TC_QT][kc][TC_BM]
-    uint32_t *idx_s = (uint32_t *)(sc_s + (size_t)TC_QT * kc * TC_BM); // [TC_QT][kc][TC_BM]
-    uint64_t *bars = (uint64_t *)(idx_s + (size_t)TC_QT * kc * TC_BM);
+    const int ks = kc | 1;  // odd row stride: the 32 rows of a warp hit 32 different banks
+    float *sc_s = (float *)(r_s + (size_t)stages * tile_bytes);        // [TC_QT][TC_BM][ks]
+    uint32_t *idx_s = (uint32_t *)(sc_s + (size_t)TC_QT * ks * TC_BM); // [TC_QT][TC_BM][ks]
+    uint64_t *bars = (uint64_t *)(((uintptr_t)(idx_s + (size_t)TC_QT * ks * TC_BM) + 7) & ~(uintptr_t)7);
     uint64_t *q_full = bars;                      // 1
     uint64_t *r_full = bars + 1;                  // [TC_MAX_STAGES]
     uint64_t *r_empty = r_full + TC_MAX_STAGES;   // [TC_MAX_STAGES]
@@ -268,7 +305,7 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qpack, const unsigned char 
     if (threadIdx.x == 0) {
         mbar_init(q_full, 1);
         for (int i = 0; i < TC_MAX_STAGES; ++i) { mbar_init(&r_full[i], 1); mbar_init(&r_empty[i], 1); }
-        for (int i = 0; i < TC_ACC; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], TC_SEL_WARPS); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }  // [query tile][buffer]
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {  // TMEM: all 512 columns, owned by this warp
@@ -280,8 +317,8 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qpack, const unsigned char 
     if (warp >= 2) {  // selection threads initialise their row's list
         const int qt = (warp - 2) >> 2, row = (warp & 3) * 32 + lane;
         for (int e = 0; e < kc; ++e) {
-            sc_s[((size_t)qt * kc + e) * TC_BM + row] = INFINITY;
-            idx_s[((size_t)qt * kc + e) * TC_BM + row] = 0xffffffffu;
+            sc_s[((size_t)qt * TC_BM + row) * ks + e] = INFINITY;
+            idx_s[((size_t)qt * TC_BM + row) * ks + e] = 0xffffffffu;
         }
     }
     tc_fence_before();
@@ -298,47 +335,61 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qpack, const unsigned char 
                          q_full);
             for (int i = 0; i < ntiles; ++i) {
                 const int s = i % stages;
-                mbar_wait(&r_empty[s], ((i / stages) & 1) ^ 1);
+                mbar_wait_sleepy(&r_empty[s], ((i / stages) & 1) ^ 1);
                 mbar_arrive_expect_tx(&r_full[s], tile_bytes);
                 bulk_g2s(r_s + (size_t)s * tile_bytes, rpack + (size_t)(t_beg + i) * tile_bytes, tile_bytes, &r_full[s]);
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            mbar_wait(q_full, 0);
-            const uint32_t q_addr = smem_u32(q_s);
-            for (int i = 0; i < ntiles; ++i) {
-                const int s = i % stages, b = i % TC_ACC;
-                mbar_wait(&t_empty[b], ((i / TC_ACC) & 1) ^ 1);
-                mbar_wait(&r_full[s], (i / stages) & 1);
-                tc_fence_after();
-                const uint32_t r_addr = smem_u32(r_s + (size_t)s * tile_bytes);
+        // ===== MMA issuer: the whole warp walks the loop, one elected lane issues =====
+        mbar_wait(q_full, 0);
+        const uint64_t q_desc = umma_desc(smem_u32(q_s));
+        const uint32_t q_step = tile_bytes >> 4;          // descriptor address units (16 B) between query tiles
+        const int ksteps = kp / 16;
+        for (int i = 0; i < ntiles; ++i) {
+            const int s = i % stages, b = i % TC_ACC;
+            mbar_wait(&r_full[s], (i / stages) & 1);
+            const uint64_t r_desc = umma_desc(smem_u32(r_s + (size_t)s * tile_bytes));
 #pragma unroll
-                for (int q = 0; q < TC_QT; ++q) {
+            for (int q = 0; q < TC_QT; ++q) {
+                mbar_wait(&t_empty[q * TC_ACC + b], ((i / TC_ACC) & 1) ^ 1);
+                tc_fence_after();
+                if (elect_one()) {
+#ifndef TC_EXPERIMENT_NO_MMA
                     const uint32_t d_tmem = tmem_base + (uint32_t)((q * TC_ACC + b) * TC_BN);
-                    for (int k = 0; k < kp / 16; ++k)
-                        tc_mma_bf16(d_tmem, umma_desc(q_addr + q * tile_bytes + k * 4096), umma_desc(r_addr + k * 4096),
-                                    TC_IDESC, k > 0);
+                    const uint64_t a0 = q_desc + (uint64_t)(q * q_step);
+#pragma unroll 2
+                    for (int k = 0; k < ksteps; ++k)   // one K=16 slice = two k-units = 4096 B = 256 address units
+                        tc_mma_bf16(d_tmem, a0 + (uint64_t)(k * 256), r_desc + (uint64_t)(k * 256), TC_IDESC, k > 0);
+#endif
+                    tc_commit(&t_full[q * TC_ACC + b]);   // this query tile's accumulator is complete
                 }
-                tc_commit(&r_empty[s]);   // smem stage reusable once these MMAs have read it
-                tc_commit(&t_full[b]);    // both accumulators of buffer b complete
+                __syncwarp();
             }
+            if (elect_one()) tc_commit(&r_empty[s]);   // smem stage reusable once all these MMAs have read it
+            __syncwarp();
         }
     } else {
         // ===== selection =====
         const int qt = (warp - 2) >> 2, quad = warp & 3;
         const int row = quad * 32 + lane;
-        float *sc_row = sc_s + (size_t)qt * kc * TC_BM + row;
-        uint32_t *idx_row = idx_s + (size_t)qt * kc * TC_BM + row;
+        float *sc_row = sc_s + ((size_t)qt * TC_BM + row) * ks;       // this thread's row
+        uint32_t *idx_row = idx_s + ((size_t)qt * TC_BM + row) * ks;
         float thr = INFINITY;
+        uint64_t *my_full = t_full + qt * TC_ACC, *my_empty = t_empty + qt * TC_ACC;
         const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(qt * TC_ACC * TC_BN);
         for (int i = 0; i < ntiles; ++i) {
             const int b = i % TC_ACC;
-            mbar_wait(&t_full[b], (i / TC_ACC) & 1);
+            mbar_wait(&my_full[b], (i / TC_ACC) & 1);
             tc_fence_after();
             const int64_t ref0 = (int64_t)(t_beg + i) * TC_BN;
             const uint32_t acc = lane_base + (uint32_t)(b * TC_BN);
+#ifdef TC_EXPERIMENT_NO_SELECT
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(&my_empty[b]);
+            __syncwarp();
+            continue;
+#endif
             uint32_t va[32], vb[32];
             tc_ld32(acc, va);
             tc_wait_ld();
@@ -356,7 +407,7 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qpack, const unsigned char 
             tc_wait_ld();
             // every score of this accumulator is in registers: hand the TMEM buffer back early
             tc_fence_before();
-            if (lane == 0) mbar_arrive(&t_empty[b]);
+            if (lane == 0) mbar_arrive(&my_empty[b]);
             thr = tc_select32(vb, thr, ref0 + 96, M, sc_row, idx_row, kc);
             __syncwarp();
         }
@@ -364,9 +415,8 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qpack, const unsigned char 
         const int64_t n = ((int64_t)blockIdx.x * TC_QT + qt) * TC_BM + row;
         if (n < N) {
             for (int e = 0; e < kc; ++e) {
-                const uint32_t id = idx_row[e * TC_BM];
-                cand_out[(n * nsplit + split) * kc + e] =
-                    id == 0xffffffffu ? ~0ull : knn_make_key(sc_row[e * TC_BM], id);
+                const uint32_t id = idx_row[e];
+                cand_out[(n * nsplit + split) * kc + e] = id == 0xffffffffu ? ~0ull : knn_make_key(sc_row[e], id);
             }
             const int64_t split_refs = min(M, (int64_t)t_end * TC_BN) - (int64_t)t_beg * TC_BN;
             thr_out[n * nsplit + split] = split_refs <= kc ? INFINITY : thr;
@@ -456,7 +506,7 @@ TcPlan tc_plan(int64_t N, int64_t M, int d, int k) {
     size_t fixed = 0;
     int stages = 0;
     for (int qt = 2; qt >= 1; --qt) {
-        fixed = qt * tile + (size_t)qt * kc * TC_BM * 8 + 256 /* barriers */ + 1024 /* alignment slack */;
+        fixed = qt * tile + (size_t)qt * (kc | 1) * TC_BM * 8 + 256 /* barriers */ + 1024 /* alignment slack */;
         stages = budget > fixed ? (int)((budget - fixed) / tile) : 0;
         if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
         p.qt = qt;
