@@ -141,7 +141,8 @@ int sym_moe_apply(const float *Zin, int32_t ldzin, const float *R, int64_t N, in
  *   unsafe [N] uint8 or NULL: rows whose over-selection margin could not be certified
  *   (tensor-core scan only; the caller re-runs those rows with method 1).
  * sym_vote (predict / predict_proba): label[n] = lowest class code among the most frequent
- *   codes of the k neighbours; conf[n] = winning votes / k.
+ *   codes of the k neighbours; conf[n] = winning votes / k.  ref_codes [M]; entries of idx outside [0, M) are
+ *   ignored (label -1 if a row has no valid neighbour).
  */
 size_t sym_knn_packed_bytes(int64_t M, int32_t d);
 int sym_knn_fit(const float *Ref, int32_t ldr, int64_t M, int32_t d, void *packed, sym_stream_t stream);
@@ -149,7 +150,7 @@ size_t sym_knn_workspace(int64_t N, int64_t M, int32_t d, int32_t k, int32_t met
 int sym_knn(const float *Q, int32_t ldq, int64_t N, const float *Ref, int32_t ldr, int64_t M,
             const void *packed, int32_t d, int32_t k, int32_t method, int32_t *idx, float *dist2,
             uint8_t *unsafe, void *workspace, size_t workspace_bytes, sym_stream_t stream);
-int sym_vote(const int32_t *idx, int64_t N, int32_t k, const int32_t *ref_codes, int32_t *label,
+int sym_vote(const int32_t *idx, int64_t N, int32_t k, const int32_t *ref_codes, int64_t M, int32_t *label,
              float *conf, sym_stream_t stream);
 
 #ifdef __cplusplus

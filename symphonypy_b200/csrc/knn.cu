@@ -305,6 +305,12 @@ knn_rerank_kernel(const float *__restrict__ Q, int ldq, int64_t N, const float *
     const double rmax2 = (double)hdr->rmax2;
     const double eps = eps_rel * (2.0 * sqrt(qn) * sqrt(rmax2) + rmax2);
     int bad = 0;  // a recorded scan score further than eps from the exact score voids the certificate
+    int nvalid = 0;
+    for (int e = lane; e < k; e += 32) {  // slots that no candidate claims (fewer than k valid candidates) stay empty
+        idx_out[n * k + e] = -1;
+        dist_out[n * k + e] = INFINITY;
+    }
+    __syncwarp();
     for (int e = lane; e < ncand; e += 32) {
         const unsigned long long key = cand[n * ncand + e];
         const uint32_t id = (uint32_t)(key & 0xffffffffull);
@@ -322,6 +328,7 @@ knn_rerank_kernel(const float *__restrict__ Q, int ldq, int64_t N, const float *
             bad |= !(fabs((double)knn_key_score(key) - s_exact) <= eps);
             dist = fmax(qn + s_exact, 0.0);  // sklearn: ||x||^2 - 2 x.y + ||y||^2, clamped at 0
         }
+        nvalid += valid;
         wd[e] = dist;
         wi[e] = valid ? (int32_t)id : 0x7fffffff;
     }
@@ -335,8 +342,8 @@ knn_rerank_kernel(const float *__restrict__ Q, int ldq, int64_t N, const float *
             const double df = wd[f];
             rank += (df < de) || (df == de && wi[f] < ie);
         }
-        if (rank < k) {
-            idx_out[n * k + rank] = ie == 0x7fffffff ? -1 : ie;
+        if (rank < k && ie != 0x7fffffff) {
+            idx_out[n * k + rank] = ie;
             dist_out[n * k + rank] = (float)de;
         }
         if (rank == k - 1) kth = de;
@@ -348,6 +355,9 @@ knn_rerank_kernel(const float *__restrict__ Q, int ldq, int64_t N, const float *
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) kth = fmax(kth, __shfl_xor_sync(0xffffffffu, kth, o));
         bad = __any_sync(0xffffffffu, bad);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
+        bad |= nvalid < k;
         if (lane == 0) {
             double tmin = INFINITY;
             for (int s = 0; s < nsplit; ++s) tmin = fmin(tmin, (double)thr[n * nsplit + s]);
@@ -361,14 +371,14 @@ knn_rerank_kernel(const float *__restrict__ Q, int ldq, int64_t N, const float *
 // code (sklearn: classes_ sorted, argmax takes the first maximum); conf = votes / k.
 constexpr int VT_KMAX = 128;
 __global__ void __launch_bounds__(128)
-knn_vote_kernel(const int32_t *__restrict__ idx, int64_t N, int k, const int32_t *__restrict__ ref_codes,
+knn_vote_kernel(const int32_t *__restrict__ idx, int64_t N, int k, const int32_t *__restrict__ ref_codes, int64_t M,
                 int32_t *__restrict__ label, float *__restrict__ conf) {
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     int32_t code[VT_KMAX];
     for (int j = 0; j < k; ++j) {
         const int32_t id = idx[n * k + j];
-        code[j] = id >= 0 ? ref_codes[id] : -1;
+        code[j] = (id >= 0 && id < M) ? ref_codes[id] : -1;
     }
     int best = -1, bestc = 0;
     for (int j = 0; j < k; ++j) {
@@ -498,11 +508,11 @@ extern "C" int sym_knn(const float *Q, int32_t ldq, int64_t N, const float *Ref,
     return SYM_OK;
 }
 
-extern "C" int sym_vote(const int32_t *idx, int64_t N, int32_t k, const int32_t *ref_codes, int32_t *label,
+extern "C" int sym_vote(const int32_t *idx, int64_t N, int32_t k, const int32_t *ref_codes, int64_t M, int32_t *label,
                         float *conf, sym_stream_t stream) {
     SYM_REQUIRE(N >= 0 && k >= 1 && k <= VT_KMAX, SYM_ERR_INVALID_ARGUMENT, "sym_vote: bad sizes (k <= %d)", VT_KMAX);
     if (N == 0) return SYM_OK;
-    knn_vote_kernel<<<(unsigned)ceil_div(N, 128), 128, 0, (cudaStream_t)stream>>>(idx, N, k, ref_codes, label, conf);
+    knn_vote_kernel<<<(unsigned)ceil_div(N, 128), 128, 0, (cudaStream_t)stream>>>(idx, N, k, ref_codes, M, label, conf);
     SYM_LAUNCH_CHECK("knn_vote_kernel");
     return SYM_OK;
 }

@@ -22,6 +22,8 @@
 // and only on a hit walks the 32 values and updates the row's top-kc list in shared memory.
 // The scan over-selects (kc = k + 8); the float64 re-rank in knn.cu certifies the margin with the
 // scores recorded here and flags rows that need the FP32 scan.
+#include <stdlib.h>
+
 #include "knn_common.cuh"
 
 namespace sym {
@@ -30,7 +32,7 @@ constexpr int TC_BM = 128;        // query rows per CTA (UMMA M)
 constexpr int TC_BN = 128;        // reference rows per tile (UMMA N)
 // query tiles per CTA: QT = 2 (256 rows share every reference tile) when shared memory allows, else 1;
 // TMEM accumulator buffers per query tile: 4 / QT  (QT * ACC * 128 = 512 columns)
-constexpr int TC_MAX_STAGES = 4;
+constexpr int TC_MAX_STAGES = 6;
 constexpr int TC_PAD = 8;         // over-selection: kc = k + TC_PAD
 
 __host__ __device__ inline int tc_kp(int d) { return (3 * d + 3 + 15) / 16 * 16; }
@@ -98,6 +100,40 @@ tc_pack_kernel(const float *__restrict__ src, int ld, int64_t rows, int64_t rows
     w.z = out[4] | ((unsigned)out[5] << 16);
     w.w = out[6] | ((unsigned)out[7] << 16);
     *reinterpret_cast<uint4 *>(p) = w;
+}
+
+// Row-major BF16x3 query rows [rows_pad][kp] (the A operand lives in tensor memory: each selection thread
+// loads its own row).  One thread = one row x one k-unit, as above.
+__global__ void __launch_bounds__(256)
+tc_pack_rows_kernel(const float *__restrict__ src, int ld, int64_t rows, int64_t rows_pad, int d, int kp,
+                    unsigned char *__restrict__ dst) {
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;  // a warp walks the k-units of a row
+    if (r >= rows_pad) return;
+    const bool real = r < rows;
+    const float *x = src + r * ld;
+    for (int j = threadIdx.x % 32; j < kp / 8; j += 32) {
+        unsigned short out[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int kk = j * 8 + e;
+            unsigned short v = 0;
+            if (real && kk < 3 * d) {
+                const int seg = kk / d, c = kk - seg * d;
+                const float val = -2.f * x[c];
+                const unsigned short hi = bf16_rn(val);
+                v = seg == 2 ? bf16_rn(val - bf16_to_f(hi)) : hi;
+            } else if (real && kk < 3 * d + 3) {
+                v = 0x3f80;  // 1.0 against the three ||r||^2 pieces
+            }
+            out[e] = v;
+        }
+        uint4 w;
+        w.x = out[0] | ((unsigned)out[1] << 16);
+        w.y = out[2] | ((unsigned)out[3] << 16);
+        w.z = out[4] | ((unsigned)out[5] << 16);
+        w.w = out[6] | ((unsigned)out[7] << 16);
+        *reinterpret_cast<uint4 *>(dst + (size_t)r * kp * 2 + (size_t)j * 16) = w;
+    }
 }
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
@@ -177,6 +213,25 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, ui
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same, A operand from tensor memory (lane = row, 32-bit column c holds K elements 2c, 2c+1)
+__device__ __forceinline__ void tc_mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// registers -> tensor memory: 8 consecutive 32-bit columns of this thread's lane
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint4 &a, const uint4 &b) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(a.x),
+                 "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -209,32 +264,40 @@ constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((TC_BN >> 3)
 // ------------------------------------------------------------------------------------------ scan kernel
 // A CTA owns TC_QT query tiles (256 rows) and streams the reference tiles once for both.
 //   warp 0       : producer (cp.async.bulk of one packed tile per stage)
-//   warp 1       : TMEM owner + MMA issuer (TC_QT chains of kp/16 tcgen05.mma per reference tile)
-//   warps 2..9   : selection; warp w serves query tile (w-2)/4, TMEM lane quadrant w%4, thread <-> query row
+//   warps 1..QT  : MMA issuers, one per query tile (warp 1 also owns the TMEM allocation)
+//   warps 4..    : selection; warp w serves query tile (w-4)/4, TMEM lane quadrant w%4, thread <-> query row
 // TMEM: accumulator (query tile q, buffer b) lives at columns (q*TC_ACC + b)*128.
 //
 // Selection, per 32-column chunk: tcgen05.ld (issued one chunk ahead), four independent 3-input-min
 // chains over groups of 8, one compare against the row's kc-th best.  Only groups in which some lane
 // of the warp has a hit are walked, and a hit calls the (single, out-of-line) list update.
 
-// Replace the slot holding the row's current maximum `thr` by (s, id); returns the new maximum.  Every lane
-// updates ITS OWN row (lanes run in lock-step when several rows hit at once).  Row stride `ks` is odd, so the
-// 32 rows of a warp never bank-conflict.  (A warp-cooperative variant — one row at a time, REDUX for the
-// maximum — was measured 2x slower end to end: its votes/shuffles serialise on the critical path.)
+// The row's kc best (score, index) pairs form a binary MAX-HEAP in shared memory (root = the kc-th best = the
+// row's threshold).  A hit replaces the root and sifts down: ~log2(kc) levels of two loads and a compare,
+// instead of a pass over the whole list.  Every lane works on ITS OWN row (lanes run in lock-step when several
+// rows hit at once); the row stride `ks` is odd so the roots / equal levels of the 32 rows of a warp fall into
+// different banks.  Returns the new threshold.
+// (A warp-cooperative variant — one row at a time, REDUX for the maximum — was measured 2x slower end to end:
+// its votes and shuffles serialise on the critical path.)
 __device__ __noinline__ float tc_insert(float *sc_row, uint32_t *idx_row, int kc, float s, uint32_t id, float thr) {
-    int pos = -1;
-    float rest = -INFINITY;  // maximum of the slots that stay
-#pragma unroll 8
-    for (int e = 0; e < kc; ++e) {
-        const float v = sc_row[e];
-        const bool take = (pos < 0) && (v == thr);
-        pos = take ? e : pos;
-        rest = take ? rest : fmaxf(rest, v);
+    (void)thr;
+    int i = 0;
+    while (true) {
+        const int l = 2 * i + 1;
+        if (l >= kc) break;
+        const int r = l + 1;
+        const float vl = sc_row[l];
+        const float vr = r < kc ? sc_row[r] : -INFINITY;
+        const int c = vr > vl ? r : l;
+        const float vc = fmaxf(vl, vr);
+        if (!(vc > s)) break;
+        sc_row[i] = vc;
+        idx_row[i] = idx_row[c];
+        i = c;
     }
-    if (pos < 0) return thr;  // cannot happen: thr is the maximum of the list
-    sc_row[pos] = s;
-    idx_row[pos] = id;
-    return fmaxf(rest, s);
+    sc_row[i] = s;
+    idx_row[i] = id;
+    return sc_row[0];
 }
 
 // walk one group of 8 scores, only if some lane of the warp has a hit in it
@@ -275,37 +338,37 @@ __device__ __forceinline__ float tc_select32(const uint32_t (&v)[32], float thr,
 }
 
 template <int TC_QT>
-__global__ void __launch_bounds__(64 + 128 * TC_QT, 1)
-knn_scan_tc_kernel(const unsigned char *__restrict__ qpack, const unsigned char *__restrict__ rpack, int64_t N,
-                   int64_t M, int kp, int kc, int stages, int tiles_per_split, int ntiles_all,
+__global__ void __launch_bounds__(128 + 128 * TC_QT, 1)
+knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char *__restrict__ rpack, int64_t N,
+                   int64_t M, int kp, int kc, int stages, int nbuf, int tiles_per_split, int ntiles_all,
                    unsigned long long *__restrict__ cand_out, float *__restrict__ thr_out) {
-    constexpr int TC_ACC = 4 / TC_QT;
-    constexpr int TC_SEL_WARPS = 4 * TC_QT;
     extern __shared__ __align__(1024) unsigned char smraw[];
     const uint32_t tile_bytes = (uint32_t)tc_tile_bytes(kp);
-    unsigned char *q_s = smraw;                                        // [TC_QT][tile_bytes]
-    unsigned char *r_s = q_s + (size_t)TC_QT * tile_bytes;             // [stages][tile_bytes]
     const int ks = kc | 1;  // odd row stride: the 32 rows of a warp hit 32 different banks
+    unsigned char *r_s = smraw;                                        // [stages][tile_bytes]
     float *sc_s = (float *)(r_s + (size_t)stages * tile_bytes);        // [TC_QT][TC_BM][ks]
     uint32_t *idx_s = (uint32_t *)(sc_s + (size_t)TC_QT * ks * TC_BM); // [TC_QT][TC_BM][ks]
     uint64_t *bars = (uint64_t *)(((uintptr_t)(idx_s + (size_t)TC_QT * ks * TC_BM) + 7) & ~(uintptr_t)7);
-    uint64_t *q_full = bars;                      // 1
-    uint64_t *r_full = bars + 1;                  // [TC_MAX_STAGES]
+    uint64_t *r_full = bars;                      // [TC_MAX_STAGES]
     uint64_t *r_empty = r_full + TC_MAX_STAGES;   // [TC_MAX_STAGES]
-    uint64_t *t_full = r_empty + TC_MAX_STAGES;   // [4]
+    uint64_t *t_full = r_empty + TC_MAX_STAGES;   // [4]  accumulator buffers, used in rotation by all query tiles
     uint64_t *t_empty = t_full + 4;               // [4]
     uint32_t *tmem_slot = (uint32_t *)(t_empty + 4);
+    volatile uint32_t *turn = tmem_slot + 1;      // sequence number of the next chain allowed to issue
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int split = blockIdx.y, nsplit = gridDim.y;
     const int t_beg = split * tiles_per_split;
     const int t_end = min(ntiles_all, t_beg + tiles_per_split);
     const int ntiles = max(0, t_end - t_beg);
+    // tensor memory map: A operand of query tile q in columns [q*kp/2, (q+1)*kp/2); accumulator b at acc0 + b*128
+    const uint32_t a_cols = (uint32_t)(kp / 2);
+    const uint32_t acc0 = 512u - (uint32_t)nbuf * TC_BN;
 
     if (threadIdx.x == 0) {
-        mbar_init(q_full, 1);
-        for (int i = 0; i < TC_MAX_STAGES; ++i) { mbar_init(&r_full[i], 1); mbar_init(&r_empty[i], 1); }
-        for (int i = 0; i < 4; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }  // [query tile][buffer]
+        for (int i = 0; i < TC_MAX_STAGES; ++i) { mbar_init(&r_full[i], 1); mbar_init(&r_empty[i], TC_QT); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+        *turn = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {  // TMEM: all 512 columns, owned by this warp
@@ -314,8 +377,8 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qpack, const unsigned char 
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (warp >= 2) {  // selection threads initialise their row's list
-        const int qt = (warp - 2) >> 2, row = (warp & 3) * 32 + lane;
+    if (warp >= 4) {  // selection threads initialise their row's list
+        const int qt = (warp - 4) >> 2, row = (warp & 3) * 32 + lane;
         for (int e = 0; e < kc; ++e) {
             sc_s[((size_t)qt * TC_BM + row) * ks + e] = INFINITY;
             idx_s[((size_t)qt * TC_BM + row) * ks + e] = 0xffffffffu;
@@ -325,71 +388,97 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qpack, const unsigned char 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (warp >= 4) {
+        // park this thread's query row (BF16x3, kp values) in tensor memory: it is the A operand of every MMA
+        const int qt = (warp - 4) >> 2, quad = warp & 3;
+        const int64_t n = ((int64_t)blockIdx.x * TC_QT + qt) * TC_BM + quad * 32 + lane;
+        const uint4 *src = reinterpret_cast<const uint4 *>(qrows + (size_t)n * kp * 2);
+        const uint32_t dst = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)qt * a_cols;
+        for (int k = 0; k < kp / 16; ++k) tc_st8(dst + k * 8, __ldg(src + 2 * k), __ldg(src + 2 * k + 1));
+        tc_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
 
     if (warp == 0) {
-        // ===== producer =====
+        // ===== producer: one bulk copy per reference tile =====
         if (lane == 0) {
-            mbar_arrive_expect_tx(q_full, TC_QT * tile_bytes);
-            for (int q = 0; q < TC_QT; ++q)
-                bulk_g2s(q_s + (size_t)q * tile_bytes, qpack + ((size_t)blockIdx.x * TC_QT + q) * tile_bytes, tile_bytes,
-                         q_full);
+            int s = 0;
+            uint32_t ph = 0;  // ring position and phase kept incrementally: no integer division on any per-tile path
             for (int i = 0; i < ntiles; ++i) {
-                const int s = i % stages;
-                mbar_wait_sleepy(&r_empty[s], ((i / stages) & 1) ^ 1);
+                mbar_wait_sleepy(&r_empty[s], ph ^ 1);
                 mbar_arrive_expect_tx(&r_full[s], tile_bytes);
                 bulk_g2s(r_s + (size_t)s * tile_bytes, rpack + (size_t)(t_beg + i) * tile_bytes, tile_bytes, &r_full[s]);
+                if (++s == stages) { s = 0; ph ^= 1; }
             }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer: the whole warp walks the loop, one elected lane issues =====
-        mbar_wait(q_full, 0);
-        const uint64_t q_desc = umma_desc(smem_u32(q_s));
-        const uint32_t q_step = tile_bytes >> 4;          // descriptor address units (16 B) between query tiles
+    } else if (warp <= TC_QT) {
+        // ===== MMA issuers: warp 1+q issues the chains of query tile q.  One warp's serial instruction stream
+        // (barrier poll, descriptor moves, 6 UTCHMMA, commit) costs about as much as the 6 MMAs take to
+        // execute, so each query tile gets its own issuer and the two streams overlap.  Chains are still
+        // ISSUED in sequence order (tile i: q0, q1; tile i+1: q0, ...) via the `turn` counter: the tensor
+        // pipe completes them in that order, which is what lets all query tiles rotate through one set of
+        // accumulators (a parity wait on a buffer's barrier is only unambiguous if its uses complete in order). =====
+        const int q = warp - 1;
         const int ksteps = kp / 16;
+        const bool leader = elect_one();
+        int buf = q % nbuf, use = q / nbuf;  // chain (tile i, query tile q) = sequence number i*QT + q
+        int s = 0;
+        uint32_t ph = 0;
+        const uint64_t r_desc0 = umma_desc(smem_u32(r_s));
+        const uint32_t r_step = tile_bytes >> 4;
+        const uint32_t a_tmem = tmem_base + (uint32_t)q * a_cols;
         for (int i = 0; i < ntiles; ++i) {
-            const int s = i % stages, b = i % TC_ACC;
-            mbar_wait(&r_full[s], (i / stages) & 1);
-            const uint64_t r_desc = umma_desc(smem_u32(r_s + (size_t)s * tile_bytes));
-#pragma unroll
-            for (int q = 0; q < TC_QT; ++q) {
-                mbar_wait(&t_empty[q * TC_ACC + b], ((i / TC_ACC) & 1) ^ 1);
-                tc_fence_after();
-                if (elect_one()) {
-#ifndef TC_EXPERIMENT_NO_MMA
-                    const uint32_t d_tmem = tmem_base + (uint32_t)((q * TC_ACC + b) * TC_BN);
-                    const uint64_t a0 = q_desc + (uint64_t)(q * q_step);
-#pragma unroll 2
-                    for (int k = 0; k < ksteps; ++k)   // one K=16 slice = two k-units = 4096 B = 256 address units
-                        tc_mma_bf16(d_tmem, a0 + (uint64_t)(k * 256), r_desc + (uint64_t)(k * 256), TC_IDESC, k > 0);
-#endif
-                    tc_commit(&t_full[q * TC_ACC + b]);   // this query tile's accumulator is complete
-                }
-                __syncwarp();
+            mbar_wait(&r_full[s], ph);
+            mbar_wait(&t_empty[buf], (use & 1) ^ 1);
+            if (TC_QT > 1) {
+                const uint32_t seq = (uint32_t)(i * TC_QT + q);
+                while (*turn != seq) {}
             }
-            if (elect_one()) tc_commit(&r_empty[s]);   // smem stage reusable once all these MMAs have read it
+            tc_fence_after();
+            if (leader) {
+#ifndef TC_EXPERIMENT_NO_MMA
+                const uint64_t r_desc = r_desc0 + (uint64_t)((uint32_t)s * r_step);
+                const uint32_t d_tmem = tmem_base + acc0 + (uint32_t)(buf * TC_BN);
+#pragma unroll 2
+                for (int k = 0; k < ksteps; ++k)   // one K=16 slice: 8 TMEM columns of A, 4096 B (256 units) of B
+                    tc_mma_bf16_ts(d_tmem, a_tmem + (uint32_t)(k * 8), r_desc + (uint64_t)(k * 256), TC_IDESC, k > 0);
+#endif
+                tc_commit(&t_full[buf]);    // this chain's accumulator is complete
+                tc_commit(&r_empty[s]);     // and this issuer is done with the shared-memory stage
+                if (TC_QT > 1) *turn = (uint32_t)(i * TC_QT + q) + 1u;
+            }
             __syncwarp();
+            if (++s == stages) { s = 0; ph ^= 1; }
+            buf += TC_QT;
+            while (buf >= nbuf) { buf -= nbuf; ++use; }
         }
+    } else if (warp < 4) {
+        // spare warp(s): nothing to do until the final barrier
     } else {
         // ===== selection =====
-        const int qt = (warp - 2) >> 2, quad = warp & 3;
+        const int qt = (warp - 4) >> 2, quad = warp & 3;
         const int row = quad * 32 + lane;
         float *sc_row = sc_s + ((size_t)qt * TC_BM + row) * ks;       // this thread's row
         uint32_t *idx_row = idx_s + ((size_t)qt * TC_BM + row) * ks;
         float thr = INFINITY;
-        uint64_t *my_full = t_full + qt * TC_ACC, *my_empty = t_empty + qt * TC_ACC;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(qt * TC_ACC * TC_BN);
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + acc0;
+        int buf = qt % nbuf, use = qt / nbuf;   // chain (i, qt) = sequence number i*QT + qt
         for (int i = 0; i < ntiles; ++i) {
-            const int b = i % TC_ACC;
-            mbar_wait(&my_full[b], (i / TC_ACC) & 1);
+#ifdef TC_SLEEPY_SELECT
+            mbar_wait_sleepy(&t_full[buf], use & 1);
+#else
+            mbar_wait(&t_full[buf], use & 1);
+#endif
             tc_fence_after();
             const int64_t ref0 = (int64_t)(t_beg + i) * TC_BN;
-            const uint32_t acc = lane_base + (uint32_t)(b * TC_BN);
+            const uint32_t acc = lane_base + (uint32_t)(buf * TC_BN);
 #ifdef TC_EXPERIMENT_NO_SELECT
             tc_fence_before();
-            if (lane == 0) mbar_arrive(&my_empty[b]);
+            if (lane == 0) mbar_arrive(&t_empty[buf]);
             __syncwarp();
-            continue;
-#endif
+#else
             uint32_t va[32], vb[32];
             tc_ld32(acc, va);
             tc_wait_ld();
@@ -407,9 +496,13 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qpack, const unsigned char 
             tc_wait_ld();
             // every score of this accumulator is in registers: hand the TMEM buffer back early
             tc_fence_before();
-            if (lane == 0) mbar_arrive(&my_empty[b]);
+            if (lane == 0) mbar_arrive(&t_empty[buf]);
             thr = tc_select32(vb, thr, ref0 + 96, M, sc_row, idx_row, kc);
             __syncwarp();
+#endif
+            // advance the rotation by TC_QT chains
+            buf += TC_QT;
+            while (buf >= nbuf) { buf -= nbuf; ++use; }
         }
         // results: the row's candidates as (score, index) keys (unordered) and its final threshold
         const int64_t n = ((int64_t)blockIdx.x * TC_QT + qt) * TC_BM + row;
@@ -434,7 +527,7 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qpack, const unsigned char 
 // One query tile x one reference tile: dumps the 128x128 FP32 accumulator (test-only entry point).
 __global__ void __launch_bounds__(128, 1)
 tc_debug_kernel(const unsigned char *__restrict__ qpack, const unsigned char *__restrict__ rpack, int kp,
-                float *__restrict__ out) {
+                float *__restrict__ out, const unsigned char *__restrict__ qrows) {
     extern __shared__ __align__(1024) unsigned char smraw[];
     const uint32_t tile_bytes = (uint32_t)tc_tile_bytes(kp);
     unsigned char *q_s = smraw, *r_s = smraw + tile_bytes;
@@ -448,7 +541,7 @@ tc_debug_kernel(const unsigned char *__restrict__ qpack, const unsigned char *__
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
-                     "r"(128u)
+                     "r"(512u)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -456,15 +549,28 @@ tc_debug_kernel(const unsigned char *__restrict__ qpack, const unsigned char *__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
+    if (qrows != nullptr) {  // TS form: every thread parks its own query row in tensor memory columns [256, 256 + kp/2)
+        const uint4 *src = reinterpret_cast<const uint4 *>(qrows + (size_t)threadIdx.x * kp * 2);
+        for (int k = 0; k < kp / 16; ++k)
+            tc_st8(tmem_base + ((uint32_t)(warp * 32) << 16) + 256 + k * 8, src[2 * k], src[2 * k + 1]);
+        tc_wait_st();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
     if (threadIdx.x == 0) {
         mbar_arrive_expect_tx(&full, 2 * tile_bytes);
         bulk_g2s(q_s, qpack, tile_bytes, &full);
         bulk_g2s(r_s, rpack, tile_bytes, &full);
         mbar_wait(&full, 0);
         tc_fence_after();
-        for (int k = 0; k < kp / 16; ++k)
-            tc_mma_bf16(tmem_base, umma_desc(smem_u32(q_s) + k * 4096), umma_desc(smem_u32(r_s) + k * 4096), TC_IDESC,
-                        k > 0);
+        for (int k = 0; k < kp / 16; ++k) {
+            if (qrows != nullptr)
+                tc_mma_bf16_ts(tmem_base, tmem_base + 256 + k * 8, umma_desc(smem_u32(r_s) + k * 4096), TC_IDESC, k > 0);
+            else
+                tc_mma_bf16(tmem_base, umma_desc(smem_u32(q_s) + k * 4096), umma_desc(smem_u32(r_s) + k * 4096), TC_IDESC,
+                            k > 0);
+        }
         tc_commit(&done);
     }
     __syncwarp();
@@ -482,14 +588,14 @@ tc_debug_kernel(const unsigned char *__restrict__ qpack, const unsigned char *__
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
 // ------------------------------------------------------------------------------------------ host side
 namespace {
 struct TcPlan {
-    int kp, kc, qt, stages, nsplit, tiles_per_split, ntiles;
+    int kp, kc, qt, stages, nbuf, nsplit, tiles_per_split, ntiles;
     int64_t qtiles;
     size_t smem, qpack_bytes, cand_bytes, thr_bytes;
     bool ok;
@@ -505,15 +611,20 @@ TcPlan tc_plan(int64_t N, int64_t M, int d, int k) {
     const size_t budget = 227 * 1024;
     size_t fixed = 0;
     int stages = 0;
-    for (int qt = 2; qt >= 1; --qt) {
-        fixed = qt * tile + (size_t)qt * (kc | 1) * TC_BM * 8 + 256 /* barriers */ + 1024 /* alignment slack */;
+    const char *force_qt = getenv("SYM_TC_QT");      // tuning / experiments only
+    const char *force_nbuf = getenv("SYM_TC_NBUF");
+    for (int qt = force_qt ? atoi(force_qt) : 2; qt >= 1; --qt) {
+        fixed = (size_t)qt * (kc | 1) * TC_BM * 8 + 256 /* barriers */ + 1024 /* alignment slack */;
         stages = budget > fixed ? (int)((budget - fixed) / tile) : 0;
         if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
         p.qt = qt;
-        if (stages >= 2) break;
+        p.nbuf = (512 - qt * p.kp / 2) / TC_BN;  // accumulators that fit beside the A operands in tensor memory
+        if (p.nbuf > 4) p.nbuf = 4;
+        if (force_nbuf && atoi(force_nbuf) >= 1 && atoi(force_nbuf) <= p.nbuf) p.nbuf = atoi(force_nbuf);
+        if (stages >= 3 && p.nbuf >= 2) break;
     }
     p.stages = stages;
-    p.ok = stages >= 2 && p.kp <= 256 && d <= 84;
+    p.ok = stages >= 2 && p.nbuf >= 1 && p.kp <= 256 && d <= 84;
     p.smem = fixed + (size_t)(stages > 0 ? stages : 0) * tile;
     if (p.smem < 120 * 1024) p.smem = 120 * 1024;  // one CTA per SM: a CTA owns all 512 TMEM columns
     p.qtiles = ceil_div(N, TC_BM * p.qt);  // CTAs along the query
@@ -529,7 +640,7 @@ TcPlan tc_plan(int64_t N, int64_t M, int d, int k) {
     }
     p.tiles_per_split = (int)ceil_div(p.ntiles, nsplit);
     p.nsplit = (int)ceil_div(p.ntiles, p.tiles_per_split);
-    p.qpack_bytes = (size_t)p.qtiles * p.qt * tile;
+    p.qpack_bytes = (size_t)p.qtiles * p.qt * TC_BM * p.kp * 2;  // row-major BF16x3 query rows
     p.cand_bytes = ((size_t)N * p.nsplit * kc * 8 + 255) & ~(size_t)255;
     p.thr_bytes = ((size_t)N * p.nsplit * 4 + 255) & ~(size_t)255;
     return p;
@@ -575,18 +686,17 @@ int knn_tc_scan(const float *Q, int ldq, int64_t N, KnnPacked pk, int64_t M, int
     float *thr_w = (float *)w;
     {
         const int64_t rows_pad = p.qtiles * p.qt * TC_BM;
-        dim3 grid((unsigned)ceil_div(rows_pad, 256), (unsigned)(p.kp / 8));
-        tc_pack_kernel<<<grid, 256, 0, st>>>(Q, ldq, N, rows_pad, d, p.kp, 1, qpack);
-        SYM_LAUNCH_CHECK("tc_pack_kernel(query)");
+        tc_pack_rows_kernel<<<(unsigned)ceil_div(rows_pad, 8), 256, 0, st>>>(Q, ldq, N, rows_pad, d, p.kp, qpack);
+        SYM_LAUNCH_CHECK("tc_pack_rows_kernel(query)");
     }
     dim3 grid((unsigned)p.qtiles, (unsigned)p.nsplit);
     if (p.qt == 2) {
         SYM_CUDA(cudaFuncSetAttribute(knn_scan_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-        knn_scan_tc_kernel<2><<<grid, 64 + 128 * 2, p.smem, st>>>(qpack, pk.tc, N, M, p.kp, p.kc, p.stages,
+        knn_scan_tc_kernel<2><<<grid, 128 + 128 * 2, p.smem, st>>>(qpack, pk.tc, N, M, p.kp, p.kc, p.stages, p.nbuf,
                                                                   p.tiles_per_split, p.ntiles, cand_w, thr_w);
     } else {
         SYM_CUDA(cudaFuncSetAttribute(knn_scan_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-        knn_scan_tc_kernel<1><<<grid, 64 + 128 * 1, p.smem, st>>>(qpack, pk.tc, N, M, p.kp, p.kc, p.stages,
+        knn_scan_tc_kernel<1><<<grid, 128 + 128 * 1, p.smem, st>>>(qpack, pk.tc, N, M, p.kp, p.kc, p.stages, p.nbuf,
                                                                   p.tiles_per_split, p.ntiles, cand_w, thr_w);
     }
     SYM_LAUNCH_CHECK("knn_scan_tc_kernel");
@@ -602,9 +712,9 @@ int knn_tc_scan(const float *Q, int ldq, int64_t N, KnnPacked pk, int64_t M, int
 }  // namespace sym
 
 // Test-only: scores of the first query tile against the first reference tile, through the same packing,
-// descriptors and MMA chain as the scan.  Q [<=128, d], Ref [<=128, d] -> out [128,128]; scratch >= 2 tiles.
+// descriptors and MMA chain as the scan.  Q [<=128, d], Ref [<=128, d] -> out [128,128]; scratch >= 3 tiles.
 extern "C" int sym_debug_tc_scores(const float *Q, int32_t nq, const float *Ref, int32_t nr, int32_t d, float *out,
-                                   void *scratch, sym_stream_t stream) {
+                                   void *scratch, sym_stream_t stream, int32_t a_in_tmem) {
     using namespace sym;
     SYM_REQUIRE(nq > 0 && nq <= 128 && nr > 0 && nr <= 128 && d > 0 && d <= 84, SYM_ERR_INVALID_ARGUMENT,
                 "sym_debug_tc_scores: bad sizes");
@@ -616,9 +726,14 @@ extern "C" int sym_debug_tc_scores(const float *Q, int32_t nq, const float *Ref,
     SYM_LAUNCH_CHECK("tc_pack_kernel");
     tc_pack_kernel<<<grid, 256, 0, st>>>(Ref, d, nr, 128, d, kp, 0, rp);
     SYM_LAUNCH_CHECK("tc_pack_kernel");
+    unsigned char *qrows = rp + tc_tile_bytes(kp);
+    if (a_in_tmem) {
+        tc_pack_rows_kernel<<<16, 256, 0, st>>>(Q, d, nq, 128, d, kp, qrows);
+        SYM_LAUNCH_CHECK("tc_pack_rows_kernel");
+    }
     const size_t smem = 2 * tc_tile_bytes(kp) + 1024;
     SYM_CUDA(cudaFuncSetAttribute(tc_debug_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_debug_kernel<<<1, 128, smem, st>>>(qp, rp, kp, out);
+    tc_debug_kernel<<<1, 128, smem, st>>>(qp, rp, kp, out, a_in_tmem ? qrows : nullptr);
     SYM_LAUNCH_CHECK("tc_debug_kernel");
     return SYM_OK;
 }

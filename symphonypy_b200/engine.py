@@ -7,6 +7,7 @@ torch stream of the tensor's device.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -250,7 +251,7 @@ def knn_search_certified(index: KnnIndex, Q: torch.Tensor, k: int, method: int =
     re-run with the FP32 FFMA scan.  Returns (idx, dist2, n_repaired)."""
     idx, dist2, unsafe = knn_search(index, Q, k, method)
     n_bad = int(unsafe.sum().item())
-    if n_bad:
+    if n_bad and os.environ.get("SYM_KNN_NO_REPAIR") != "1":  # (the switch exists for kernel timing experiments only)
         rows = torch.nonzero(unsafe, as_tuple=False).flatten()
         i2, d2, _ = knn_search(index, Q[rows].contiguous(), k, KNN_FFMA)
         idx[rows] = i2
@@ -266,6 +267,7 @@ def vote(idx: torch.Tensor, ref_codes: torch.Tensor, want_conf: bool = True):
     label = torch.empty(N, device=dev, dtype=torch.int32)
     conf = torch.empty(N, device=dev, dtype=torch.float32) if want_conf else None
     assert ref_codes.dtype == torch.int32 and idx.is_contiguous()
-    _lib.check(lib.sym_vote(idx.data_ptr(), N, k, ref_codes.data_ptr(), label.data_ptr(), _ptr(conf), _stream(dev)),
+    _lib.check(lib.sym_vote(idx.data_ptr(), N, k, ref_codes.data_ptr(), ref_codes.numel(), label.data_ptr(), _ptr(conf),
+                            _stream(dev)),
                "sym_vote")
     return label, conf

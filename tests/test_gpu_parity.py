@@ -365,14 +365,14 @@ def test_tc_score_tile(cuda_device, built_library):
 
     lib = ctypes.CDLL(built_library)
     rng = np.random.default_rng(0)
-    for d in (20, 30, 50, 7):
+    for d, a_in_tmem in [(20, 0), (30, 0), (50, 0), (7, 0), (20, 1), (30, 1), (50, 1), (7, 1)]:
         q = (rng.normal(size=(100, d)) * 3).astype(np.float32)
         r = (rng.normal(size=(128, d)) * 3).astype(np.float32)
         Q, R = torch.from_numpy(q).to(cuda_device), torch.from_numpy(r).to(cuda_device)
         out = torch.zeros((128, 128), device=cuda_device)
-        scratch = torch.zeros(2 * 256 * 256 + 1024, dtype=torch.uint8, device=cuda_device)
+        scratch = torch.zeros(3 * 256 * 256 + 1024, dtype=torch.uint8, device=cuda_device)
         rc = lib.sym_debug_tc_scores(ctypes.c_void_p(Q.data_ptr()), 100, ctypes.c_void_p(R.data_ptr()), 128, d,
-                                     ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(scratch.data_ptr()), None)
+                                     ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(scratch.data_ptr()), None, a_in_tmem)
         assert rc == 0
         torch.cuda.synchronize()
         got = out.cpu().numpy()[:100]

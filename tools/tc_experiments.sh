@@ -1,7 +1,8 @@
 #!/bin/bash
 # Rebuild the library with each experiment define and time the kNN stage (config2).
+export SYM_KNN_NO_REPAIR=1
 for DEF in "-DTC_EXPERIMENT_NO_SELECT" "-DTC_EXPERIMENT_NO_MMA -DTC_EXPERIMENT_NO_WALK" "-DTC_EXPERIMENT_NO_WALK" ""; do
   SYM_NVCC_EXTRA="$DEF" python -m symphonypy_b200.build --force > /dev/null 2>&1
   echo "== $DEF"
-  timeout 300 python bench.py --steps 3 --warmup 2 --no-cpu --no-e2e 2>&1 | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('knn ms', d['stage_ms']['knn'])"
+  timeout 300 python bench.py --steps 3 --warmup 2 --no-cpu --no-e2e $* 2>&1 | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('knn ms', d['stage_ms']['knn'])"
 done
