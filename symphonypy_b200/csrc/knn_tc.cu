@@ -479,25 +479,20 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
             if (lane == 0) mbar_arrive(&t_empty[buf]);
             __syncwarp();
 #else
-            uint32_t va[32], vb[32];
-            tc_ld32(acc, va);
+            // pull the whole 128-column accumulator row into registers and hand the TMEM buffer straight back:
+            // the next chain can then run while this tile is examined (the buffer is held for one load latency)
+            uint32_t v0[32], v1[32], v2[32], v3[32];
+            tc_ld32(acc, v0);
+            tc_ld32(acc + 32, v1);
+            tc_ld32(acc + 64, v2);
+            tc_ld32(acc + 96, v3);
             tc_wait_ld();
-            tc_ld32(acc + 32, vb);                       // in flight while chunk 0 is examined
-            thr = tc_select32(va, thr, ref0, M, sc_row, idx_row, kc);
-            __syncwarp();
-            tc_wait_ld();
-            tc_ld32(acc + 64, va);
-            thr = tc_select32(vb, thr, ref0 + 32, M, sc_row, idx_row, kc);
-            __syncwarp();
-            tc_wait_ld();
-            tc_ld32(acc + 96, vb);
-            thr = tc_select32(va, thr, ref0 + 64, M, sc_row, idx_row, kc);
-            __syncwarp();
-            tc_wait_ld();
-            // every score of this accumulator is in registers: hand the TMEM buffer back early
             tc_fence_before();
             if (lane == 0) mbar_arrive(&t_empty[buf]);
-            thr = tc_select32(vb, thr, ref0 + 96, M, sc_row, idx_row, kc);
+            thr = tc_select32(v0, thr, ref0, M, sc_row, idx_row, kc);
+            thr = tc_select32(v1, thr, ref0 + 32, M, sc_row, idx_row, kc);
+            thr = tc_select32(v2, thr, ref0 + 64, M, sc_row, idx_row, kc);
+            thr = tc_select32(v3, thr, ref0 + 96, M, sc_row, idx_row, kc);
             __syncwarp();
 #endif
             // advance the rotation by TC_QT chains
