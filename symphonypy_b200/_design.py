@@ -16,9 +16,9 @@ from . import _dist
 def batch_codes(adata_query, key):
     """Returns (codes [V, N] int32, level names per variable)."""
     n = len(adata_query)
-    if key is None:  # tl.py:368-369: one constant column "batch" = "1"
-        cols = [np.full(n, "1", dtype=object)]
-    elif isinstance(key, str):
+    if key is None:  # tl.py:368-369: one constant column "batch" = "1" -> a single level, code 0 everywhere
+        return np.zeros((1, n), dtype=np.int32), _dist.union_levels([["1"]])
+    if isinstance(key, str):
         cols = [np.asarray(adata_query.obs[key].astype(str), dtype=object)]
     else:
         cols = [np.asarray(adata_query.obs[k].astype(str), dtype=object) for k in key]

@@ -300,9 +300,10 @@ __device__ __noinline__ float tc_insert(float *sc_row, uint32_t *idx_row, int kc
     return sc_row[0];
 }
 
-// walk one group of 8 scores, only if some lane of the warp has a hit in it
+// walk one group of 8 scores of a lane that has a hit in it (plain divergent branches: when no lane of the
+// warp hits, the hardware skips the block at the cost of one predicated branch — cheaper than a vote)
 #define TC_WALK8(G)                                                                                   \
-    if (__any_sync(0xffffffffu, g##G < thr)) {                                                        \
+    if (g##G < thr) {                                                                                 \
         _Pragma("unroll") for (int j = 0; j < 8; ++j) {                                               \
             const float sv = __uint_as_float(v[(G) * 8 + j]);                                         \
             if (sv < thr) {                                                                           \
@@ -325,7 +326,7 @@ __device__ __forceinline__ float tc_select32(const uint32_t (&v)[32], float thr,
     const float g0 = tc_min8(v), g1 = tc_min8(v + 8), g2 = tc_min8(v + 16), g3 = tc_min8(v + 24);
     const float m = fminf(fmin3(g0, g1, g2), g3);
 #ifndef TC_EXPERIMENT_NO_WALK
-    if (__any_sync(0xffffffffu, m < thr)) {
+    if (m < thr) {
         TC_WALK8(0)
         TC_WALK8(1)
         TC_WALK8(2)

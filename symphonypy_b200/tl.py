@@ -222,10 +222,49 @@ def _inv_sigma(sigma, K: int, dev) -> torch.Tensor:
     return torch.from_numpy((1.0 / s.astype(np.float64)).astype(np.float32)).to(dev)
 
 
+class _PinnedPool:
+    """Page-locked host buffers for results.  A device->host copy into pageable memory runs at a few GB/s;
+    into pinned memory it runs at PCIe speed and asynchronously.  The numpy arrays handed to the user are
+    views of pool buffers; a buffer goes back to the pool when its array is garbage collected."""
+
+    def __init__(self):
+        self.free: dict[int, list] = {}
+
+    def take(self, nbytes: int) -> torch.Tensor:
+        size = 1 << max(12, int(nbytes - 1).bit_length())  # power-of-two size classes
+        bucket = self.free.get(size)
+        if bucket:
+            return bucket.pop()
+        return torch.empty(size, dtype=torch.uint8).pin_memory()
+
+    def give(self, buf: torch.Tensor) -> None:
+        bucket = self.free.setdefault(buf.numel(), [])
+        if len(bucket) < 4:
+            bucket.append(buf)
+
+
+_POOL = _PinnedPool()
+
+
+def _to_host_async(t: torch.Tensor) -> np.ndarray:
+    """Starts a D2H copy of `t` on the current stream into pinned memory and returns the numpy view;
+    the caller synchronises the stream before handing the array out."""
+    t = t.contiguous()
+    nbytes = t.numel() * t.element_size()
+    if nbytes == 0:
+        return np.empty(tuple(t.shape), dtype=np.float32 if t.dtype == torch.float32 else np.int32)
+    buf = _POOL.take(nbytes)
+    host = buf[:nbytes].view(t.dtype).view(t.shape)
+    host.copy_(t, non_blocking=True)
+    arr = host.numpy()
+    weakref.finalize(arr, _POOL.give, buf)
+    return arr
+
+
 def _to_host(t: torch.Tensor) -> np.ndarray:
-    out = torch.empty(t.shape, dtype=t.dtype, device="cpu")
-    out.copy_(t)  # D2H on the current stream, synchronous for pageable destinations
-    return out.numpy()
+    arr = _to_host_async(t)
+    torch.cuda.current_stream(t.device).synchronize()
+    return arr
 
 
 def map_embedding(
@@ -292,13 +331,14 @@ def map_embedding(
         pipeline.check_solve(info)
 
         # 4. results back into the AnnData, as the reference does (`tl.py:394-397`, `_utils.py:306`)
-        z_h, zc_h = _to_host(Z), _to_host(Zc)
+        z_h, zc_h = _to_host_async(Z), _to_host_async(Zc)
+        r_h = _to_host_async(R) if settings.store_R else None
+        torch.cuda.current_stream(dev).synchronize()
         adata_query.obsm[transferred_primary_basis] = z_h
         adata_query.obsm[transferred_adjusted_basis] = zc_h
         _remember(z_h, Z)
         _remember(zc_h, Zc)
-        if settings.store_R:
-            r_h = _to_host(R)
+        if r_h is not None:
             adata_query.obsm[f"{transferred_adjusted_basis}_symphony_R"] = r_h
             _remember(r_h, R)
 
@@ -342,12 +382,30 @@ def _knn_params(args, kwargs) -> dict:
 def _label_columns(adata_ref, ref_labels):
     y = adata_ref.obs[ref_labels]
     if isinstance(y, pd.DataFrame):
-        cols = [np.asarray(y[c]) for c in y.columns]
-        two_d = True
-    else:
-        cols = [np.asarray(y)]
-        two_d = False
-    return cols, two_d
+        return [y[c] for c in y.columns], True
+    return [y], False
+
+
+def _encode_labels(adata_ref, col: pd.Series, dev):
+    """sklearn's `classes_` (sorted unique labels) and the integer code of every reference cell, on the
+    device.  Cached per reference: encoding 500k strings costs more than the whole GPU search.  The cache key
+    carries a fingerprint of the column (length + hash of ~1k evenly spaced values) so edits are noticed."""
+    n = len(col)
+    probe = col.iloc[:: max(1, n // 1024)]
+    fp = (n, int(pd.util.hash_pandas_object(probe, index=False).sum()))
+
+    def build():
+        values = np.asarray(col)
+        try:
+            inv, classes = pd.factorize(values, sort=True)
+            classes = np.asarray(classes)
+            if (inv < 0).any():
+                raise ValueError("missing labels")
+        except (TypeError, ValueError):
+            classes, inv = np.unique(values, return_inverse=True)
+        return classes, torch.from_numpy(inv.astype(np.int32)).to(dev)
+
+    return _cached(("labels", id(adata_ref), col.name, fp, str(dev)), adata_ref, build)
 
 
 def transfer_labels_kNN(
@@ -394,15 +452,14 @@ def transfer_labels_kNN(
             logger.debug("kNN: %d query rows re-run with the FP32 scan", n_repaired)
         preds, confs = [], []
         for col in label_cols:
-            classes, inv = np.unique(col, return_inverse=True)  # sklearn: classes_ = sorted unique labels
-            codes = torch.from_numpy(inv.astype(np.int32)).to(dev)
+            classes, codes = _encode_labels(adata_ref, col, dev)  # sklearn: classes_ = sorted unique labels
             lab, conf = engine.vote(idx, codes, want_conf=confidence_key is not None)
-            preds.append(classes[lab.cpu().numpy()])
+            preds.append(classes[_to_host(lab)])
             if conf is not None:
-                confs.append(conf.cpu().numpy())
+                confs.append(_to_host(conf))
         if neighbors_key is not None:
-            adata_query.obsm[neighbors_key + "_indices"] = idx.cpu().numpy()
-            adata_query.obsm[neighbors_key + "_sqdist"] = dist2.cpu().numpy()
+            adata_query.obsm[neighbors_key + "_indices"] = _to_host(idx)
+            adata_query.obsm[neighbors_key + "_sqdist"] = _to_host(dist2)
 
     labels_pred = np.stack(preds, axis=1) if two_d and len(preds) > 1 else preds[0]
     if isinstance(query_labels, list) and len(query_labels) == 1:  # `tl.py:434-435`
