@@ -133,6 +133,11 @@ int sym_moe_apply(const float *Zin, int32_t ldzin, const float *R, int64_t N, in
  *
  * sym_knn_fit (KNeighborsClassifier.fit): packs the reference embedding once.
  *   Ref [M,ldr] -> packed (opaque, sym_knn_packed_bytes(M,d) bytes).
+ *   order [M] or NULL: a permutation of the reference rows (packed position -> row).  Any permutation gives
+ *   the same results; one that keeps spatially close rows together (rows sorted by nearest of a few hundred
+ *   centroids, see sym_nearest_centroid) makes the scan several times faster.
+ * sym_nearest_centroid: code[n] = index of the nearest of C centroids [C,d] (squared Euclidean, lowest index
+ *   on ties) — the coarse spatial key used to order reference rows and query rows alike.
  * sym_knn (kneighbors): idx [N,k] int32 ascending by (squared distance, index), dist2 [N,k] f32.
  *   Candidates are selected by a float32 (or tensor-core) scan over-selecting k+pad per row and
  *   re-ranked in float64 with sklearn's formula ||x||^2 - 2x.y + ||y||^2 clamped at 0; ties go
@@ -140,16 +145,23 @@ int sym_moe_apply(const float *Zin, int32_t ldzin, const float *R, int64_t N, in
  *   method: 0 = auto, 1 = FP32 FFMA scan, 2 = tcgen05 scan (sm_100a tensor cores).
  *   unsafe [N] uint8 or NULL: rows whose over-selection margin could not be certified
  *   (tensor-core scan only; the caller re-runs those rows with method 1).
+ *   Optional scan order (all three or none): q_perm [N] = query rows sorted by coarse cluster code,
+ *   q_code [N] = cluster code of every query row, cl_tile [C] = first 128-row tile of the packed reference
+ *   that holds rows of cluster c.  Results do not depend on them.
  * sym_vote (predict / predict_proba): label[n] = lowest class code among the most frequent
  *   codes of the k neighbours; conf[n] = winning votes / k.  ref_codes [M]; entries of idx outside [0, M) are
  *   ignored (label -1 if a row has no valid neighbour).
  */
 size_t sym_knn_packed_bytes(int64_t M, int32_t d);
-int sym_knn_fit(const float *Ref, int32_t ldr, int64_t M, int32_t d, void *packed, sym_stream_t stream);
+int sym_knn_fit(const float *Ref, int32_t ldr, int64_t M, int32_t d, const int32_t *order, void *packed,
+                sym_stream_t stream);
+int sym_nearest_centroid(const float *X, int32_t ldx, int64_t N, int32_t d, const float *centroids, int32_t C,
+                         int32_t *code, sym_stream_t stream);
 size_t sym_knn_workspace(int64_t N, int64_t M, int32_t d, int32_t k, int32_t method);
 int sym_knn(const float *Q, int32_t ldq, int64_t N, const float *Ref, int32_t ldr, int64_t M,
-            const void *packed, int32_t d, int32_t k, int32_t method, int32_t *idx, float *dist2,
-            uint8_t *unsafe, void *workspace, size_t workspace_bytes, sym_stream_t stream);
+            const void *packed, int32_t d, int32_t k, int32_t method, const int32_t *q_perm, const int32_t *q_code,
+            const int32_t *cl_tile, int32_t *idx, float *dist2, uint8_t *unsafe, void *workspace,
+            size_t workspace_bytes, sym_stream_t stream);
 int sym_vote(const int32_t *idx, int64_t N, int32_t k, const int32_t *ref_codes, int64_t M, int32_t *label,
              float *conf, sym_stream_t stream);
 

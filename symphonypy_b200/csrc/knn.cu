@@ -24,7 +24,8 @@ namespace sym {
 // RefT[dd][m] = Ref[m][dd] (zero padded to d4 x Mpad), norm2[m] = ||Ref[m]||^2 (NaN for padding),
 // header.rmax2 = max_m norm2[m].
 __global__ void __launch_bounds__(256)
-knn_fit_kernel(const float *__restrict__ Ref, int ldr, int64_t M, int d, KnnPacked pk) {
+knn_fit_kernel(const float *__restrict__ Ref, int ldr, int64_t M, int d, const int32_t *__restrict__ order,
+               KnnPacked pk) {
     __shared__ float tile[128][33];
     const int64_t m0 = (int64_t)blockIdx.x * 128;
     const int tid = threadIdx.x;
@@ -34,7 +35,8 @@ knn_fit_kernel(const float *__restrict__ Ref, int ldr, int64_t M, int d, KnnPack
         for (int i = tid; i < 128 * 32; i += 256) {
             const int r = i / 32, c = i % 32;
             const int64_t m = m0 + r;
-            tile[r][c] = (m < M && d0 + c < d) ? Ref[m * ldr + d0 + c] : 0.f;
+            const int64_t src = (m < M && order) ? order[m] : m;  // packed position m holds reference row order[m]
+            tile[r][c] = (m < M && d0 + c < d) ? Ref[src * ldr + d0 + c] : 0.f;
         }
         __syncthreads();
         for (int i = tid; i < 32 * 128; i += 256) {
@@ -47,6 +49,7 @@ knn_fit_kernel(const float *__restrict__ Ref, int ldr, int64_t M, int d, KnnPack
     if (tid < 128) {
         const bool real = m0 + tid < M;
         pk.norm2[m0 + tid] = real ? nrm : __int_as_float(0x7fc00000);  // NaN: padding never passes a compare
+        pk.order[m0 + tid] = real ? (order ? order[m0 + tid] : (int32_t)(m0 + tid)) : -1;
         // max over the block -> header (float atomic max through the int ordering of non-negatives)
         float v = real ? nrm : 0.f;
         v = warp_max(v);
@@ -104,7 +107,8 @@ __device__ __forceinline__ void topk_insert(unsigned long long *top_row, int kc,
 }
 
 __global__ void __launch_bounds__(SC_THREADS)
-knn_scan_ffma_kernel(const float *__restrict__ Q, int ldq, int64_t N, int64_t M, KnnPacked pk, int d, int kc, int kcap,
+knn_scan_ffma_kernel(const float *__restrict__ Q, int ldq, int64_t N, const int32_t *__restrict__ q_perm, int64_t M,
+                     KnnPacked pk, int d, int kc, int kcap,
                      int tiles_per_split, int top_in_smem, unsigned long long *__restrict__ top_ws,
                      unsigned long long *__restrict__ cand_out, float *__restrict__ thr_out) {
     extern __shared__ __align__(16) unsigned char smraw[];
@@ -139,7 +143,8 @@ knn_scan_ffma_kernel(const float *__restrict__ Q, int ldq, int64_t N, int64_t M,
     for (int i = tid; i < SC_BQ * d4; i += SC_THREADS) {
         const int r = i / d4, c = i % d4;
         const int64_t n = q0 + r;
-        S.Qs[c * SC_BQ + r] = (n < N && c < d) ? -2.f * Q[n * ldq + c] : 0.f;
+        const int64_t src = (n < N && q_perm) ? q_perm[n] : n;
+        S.Qs[c * SC_BQ + r] = (n < N && c < d) ? -2.f * Q[src * ldq + c] : 0.f;
     }
     for (int i = tid; i < SC_BQ * kcap; i += SC_THREADS) S.top[i] = ~0ull;
     for (int i = tid; i < SC_BQ; i += SC_THREADS) {
@@ -287,13 +292,15 @@ constexpr int RR_MAXC = 512;  // candidates per row the shared scratch can hold
 __global__ void __launch_bounds__(RR_THREADS)
 knn_rerank_kernel(const float *__restrict__ Q, int ldq, int64_t N, const float *__restrict__ Ref, int ldr, int64_t M,
                   int d, int k, const unsigned long long *__restrict__ cand, const float *__restrict__ thr, int ncand, int nsplit,
-                  double eps_rel, const KnnHeader *__restrict__ hdr, int32_t *__restrict__ idx_out,
-                  float *__restrict__ dist_out, uint8_t *__restrict__ unsafe) {
+                  double eps_rel, const KnnHeader *__restrict__ hdr, const int32_t *__restrict__ order,
+                  const int32_t *__restrict__ q_perm, int32_t *__restrict__ idx_out, float *__restrict__ dist_out,
+                  uint8_t *__restrict__ unsafe) {
     __shared__ double sd[RR_THREADS / 32][RR_MAXC];
     __shared__ int32_t si[RR_THREADS / 32][RR_MAXC];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t n = (int64_t)blockIdx.x * (RR_THREADS / 32) + warp;
-    if (n >= N) return;
+    const int64_t row = (int64_t)blockIdx.x * (RR_THREADS / 32) + warp;  // row of the scan (locality order)
+    if (row >= N) return;
+    const int64_t n = q_perm ? q_perm[row] : row;                        // the query it stands for
     const float *q = Q + n * ldq;
     double qn = 0.0;
     for (int c = 0; c < d; ++c) {
@@ -312,10 +319,11 @@ knn_rerank_kernel(const float *__restrict__ Q, int ldq, int64_t N, const float *
     }
     __syncwarp();
     for (int e = lane; e < ncand; e += 32) {
-        const unsigned long long key = cand[n * ncand + e];
-        const uint32_t id = (uint32_t)(key & 0xffffffffull);
+        const unsigned long long key = cand[row * ncand + e];
+        const uint32_t pos = (uint32_t)(key & 0xffffffffull);   // position in the packed reference
         double dist = INFINITY;
-        const bool valid = key != ~0ull && (int64_t)id < M;
+        const bool valid = key != ~0ull && (int64_t)pos < M;
+        const uint32_t id = valid ? (uint32_t)order[pos] : 0u;  // original reference row
         if (valid) {
             const float *r = Ref + (int64_t)id * ldr;
             double rn = 0.0, dot = 0.0;
@@ -360,10 +368,54 @@ knn_rerank_kernel(const float *__restrict__ Q, int ldq, int64_t N, const float *
         bad |= nvalid < k;
         if (lane == 0) {
             double tmin = INFINITY;
-            for (int s = 0; s < nsplit; ++s) tmin = fmin(tmin, (double)thr[n * nsplit + s]);
+            for (int s = 0; s < nsplit; ++s) tmin = fmin(tmin, (double)thr[row * nsplit + s]);
             unsafe[n] = (!bad && kth - qn + 2.0 * eps < tmin) ? 0 : 1;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------ nearest centroid
+// code[n] = argmin_c ||x_n - cent_c||^2 (lowest c on ties).  Used to put queries and reference rows into the
+// same coarse spatial order, so that a query tile meets its likely neighbours in the first reference tiles
+// it scans and its thresholds are tight for the rest of the scan.  128 rows per block, rows and a chunk of
+// centroids in shared memory.
+constexpr int NC_ROWS = 128;
+constexpr int NC_CHUNK = 64;
+__global__ void __launch_bounds__(NC_ROWS)
+nearest_centroid_kernel(const float *__restrict__ X, int ldx, int64_t N, int d, const float *__restrict__ cent, int C,
+                        int32_t *__restrict__ code) {
+    extern __shared__ __align__(16) float nsm[];
+    float *xs = nsm;                      // [d][NC_ROWS]
+    float *cs = nsm + (size_t)d * NC_ROWS;  // [NC_CHUNK][d + 1]  (last = ||c||^2)
+    const int tid = threadIdx.x;
+    const int64_t n0 = (int64_t)blockIdx.x * NC_ROWS;
+    for (int i = tid; i < NC_ROWS * d; i += NC_ROWS) {
+        const int r = i / d, c = i % d;
+        xs[c * NC_ROWS + r] = (n0 + r < N) ? X[(n0 + r) * ldx + c] : 0.f;
+    }
+    float best = INFINITY;
+    int bestc = 0;
+    for (int c0 = 0; c0 < C; c0 += NC_CHUNK) {
+        __syncthreads();
+        const int nc = min(NC_CHUNK, C - c0);
+        for (int i = tid; i < nc * d; i += NC_ROWS) cs[(i / d) * (d + 1) + i % d] = cent[(int64_t)(c0 + i / d) * d + i % d];
+        __syncthreads();
+        for (int i = tid; i < nc; i += NC_ROWS) {
+            float nn = 0.f;
+            for (int j = 0; j < d; ++j) nn = fmaf(cs[i * (d + 1) + j], cs[i * (d + 1) + j], nn);
+            cs[i * (d + 1) + d] = nn;
+        }
+        __syncthreads();
+        for (int c = 0; c < nc; ++c) {
+            const float *cr = cs + c * (d + 1);
+            float dot = 0.f;
+#pragma unroll 4
+            for (int j = 0; j < d; ++j) dot = fmaf(xs[j * NC_ROWS + tid], cr[j], dot);
+            const float s = cr[d] - 2.f * dot;  // ||x||^2 is common to all centroids
+            if (s < best) { best = s; bestc = c0 + c; }
+        }
+    }
+    if (n0 + tid < N) code[n0 + tid] = bestc;
 }
 
 // ------------------------------------------------------------------------------------------ vote
@@ -399,7 +451,20 @@ using namespace sym;
 
 extern "C" size_t sym_knn_packed_bytes(int64_t M, int32_t d) { return knn_packed_layout(nullptr, M, d).total; }
 
-extern "C" int sym_knn_fit(const float *Ref, int32_t ldr, int64_t M, int32_t d, void *packed, sym_stream_t stream) {
+extern "C" int sym_nearest_centroid(const float *X, int32_t ldx, int64_t N, int32_t d, const float *centroids, int32_t C,
+                                    int32_t *code, sym_stream_t stream) {
+    SYM_REQUIRE(N >= 0 && d > 0 && d <= 128 && C > 0 && ldx >= d, SYM_ERR_INVALID_ARGUMENT, "sym_nearest_centroid: bad sizes");
+    if (N == 0) return SYM_OK;
+    const size_t smem = ((size_t)d * NC_ROWS + (size_t)NC_CHUNK * (d + 1)) * sizeof(float);
+    SYM_CUDA(cudaFuncSetAttribute(nearest_centroid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nearest_centroid_kernel<<<(unsigned)ceil_div(N, NC_ROWS), NC_ROWS, smem, (cudaStream_t)stream>>>(X, ldx, N, d, centroids,
+                                                                                                  C, code);
+    SYM_LAUNCH_CHECK("nearest_centroid_kernel");
+    return SYM_OK;
+}
+
+extern "C" int sym_knn_fit(const float *Ref, int32_t ldr, int64_t M, int32_t d, const int32_t *order, void *packed,
+                           sym_stream_t stream) {
     SYM_REQUIRE(M > 0 && d > 0 && ldr >= d, SYM_ERR_INVALID_ARGUMENT, "sym_knn_fit: bad sizes");
     SYM_REQUIRE(d <= 128, SYM_ERR_UNSUPPORTED_SHAPE, "sym_knn_fit: d=%d > 128", d);
     SYM_REQUIRE(M < (1ll << 31) - 256, SYM_ERR_UNSUPPORTED_SHAPE, "sym_knn_fit: M too large");
@@ -407,9 +472,9 @@ extern "C" int sym_knn_fit(const float *Ref, int32_t ldr, int64_t M, int32_t d, 
     cudaStream_t st = (cudaStream_t)stream;
     KnnPacked pk = knn_packed_layout(packed, M, d);
     SYM_CUDA(cudaMemsetAsync(pk.hdr, 0, sizeof(KnnHeader), st));
-    knn_fit_kernel<<<(unsigned)(pk.Mpad / 128), 256, 0, st>>>(Ref, ldr, M, d, pk);
+    knn_fit_kernel<<<(unsigned)(pk.Mpad / 128), 256, 0, st>>>(Ref, ldr, M, d, order, pk);
     SYM_LAUNCH_CHECK("knn_fit_kernel");
-    return knn_tc_fit(Ref, ldr, M, d, pk, st);
+    return knn_tc_fit(Ref, ldr, M, d, order, pk, st);
 }
 
 namespace {
@@ -460,8 +525,9 @@ extern "C" size_t sym_knn_workspace(int64_t N, int64_t M, int32_t d, int32_t k, 
 }
 
 extern "C" int sym_knn(const float *Q, int32_t ldq, int64_t N, const float *Ref, int32_t ldr, int64_t M,
-                       const void *packed, int32_t d, int32_t k, int32_t method, int32_t *idx, float *dist2,
-                       uint8_t *unsafe, void *workspace, size_t workspace_bytes, sym_stream_t stream) {
+                       const void *packed, int32_t d, int32_t k, int32_t method, const int32_t *q_perm,
+                       const int32_t *q_code, const int32_t *cl_tile, int32_t *idx, float *dist2, uint8_t *unsafe,
+                       void *workspace, size_t workspace_bytes, sym_stream_t stream) {
     SYM_REQUIRE(N >= 0 && M > 0 && d > 0 && ldq >= d && ldr >= d, SYM_ERR_INVALID_ARGUMENT, "sym_knn: bad sizes");
     SYM_REQUIRE(k >= 1 && k <= M, SYM_ERR_INVALID_ARGUMENT,
                 "sym_knn: Expected n_neighbors <= n_samples_fit, but n_neighbors = %d, n_samples_fit = %lld", k,
@@ -482,7 +548,8 @@ extern "C" int sym_knn(const float *Q, int32_t ldq, int64_t N, const float *Ref,
     const float *thr = nullptr;
     if (method == 2) {
         SYM_REQUIRE(knn_tc_supported(N, M, d, k), SYM_ERR_UNSUPPORTED_SHAPE, "sym_knn: tcgen05 scan does not support this shape");
-        int rc = knn_tc_scan(Q, ldq, N, pk, M, d, k, workspace, workspace_bytes, st, &cand, &thr, &ncand, &nsplit, &eps_rel);
+        int rc = knn_tc_scan(Q, ldq, N, q_perm, q_code, cl_tile, pk, M, d, k, workspace, workspace_bytes, st, &cand, &thr,
+                             &ncand, &nsplit, &eps_rel);
         if (rc != SYM_OK) return rc;
     } else {
         ScanPlan p;
@@ -494,7 +561,7 @@ extern "C" int sym_knn(const float *Q, int32_t ldq, int64_t N, const float *Ref,
         SYM_REQUIRE(p.smem <= 227 * 1024, SYM_ERR_UNSUPPORTED_SHAPE, "sym_knn: d=%d k=%d needs %zu B of shared memory", d, k, p.smem);
         SYM_CUDA(cudaFuncSetAttribute(knn_scan_ffma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
         dim3 grid((unsigned)p.qtiles, (unsigned)p.nsplit);
-        knn_scan_ffma_kernel<<<grid, SC_THREADS, p.smem, st>>>(Q, ldq, N, M, pk, d, p.kc, p.kcap, p.tiles_per_split,
+        knn_scan_ffma_kernel<<<grid, SC_THREADS, p.smem, st>>>(Q, ldq, N, q_perm, M, pk, d, p.kc, p.kcap, p.tiles_per_split,
                                                                p.top_in_smem, top_w, cand_w, thr_w);
         SYM_LAUNCH_CHECK("knn_scan_ffma_kernel");
         cand = cand_w; thr = thr_w; ncand = p.nsplit * p.kc; nsplit = p.nsplit;
@@ -503,7 +570,7 @@ extern "C" int sym_knn(const float *Q, int32_t ldq, int64_t N, const float *Ref,
     }
     SYM_REQUIRE(ncand <= RR_MAXC, SYM_ERR_UNSUPPORTED_SHAPE, "sym_knn: internal: %d candidates per row", ncand);
     knn_rerank_kernel<<<(unsigned)ceil_div(N, RR_THREADS / 32), RR_THREADS, 0, st>>>(
-        Q, ldq, N, Ref, ldr, M, d, k, cand, thr, ncand, nsplit, eps_rel, pk.hdr, idx, dist2, unsafe);
+        Q, ldq, N, Ref, ldr, M, d, k, cand, thr, ncand, nsplit, eps_rel, pk.hdr, pk.order, q_perm, idx, dist2, unsafe);
     SYM_LAUNCH_CHECK("knn_rerank_kernel");
     return SYM_OK;
 }

@@ -6,17 +6,18 @@ namespace sym {
 
 struct KnnHeader {
     float rmax2;       // max ||ref||^2 (written by fit with an integer atomicMax: values are >= 0)
-    int32_t tc_ready;  // 1 once the tensor-core operand section has been packed
+    int32_t has_order;  // 1 when the reference was packed in a caller-given (locality) order
     int32_t pad[62];
 };
 
 // Layout of the opaque "packed reference" buffer produced by sym_knn_fit:
-//   [KnnHeader | norm2 f32[Mpad] | refT f32[d4][Mpad] | tensor-core section]
+//   [KnnHeader | norm2 f32[Mpad] | refT f32[d4][Mpad] | tensor-core section | order i32[Mpad]]
 struct KnnPacked {
     KnnHeader *hdr;
     float *norm2;
     float *refT;
     unsigned char *tc;  // tensor-core operand section (layout private to knn_tc.cu)
+    int32_t *order;     // [Mpad] packed position -> original reference row (identity when no order was given)
     int64_t Mpad;
     int d4;
     size_t total;
@@ -41,6 +42,9 @@ inline KnnPacked knn_packed_layout(void *base, int64_t M, int d) {
     off = (off + 1023) & ~(size_t)1023;
     p.tc = b + off;
     off += knn_tc_packed_bytes(M, d);
+    off = (off + 255) & ~(size_t)255;
+    p.order = (int32_t *)(b + off);
+    off += (size_t)p.Mpad * sizeof(int32_t);
     p.total = off;
     return p;
 }
@@ -68,8 +72,9 @@ __device__ __forceinline__ float knn_key_score(unsigned long long key) {
 // tcgen05 scan entry points (knn_tc.cu)
 bool knn_tc_supported(int64_t N, int64_t M, int d, int k);
 size_t knn_tc_workspace(int64_t N, int64_t M, int d, int k);
-int knn_tc_fit(const float *Ref, int ldr, int64_t M, int d, KnnPacked pk, cudaStream_t st);
-int knn_tc_scan(const float *Q, int ldq, int64_t N, KnnPacked pk, int64_t M, int d, int k, void *workspace,
+int knn_tc_fit(const float *Ref, int ldr, int64_t M, int d, const int32_t *order, KnnPacked pk, cudaStream_t st);
+int knn_tc_scan(const float *Q, int ldq, int64_t N, const int32_t *q_perm, const int32_t *q_code,
+                const int32_t *cl_tile, KnnPacked pk, int64_t M, int d, int k, void *workspace,
                 size_t workspace_bytes, cudaStream_t st, const unsigned long long **cand, const float **thr, int *ncand,
                 int *nsplit, double *eps_rel);
 

@@ -51,13 +51,13 @@ __device__ __forceinline__ float bf16_to_f(unsigned short h) { return __uint_as_
 // Element (r, kk) of a tile lives at  (kk/8)*2048 + (r/8)*128 + (r%8)*16 + (kk%8)*2  bytes.
 __global__ void __launch_bounds__(256)
 tc_pack_kernel(const float *__restrict__ src, int ld, int64_t rows, int64_t rows_pad, int d, int kp, int is_query,
-               unsigned char *__restrict__ dst) {
+               const int32_t *__restrict__ gather, unsigned char *__restrict__ dst) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;  // k-unit
     if (r >= rows_pad) return;
     unsigned short out[8];
     const bool real = r < rows;
-    const float *x = src + r * ld;
+    const float *x = src + ((real && gather) ? (int64_t)gather[r] : (real ? r : 0)) * ld;
     float nrm = 0.f;
     const int k0 = j * 8;
     if (real && !is_query && k0 + 8 > 3 * d && k0 < 3 * d + 3) {
@@ -106,11 +106,11 @@ tc_pack_kernel(const float *__restrict__ src, int ld, int64_t rows, int64_t rows
 // loads its own row).  One thread = one row x one k-unit, as above.
 __global__ void __launch_bounds__(256)
 tc_pack_rows_kernel(const float *__restrict__ src, int ld, int64_t rows, int64_t rows_pad, int d, int kp,
-                    unsigned char *__restrict__ dst) {
+                    const int32_t *__restrict__ gather, unsigned char *__restrict__ dst) {
     const int64_t r = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;  // a warp walks the k-units of a row
     if (r >= rows_pad) return;
     const bool real = r < rows;
-    const float *x = src + r * ld;
+    const float *x = src + ((real && gather) ? (int64_t)gather[r] : (real ? r : 0)) * ld;
     for (int j = threadIdx.x % 32; j < kp / 8; j += 32) {
         unsigned short out[8];
 #pragma unroll
@@ -341,7 +341,9 @@ __device__ __forceinline__ float tc_select32(const uint32_t (&v)[32], float thr,
 template <int TC_QT>
 __global__ void __launch_bounds__(128 + 128 * TC_QT, 1)
 knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char *__restrict__ rpack, int64_t N,
-                   int64_t M, int kp, int kc, int stages, int nbuf, int tiles_per_split, int ntiles_all,
+                   const int32_t *__restrict__ q_perm, const int32_t *__restrict__ q_code,
+                   const int32_t *__restrict__ cl_tile, int64_t M, int kp, int kc, int stages, int nbuf,
+                   int tiles_per_split, int ntiles_all,
                    unsigned long long *__restrict__ cand_out, float *__restrict__ thr_out) {
     extern __shared__ __align__(1024) unsigned char smraw[];
     const uint32_t tile_bytes = (uint32_t)tc_tile_bytes(kp);
@@ -362,6 +364,15 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
     const int t_beg = split * tiles_per_split;
     const int t_end = min(ntiles_all, t_beg + tiles_per_split);
     const int ntiles = max(0, t_end - t_beg);
+    // Scan order: cyclic, starting at the reference tile where the cluster of this CTA's first query row begins
+    // (queries and reference are both sorted by coarse cluster): the likely neighbours come first, the row
+    // thresholds are tight after a few tiles and the rest of the scan is almost free of list updates.
+    int t_home = t_beg;
+    if (cl_tile != nullptr && ntiles > 0) {
+        const int64_t r0 = min((int64_t)blockIdx.x * TC_QT * TC_BM, N - 1);
+        const int t = cl_tile[q_code[q_perm ? q_perm[r0] : r0]];
+        t_home = min(max(t, t_beg), t_end - 1);
+    }
     // tensor memory map: A operand of query tile q in columns [q*kp/2, (q+1)*kp/2); accumulator b at acc0 + b*128
     const uint32_t a_cols = (uint32_t)(kp / 2);
     const uint32_t acc0 = 512u - (uint32_t)nbuf * TC_BN;
@@ -405,13 +416,14 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
     if (warp == 0) {
         // ===== producer: one bulk copy per reference tile =====
         if (lane == 0) {
-            int s = 0;
+            int s = 0, t = t_home;
             uint32_t ph = 0;  // ring position and phase kept incrementally: no integer division on any per-tile path
             for (int i = 0; i < ntiles; ++i) {
                 mbar_wait_sleepy(&r_empty[s], ph ^ 1);
                 mbar_arrive_expect_tx(&r_full[s], tile_bytes);
-                bulk_g2s(r_s + (size_t)s * tile_bytes, rpack + (size_t)(t_beg + i) * tile_bytes, tile_bytes, &r_full[s]);
+                bulk_g2s(r_s + (size_t)s * tile_bytes, rpack + (size_t)t * tile_bytes, tile_bytes, &r_full[s]);
                 if (++s == stages) { s = 0; ph ^= 1; }
+                if (++t == t_end) t = t_beg;
             }
         }
     } else if (warp <= TC_QT) {
@@ -466,6 +478,7 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
         float thr = INFINITY;
         const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + acc0;
         int buf = qt % nbuf, use = qt / nbuf;   // chain (i, qt) = sequence number i*QT + qt
+        int t_cur = t_home;
         for (int i = 0; i < ntiles; ++i) {
 #ifdef TC_SLEEPY_SELECT
             mbar_wait_sleepy(&t_full[buf], use & 1);
@@ -473,7 +486,8 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
             mbar_wait(&t_full[buf], use & 1);
 #endif
             tc_fence_after();
-            const int64_t ref0 = (int64_t)(t_beg + i) * TC_BN;
+            const int64_t ref0 = (int64_t)t_cur * TC_BN;
+            if (++t_cur == t_end) t_cur = t_beg;
             const uint32_t acc = lane_base + (uint32_t)(buf * TC_BN);
 #ifdef TC_EXPERIMENT_NO_SELECT
             tc_fence_before();
@@ -659,17 +673,18 @@ size_t knn_tc_workspace(int64_t N, int64_t M, int d, int k) {
     return p.qpack_bytes + p.cand_bytes + p.thr_bytes + 1024;
 }
 
-int knn_tc_fit(const float *Ref, int ldr, int64_t M, int d, KnnPacked pk, cudaStream_t st) {
+int knn_tc_fit(const float *Ref, int ldr, int64_t M, int d, const int32_t *order, KnnPacked pk, cudaStream_t st) {
     if (d > 84) return SYM_OK;
     const int kp = tc_kp(d);
     const int64_t rows_pad = knn_mpad(M);
     dim3 grid((unsigned)ceil_div(rows_pad, 256), (unsigned)(kp / 8));
-    tc_pack_kernel<<<grid, 256, 0, st>>>(Ref, ldr, M, rows_pad, d, kp, 0, pk.tc);
+    tc_pack_kernel<<<grid, 256, 0, st>>>(Ref, ldr, M, rows_pad, d, kp, 0, order, pk.tc);
     SYM_LAUNCH_CHECK("tc_pack_kernel(ref)");
     return SYM_OK;
 }
 
-int knn_tc_scan(const float *Q, int ldq, int64_t N, KnnPacked pk, int64_t M, int d, int k, void *workspace,
+int knn_tc_scan(const float *Q, int ldq, int64_t N, const int32_t *q_perm, const int32_t *q_code,
+                const int32_t *cl_tile, KnnPacked pk, int64_t M, int d, int k, void *workspace,
                 size_t workspace_bytes, cudaStream_t st, const unsigned long long **cand, const float **thr,
                 int *ncand, int *nsplit, double *eps_rel) {
     TcPlan p = tc_plan(N, M, d, k);
@@ -682,17 +697,17 @@ int knn_tc_scan(const float *Q, int ldq, int64_t N, KnnPacked pk, int64_t M, int
     float *thr_w = (float *)w;
     {
         const int64_t rows_pad = p.qtiles * p.qt * TC_BM;
-        tc_pack_rows_kernel<<<(unsigned)ceil_div(rows_pad, 8), 256, 0, st>>>(Q, ldq, N, rows_pad, d, p.kp, qpack);
+        tc_pack_rows_kernel<<<(unsigned)ceil_div(rows_pad, 8), 256, 0, st>>>(Q, ldq, N, rows_pad, d, p.kp, q_perm, qpack);
         SYM_LAUNCH_CHECK("tc_pack_rows_kernel(query)");
     }
     dim3 grid((unsigned)p.qtiles, (unsigned)p.nsplit);
     if (p.qt == 2) {
         SYM_CUDA(cudaFuncSetAttribute(knn_scan_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-        knn_scan_tc_kernel<2><<<grid, 128 + 128 * 2, p.smem, st>>>(qpack, pk.tc, N, M, p.kp, p.kc, p.stages, p.nbuf,
+        knn_scan_tc_kernel<2><<<grid, 128 + 128 * 2, p.smem, st>>>(qpack, pk.tc, N, q_perm, q_code, cl_tile, M, p.kp, p.kc, p.stages, p.nbuf,
                                                                   p.tiles_per_split, p.ntiles, cand_w, thr_w);
     } else {
         SYM_CUDA(cudaFuncSetAttribute(knn_scan_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-        knn_scan_tc_kernel<1><<<grid, 128 + 128 * 1, p.smem, st>>>(qpack, pk.tc, N, M, p.kp, p.kc, p.stages, p.nbuf,
+        knn_scan_tc_kernel<1><<<grid, 128 + 128 * 1, p.smem, st>>>(qpack, pk.tc, N, q_perm, q_code, cl_tile, M, p.kp, p.kc, p.stages, p.nbuf,
                                                                   p.tiles_per_split, p.ntiles, cand_w, thr_w);
     }
     SYM_LAUNCH_CHECK("knn_scan_tc_kernel");
@@ -718,13 +733,13 @@ extern "C" int sym_debug_tc_scores(const float *Q, int32_t nq, const float *Ref,
     const int kp = tc_kp(d);
     unsigned char *qp = (unsigned char *)scratch, *rp = qp + tc_tile_bytes(kp);
     dim3 grid(1, (unsigned)(kp / 8));
-    tc_pack_kernel<<<grid, 256, 0, st>>>(Q, d, nq, 128, d, kp, 1, qp);
+    tc_pack_kernel<<<grid, 256, 0, st>>>(Q, d, nq, 128, d, kp, 1, nullptr, qp);
     SYM_LAUNCH_CHECK("tc_pack_kernel");
-    tc_pack_kernel<<<grid, 256, 0, st>>>(Ref, d, nr, 128, d, kp, 0, rp);
+    tc_pack_kernel<<<grid, 256, 0, st>>>(Ref, d, nr, 128, d, kp, 0, nullptr, rp);
     SYM_LAUNCH_CHECK("tc_pack_kernel");
     unsigned char *qrows = rp + tc_tile_bytes(kp);
     if (a_in_tmem) {
-        tc_pack_rows_kernel<<<16, 256, 0, st>>>(Q, d, nq, 128, d, kp, qrows);
+        tc_pack_rows_kernel<<<16, 256, 0, st>>>(Q, d, nq, 128, d, kp, nullptr, qrows);
         SYM_LAUNCH_CHECK("tc_pack_rows_kernel");
     }
     const size_t smem = 2 * tc_tile_bytes(kp) + 1024;

@@ -202,25 +202,82 @@ def moe_apply(Z, R, codes, levels, orders, W, out=None):
 # ------------------------------------------------------------------------------------- kNN
 @dataclass
 class KnnIndex:
-    """`KNeighborsClassifier.fit` result: the reference embedding, packed for the scan kernels."""
+    """`KNeighborsClassifier.fit` result: the reference embedding, packed for the scan kernels.
 
-    ref: torch.Tensor      # [M, d] f32
+    The packed copy is stored in a coarse spatial order (rows sorted by nearest of C k-means centroids, the
+    centroids themselves chained by proximity).  Queries are sorted by the same key at search time and every
+    query tile starts its scan at the reference tiles of its own cluster, so its thresholds are tight after a
+    few tiles.  The order changes the speed of the scan only, never its result."""
+
+    ref: torch.Tensor      # [M, d] f32, original row order
     packed: torch.Tensor   # opaque bytes
     M: int
     d: int
+    centroids: torch.Tensor | None = None   # [C, d] f32, in chain order
+    cl_tile: torch.Tensor | None = None     # [C] i32: first 128-row tile of the packed reference with rows of cluster c
     workspace: dict = field(default_factory=dict)
 
 
-def knn_fit(ref: torch.Tensor) -> KnnIndex:
+LOCALITY_MIN_REF = 32768     # below this the whole reference is a few hundred tiles: no ordering
+LOCALITY_MIN_QUERY = 8192
+
+
+def nearest_centroid(X: torch.Tensor, centroids: torch.Tensor) -> torch.Tensor:
+    """code [N] i32 = nearest of the centroids [C, d] (our kernel; used at fit and at search time)."""
+    lib = _lib.load()
+    N, d = X.shape
+    code = torch.empty(N, device=X.device, dtype=torch.int32)
+    _lib.check(lib.sym_nearest_centroid(X.data_ptr(), X.stride(0), N, d, centroids.data_ptr(), centroids.shape[0],
+                                        code.data_ptr(), _stream(X.device)), "sym_nearest_centroid")
+    return code
+
+
+def _coarse_centroids(ref: torch.Tensor, C: int, iters: int = 4) -> torch.Tensor:
+    """A few Lloyd iterations on a sample of the reference (fit time only; the quality of the clustering
+    affects scan speed, not results), then the centroids are chained greedily by proximity so that
+    neighbouring cluster ids are neighbouring regions."""
+    M, d = ref.shape
+    g = torch.Generator(device="cpu")
+    g.manual_seed(12345)
+    sample = ref[torch.randperm(M, generator=g)[: min(M, 128 * C)].to(ref.device)].contiguous()
+    cent = sample[:C].clone()
+    for _ in range(iters):
+        code = nearest_centroid(sample, cent).long()
+        sums = torch.zeros_like(cent).index_add_(0, code, sample)
+        cnt = torch.zeros(C, device=ref.device).index_add_(0, code, torch.ones_like(code, dtype=torch.float32))
+        cent = torch.where(cnt[:, None] > 0, sums / cnt.clamp_min(1.0)[:, None], cent)
+    c = cent.double().cpu().numpy()
+    left = np.ones(C, dtype=bool)
+    cur = int(np.argmin(c[:, 0]))
+    chain = [cur]
+    left[cur] = False
+    for _ in range(C - 1):
+        dist = ((c - c[cur]) ** 2).sum(1)
+        dist[~left] = np.inf
+        cur = int(np.argmin(dist))
+        chain.append(cur)
+        left[cur] = False
+    return cent[torch.as_tensor(chain, device=ref.device)].contiguous()
+
+
+def knn_fit(ref: torch.Tensor, locality: bool = True) -> KnnIndex:
     lib = _lib.load()
     ref = _f32c(ref)
     M, d = ref.shape
+    centroids = cl_tile = order = None
+    if locality and M >= LOCALITY_MIN_REF:
+        C = int(min(1024, max(16, M // 2048)))
+        centroids = _coarse_centroids(ref, C)
+        code = nearest_centroid(ref, centroids)
+        bo = batch_order(code, C)          # counting sort of the reference rows by cluster
+        order = bo.perm
+        cl_tile = (bo.seg[:-1] // 128).to(torch.int32).contiguous()
     nbytes = int(lib.sym_knn_packed_bytes(M, d))
     packed = torch.empty(nbytes, device=ref.device, dtype=torch.uint8)
     assert packed.data_ptr() % 256 == 0
-    _lib.check(lib.sym_knn_fit(ref.data_ptr(), ref.stride(0), M, d, packed.data_ptr(), _stream(ref.device)),
+    _lib.check(lib.sym_knn_fit(ref.data_ptr(), ref.stride(0), M, d, _ptr(order), packed.data_ptr(), _stream(ref.device)),
                "sym_knn_fit")
-    return KnnIndex(ref=ref, packed=packed, M=M, d=d)
+    return KnnIndex(ref=ref, packed=packed, M=M, d=d, centroids=centroids, cl_tile=cl_tile)
 
 
 def knn_search(index: KnnIndex, Q: torch.Tensor, k: int, method: int = KNN_AUTO, want_unsafe: bool = True):
@@ -233,6 +290,11 @@ def knn_search(index: KnnIndex, Q: torch.Tensor, k: int, method: int = KNN_AUTO,
     idx = torch.empty((N, k), device=dev, dtype=torch.int32)
     dist2 = torch.empty((N, k), device=dev, dtype=torch.float32)
     unsafe = torch.empty(N, device=dev, dtype=torch.uint8) if want_unsafe else None
+    q_perm = q_code = cl_tile = None
+    if index.centroids is not None and N >= LOCALITY_MIN_QUERY and method != KNN_FFMA:
+        q_code = nearest_centroid(Q, index.centroids)
+        q_perm = batch_order(q_code, index.centroids.shape[0]).perm
+        cl_tile = index.cl_tile
     ws_bytes = int(lib.sym_knn_workspace(N, index.M, d, k, method))
     key = "ws"
     ws = index.workspace.get(key)
@@ -240,8 +302,9 @@ def knn_search(index: KnnIndex, Q: torch.Tensor, k: int, method: int = KNN_AUTO,
         ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
         index.workspace[key] = ws
     _lib.check(lib.sym_knn(Q.data_ptr(), Q.stride(0), N, index.ref.data_ptr(), index.ref.stride(0), index.M,
-                           index.packed.data_ptr(), d, k, method, idx.data_ptr(), dist2.data_ptr(), _ptr(unsafe),
-                           ws.data_ptr(), ws.numel(), _stream(dev)), "sym_knn")
+                           index.packed.data_ptr(), d, k, method, _ptr(q_perm), _ptr(q_code), _ptr(cl_tile),
+                           idx.data_ptr(), dist2.data_ptr(), _ptr(unsafe), ws.data_ptr(), ws.numel(), _stream(dev)),
+               "sym_knn")
     return idx, dist2, unsafe
 
 

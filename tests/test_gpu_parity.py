@@ -399,3 +399,25 @@ def test_knn_tcgen05_matches_sklearn(cuda_device, N, M, d, k):
     # and the certified wrapper repairs whatever was flagged
     idx2, dist22, _ = engine.knn_search_certified(index, torch.from_numpy(q).to(cuda_device), k, engine.KNN_TCGEN05)
     _check_knn(idx2.cpu().numpy(), dist22.cpu().numpy(), ref, q, k)
+
+
+def test_knn_locality_order_does_not_change_results(cuda_device):
+    """Reference packed in cluster order + queries scanned in cluster order == plain order, and both == sklearn."""
+    rng = np.random.default_rng(11)
+    M, N, d, k = 60000, 9000, 30, 10
+    centres = rng.normal(size=(12, d)) * 4
+    ref = (centres[rng.integers(0, 12, M)] + rng.normal(size=(M, d))).astype(np.float32)
+    q = (centres[rng.integers(0, 12, N)] + rng.normal(size=(N, d))).astype(np.float32)
+    R, Q = torch.from_numpy(ref).to(cuda_device), torch.from_numpy(q).to(cuda_device)
+    plain = engine.knn_fit(R, locality=False)
+    local = engine.knn_fit(R, locality=True)
+    assert plain.centroids is None and local.centroids is not None
+    code = engine.nearest_centroid(R, local.centroids).cpu().numpy()
+    c = local.centroids.cpu().numpy().astype(np.float64)
+    want_code = ((ref[:2000, None, :].astype(np.float64) - c[None]) ** 2).sum(2).argmin(1)
+    assert (code[:2000] == want_code).mean() > 0.999
+    for method in (engine.KNN_AUTO, engine.KNN_FFMA):
+        i0, d0, _ = engine.knn_search_certified(plain, Q, k, method)
+        i1, d1, _ = engine.knn_search_certified(local, Q, k, method)
+        assert torch.equal(i0, i1) and torch.equal(d0, d1)
+    _check_knn(i1.cpu().numpy(), d1.cpu().numpy(), ref, q, k)
