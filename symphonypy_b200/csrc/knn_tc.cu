@@ -272,32 +272,31 @@ constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((TC_BN >> 3)
 // chains over groups of 8, one compare against the row's kc-th best.  Only groups in which some lane
 // of the warp has a hit are walked, and a hit calls the (single, out-of-line) list update.
 
-// The row's kc best (score, index) pairs form a binary MAX-HEAP in shared memory (root = the kc-th best = the
-// row's threshold).  A hit replaces the root and sifts down: ~log2(kc) levels of two loads and a compare,
-// instead of a pass over the whole list.  Every lane works on ITS OWN row (lanes run in lock-step when several
-// rows hit at once); the row stride `ks` is odd so the roots / equal levels of the 32 rows of a warp fall into
-// different banks.  Returns the new threshold.
+// The row's kc best candidates form a binary MAX-HEAP of 64-bit keys (order-preserving score bits | position)
+// in shared memory; the root is the kc-th best = the row's threshold.  A hit replaces the root and sifts down:
+// ~log2(kc) levels of two 8-byte loads, a compare and one 8-byte store, instead of a pass over the list.
+// Every lane works on ITS OWN row (lanes run in lock-step when several rows hit at once); the row stride `ks`
+// is odd, so equal heap levels of the 32 rows of a warp fall into different banks.  Returns the new threshold.
 // (A warp-cooperative variant — one row at a time, REDUX for the maximum — was measured 2x slower end to end:
-// its votes and shuffles serialise on the critical path.)
-__device__ __noinline__ float tc_insert(float *sc_row, uint32_t *idx_row, int kc, float s, uint32_t id, float thr) {
-    (void)thr;
+// its votes and shuffles serialise on the critical path.  Deferring the updates into the wait for the next
+// accumulator was slower too: the selection warps have no such slack once updates are frequent.)
+__device__ __noinline__ float tc_insert(unsigned long long *heap, int kc, float s, uint32_t id) {
+    const unsigned long long key = knn_make_key(s, id);
     int i = 0;
     while (true) {
         const int l = 2 * i + 1;
         if (l >= kc) break;
         const int r = l + 1;
-        const float vl = sc_row[l];
-        const float vr = r < kc ? sc_row[r] : -INFINITY;
-        const int c = vr > vl ? r : l;
-        const float vc = fmaxf(vl, vr);
-        if (!(vc > s)) break;
-        sc_row[i] = vc;
-        idx_row[i] = idx_row[c];
-        i = c;
+        const unsigned long long vl = heap[l];
+        const unsigned long long vr = r < kc ? heap[r] : 0ull;
+        const bool right = vr > vl;
+        const unsigned long long vc = right ? vr : vl;
+        if (!(vc > key)) break;
+        heap[i] = vc;
+        i = right ? r : l;
     }
-    sc_row[i] = s;
-    idx_row[i] = id;
-    return sc_row[0];
+    heap[i] = key;
+    return knn_key_score(heap[0]);
 }
 
 // walk one group of 8 scores of a lane that has a hit in it (plain divergent branches: when no lane of the
@@ -308,7 +307,7 @@ __device__ __noinline__ float tc_insert(float *sc_row, uint32_t *idx_row, int kc
             const float sv = __uint_as_float(v[(G) * 8 + j]);                                         \
             if (sv < thr) {                                                                           \
                 const int64_t id = ref0 + (G) * 8 + j;                                                \
-                if (id < M) thr = tc_insert(sc_row, idx_row, kc, sv, (uint32_t)id, thr);              \
+                if (id < M) thr = tc_insert(heap, kc, sv, (uint32_t)id);                              \
             }                                                                                         \
         }                                                                                             \
     }
@@ -321,8 +320,8 @@ __device__ __forceinline__ float tc_min8(const uint32_t *v) {
 }
 
 // one 32-column chunk of the warp's 32 rows against the rows' thresholds
-__device__ __forceinline__ float tc_select32(const uint32_t (&v)[32], float thr, int64_t ref0, int64_t M, float *sc_row,
-                                             uint32_t *idx_row, int kc) {
+__device__ __forceinline__ float tc_select32(const uint32_t (&v)[32], float thr, int64_t ref0, int64_t M,
+                                             unsigned long long *heap, int kc) {
     const float g0 = tc_min8(v), g1 = tc_min8(v + 8), g2 = tc_min8(v + 16), g3 = tc_min8(v + 24);
     const float m = fminf(fmin3(g0, g1, g2), g3);
 #ifndef TC_EXPERIMENT_NO_WALK
@@ -338,8 +337,8 @@ __device__ __forceinline__ float tc_select32(const uint32_t (&v)[32], float thr,
     return thr;
 }
 
-template <int TC_QT>
-__global__ void __launch_bounds__(128 + 128 * TC_QT, 1)
+template <int TC_QT, int TC_H>
+__global__ void __launch_bounds__(128 + 128 * TC_QT * TC_H, 1)
 knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char *__restrict__ rpack, int64_t N,
                    const int32_t *__restrict__ q_perm, const int32_t *__restrict__ q_code,
                    const int32_t *__restrict__ cl_tile, int64_t M, int kp, int kc, int stages, int nbuf,
@@ -349,9 +348,11 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
     const uint32_t tile_bytes = (uint32_t)tc_tile_bytes(kp);
     const int ks = kc | 1;  // odd row stride: the 32 rows of a warp hit 32 different banks
     unsigned char *r_s = smraw;                                        // [stages][tile_bytes]
-    float *sc_s = (float *)(r_s + (size_t)stages * tile_bytes);        // [TC_QT][TC_BM][ks]
-    uint32_t *idx_s = (uint32_t *)(sc_s + (size_t)TC_QT * ks * TC_BM); // [TC_QT][TC_BM][ks]
-    uint64_t *bars = (uint64_t *)(((uintptr_t)(idx_s + (size_t)TC_QT * ks * TC_BM) + 7) & ~(uintptr_t)7);
+    // TC_H = 1: one selection warp per (query tile, TMEM lane quadrant) examines all 128 columns of a tile;
+    // TC_H = 2: two warps share a quadrant, 64 columns each, each with its own heap per row (the re-rank merges
+    // the two candidate lists) — twice the selection throughput for twice the list memory.
+    unsigned long long *heap_s = (unsigned long long *)(r_s + (size_t)stages * tile_bytes);  // [TC_QT*TC_H][TC_BM][ks]
+    uint64_t *bars = (uint64_t *)(heap_s + (size_t)TC_QT * TC_H * ks * TC_BM);
     uint64_t *r_full = bars;                      // [TC_MAX_STAGES]
     uint64_t *r_empty = r_full + TC_MAX_STAGES;   // [TC_MAX_STAGES]
     uint64_t *t_full = r_empty + TC_MAX_STAGES;   // [4]  accumulator buffers, used in rotation by all query tiles
@@ -379,7 +380,7 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < TC_MAX_STAGES; ++i) { mbar_init(&r_full[i], 1); mbar_init(&r_empty[i], TC_QT); }
-        for (int i = 0; i < 4; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4 * TC_H); }
         *turn = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -389,20 +390,17 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (warp >= 4) {  // selection threads initialise their row's list
-        const int qt = (warp - 4) >> 2, row = (warp & 3) * 32 + lane;
-        for (int e = 0; e < kc; ++e) {
-            sc_s[((size_t)qt * TC_BM + row) * ks + e] = INFINITY;
-            idx_s[((size_t)qt * TC_BM + row) * ks + e] = 0xffffffffu;
-        }
+    if (warp >= 4) {  // selection threads initialise their row's heap (all slots empty = the largest key)
+        const int list = (warp - 4) >> 2, row = (warp & 3) * 32 + lane;
+        for (int e = 0; e < kc; ++e) heap_s[((size_t)list * TC_BM + row) * ks + e] = ~0ull;
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if (warp >= 4) {
+    if (warp >= 4 && ((warp - 4) >> 2) % TC_H == 0) {
         // park this thread's query row (BF16x3, kp values) in tensor memory: it is the A operand of every MMA
-        const int qt = (warp - 4) >> 2, quad = warp & 3;
+        const int qt = ((warp - 4) >> 2) / TC_H, quad = warp & 3;
         const int64_t n = ((int64_t)blockIdx.x * TC_QT + qt) * TC_BM + quad * 32 + lane;
         const uint4 *src = reinterpret_cast<const uint4 *>(qrows + (size_t)n * kp * 2);
         const uint32_t dst = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)qt * a_cols;
@@ -471,12 +469,13 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
         // spare warp(s): nothing to do until the final barrier
     } else {
         // ===== selection =====
-        const int qt = (warp - 4) >> 2, quad = warp & 3;
+        const int list = (warp - 4) >> 2, quad = warp & 3;
+        const int qt = list / TC_H, half = list % TC_H;
+        constexpr int COLS = TC_BN / TC_H;   // columns of every tile this warp examines
         const int row = quad * 32 + lane;
-        float *sc_row = sc_s + ((size_t)qt * TC_BM + row) * ks;       // this thread's row
-        uint32_t *idx_row = idx_s + ((size_t)qt * TC_BM + row) * ks;
+        unsigned long long *heap = heap_s + ((size_t)list * TC_BM + row) * ks;   // this thread's row
         float thr = INFINITY;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + acc0;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + acc0 + (uint32_t)(half * COLS);
         int buf = qt % nbuf, use = qt / nbuf;   // chain (i, qt) = sequence number i*QT + qt
         int t_cur = t_home;
         for (int i = 0; i < ntiles; ++i) {
@@ -486,7 +485,7 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
             mbar_wait(&t_full[buf], use & 1);
 #endif
             tc_fence_after();
-            const int64_t ref0 = (int64_t)t_cur * TC_BN;
+            const int64_t ref0 = (int64_t)t_cur * TC_BN + half * COLS;
             if (++t_cur == t_end) t_cur = t_beg;
             const uint32_t acc = lane_base + (uint32_t)(buf * TC_BN);
 #ifdef TC_EXPERIMENT_NO_SELECT
@@ -494,35 +493,42 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
             if (lane == 0) mbar_arrive(&t_empty[buf]);
             __syncwarp();
 #else
-            // pull the whole 128-column accumulator row into registers and hand the TMEM buffer straight back:
-            // the next chain can then run while this tile is examined (the buffer is held for one load latency)
-            uint32_t v0[32], v1[32], v2[32], v3[32];
+            // pull this warp's share of the accumulator row into registers and hand the TMEM buffer straight
+            // back: the next chain can then run while this tile is examined (the buffer is held for one load latency)
+            uint32_t v0[32], v1[32];
             tc_ld32(acc, v0);
             tc_ld32(acc + 32, v1);
-            tc_ld32(acc + 64, v2);
-            tc_ld32(acc + 96, v3);
-            tc_wait_ld();
-            tc_fence_before();
-            if (lane == 0) mbar_arrive(&t_empty[buf]);
-            thr = tc_select32(v0, thr, ref0, M, sc_row, idx_row, kc);
-            thr = tc_select32(v1, thr, ref0 + 32, M, sc_row, idx_row, kc);
-            thr = tc_select32(v2, thr, ref0 + 64, M, sc_row, idx_row, kc);
-            thr = tc_select32(v3, thr, ref0 + 96, M, sc_row, idx_row, kc);
+            if (TC_H == 1) {
+                uint32_t v2[32], v3[32];
+                tc_ld32(acc + 64, v2);
+                tc_ld32(acc + 96, v3);
+                tc_wait_ld();
+                tc_fence_before();
+                if (lane == 0) mbar_arrive(&t_empty[buf]);
+                thr = tc_select32(v0, thr, ref0, M, heap, kc);
+                thr = tc_select32(v1, thr, ref0 + 32, M, heap, kc);
+                thr = tc_select32(v2, thr, ref0 + 64, M, heap, kc);
+                thr = tc_select32(v3, thr, ref0 + 96, M, heap, kc);
+            } else {
+                tc_wait_ld();
+                tc_fence_before();
+                if (lane == 0) mbar_arrive(&t_empty[buf]);
+                thr = tc_select32(v0, thr, ref0, M, heap, kc);
+                thr = tc_select32(v1, thr, ref0 + 32, M, heap, kc);
+            }
             __syncwarp();
 #endif
             // advance the rotation by TC_QT chains
             buf += TC_QT;
             while (buf >= nbuf) { buf -= nbuf; ++use; }
         }
-        // results: the row's candidates as (score, index) keys (unordered) and its final threshold
+        // results: the row's candidates as (score, position) keys (unordered) and its final threshold
         const int64_t n = ((int64_t)blockIdx.x * TC_QT + qt) * TC_BM + row;
         if (n < N) {
-            for (int e = 0; e < kc; ++e) {
-                const uint32_t id = idx_row[e];
-                cand_out[(n * nsplit + split) * kc + e] = id == 0xffffffffu ? ~0ull : knn_make_key(sc_row[e], id);
-            }
+            const int64_t slot = (n * nsplit + split) * TC_H + half;
+            for (int e = 0; e < kc; ++e) cand_out[slot * kc + e] = heap[e];
             const int64_t split_refs = min(M, (int64_t)t_end * TC_BN) - (int64_t)t_beg * TC_BN;
-            thr_out[n * nsplit + split] = split_refs <= kc ? INFINITY : thr;
+            thr_out[slot] = split_refs <= kc ? INFINITY : thr;  // nothing was left out of such a split
         }
     }
     tc_fence_before();
@@ -605,7 +611,7 @@ tc_debug_kernel(const unsigned char *__restrict__ qpack, const unsigned char *__
 // ------------------------------------------------------------------------------------------ host side
 namespace {
 struct TcPlan {
-    int kp, kc, qt, stages, nbuf, nsplit, tiles_per_split, ntiles;
+    int kp, kc, qt, halves, stages, nbuf, nsplit, tiles_per_split, ntiles;
     int64_t qtiles;
     size_t smem, qpack_bytes, cand_bytes, thr_bytes;
     bool ok;
@@ -623,11 +629,19 @@ TcPlan tc_plan(int64_t N, int64_t M, int d, int k) {
     int stages = 0;
     const char *force_qt = getenv("SYM_TC_QT");      // tuning / experiments only
     const char *force_nbuf = getenv("SYM_TC_NBUF");
-    for (int qt = force_qt ? atoi(force_qt) : 2; qt >= 1; --qt) {
-        fixed = (size_t)qt * (kc | 1) * TC_BM * 8 + 256 /* barriers */ + 1024 /* alignment slack */;
+    const char *force_h = getenv("SYM_TC_HALVES");
+    // preference: 256 rows per CTA, then 128.  Two selection warps per quadrant (64 columns each, two heaps per
+    // row) are implemented but measured ~8% slower at config 2, so they are only used when asked for.
+    const int cfg[4][2] = {{2, 1}, {1, 1}, {2, 2}, {1, 2}};
+    for (int c = 0; c < 4; ++c) {
+        const int qt = cfg[c][0], h = cfg[c][1];
+        if (force_qt && atoi(force_qt) != qt) continue;
+        if (force_h ? atoi(force_h) != h : h != 1) continue;
+        fixed = (size_t)qt * h * (kc | 1) * TC_BM * 8 + 256 /* barriers */ + 1024 /* alignment slack */;
         stages = budget > fixed ? (int)((budget - fixed) / tile) : 0;
         if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
         p.qt = qt;
+        p.halves = h;
         p.nbuf = (512 - qt * p.kp / 2) / TC_BN;  // accumulators that fit beside the A operands in tensor memory
         if (p.nbuf > 4) p.nbuf = 4;
         if (force_nbuf && atoi(force_nbuf) >= 1 && atoi(force_nbuf) <= p.nbuf) p.nbuf = atoi(force_nbuf);
@@ -643,7 +657,7 @@ TcPlan tc_plan(int64_t N, int64_t M, int d, int k) {
     if (p.qtiles < kNumSMs) {
         nsplit = (int)ceil_div(kNumSMs, p.qtiles);
         const int by_work = p.ntiles / 16 > 0 ? p.ntiles / 16 : 1;
-        const int by_rerank = 512 / kc > 0 ? 512 / kc : 1;
+        const int by_rerank = 512 / (kc * p.halves) > 0 ? 512 / (kc * p.halves) : 1;
         nsplit = nsplit < by_work ? nsplit : by_work;
         nsplit = nsplit < by_rerank ? nsplit : by_rerank;
         if (nsplit < 1) nsplit = 1;
@@ -651,8 +665,8 @@ TcPlan tc_plan(int64_t N, int64_t M, int d, int k) {
     p.tiles_per_split = (int)ceil_div(p.ntiles, nsplit);
     p.nsplit = (int)ceil_div(p.ntiles, p.tiles_per_split);
     p.qpack_bytes = (size_t)p.qtiles * p.qt * TC_BM * p.kp * 2;  // row-major BF16x3 query rows
-    p.cand_bytes = ((size_t)N * p.nsplit * kc * 8 + 255) & ~(size_t)255;
-    p.thr_bytes = ((size_t)N * p.nsplit * 4 + 255) & ~(size_t)255;
+    p.cand_bytes = ((size_t)N * p.nsplit * p.halves * kc * 8 + 255) & ~(size_t)255;
+    p.thr_bytes = ((size_t)N * p.nsplit * p.halves * 4 + 255) & ~(size_t)255;
     return p;
 }
 }  // namespace
@@ -701,20 +715,25 @@ int knn_tc_scan(const float *Q, int ldq, int64_t N, const int32_t *q_perm, const
         SYM_LAUNCH_CHECK("tc_pack_rows_kernel(query)");
     }
     dim3 grid((unsigned)p.qtiles, (unsigned)p.nsplit);
-    if (p.qt == 2) {
-        SYM_CUDA(cudaFuncSetAttribute(knn_scan_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-        knn_scan_tc_kernel<2><<<grid, 128 + 128 * 2, p.smem, st>>>(qpack, pk.tc, N, q_perm, q_code, cl_tile, M, p.kp, p.kc, p.stages, p.nbuf,
-                                                                  p.tiles_per_split, p.ntiles, cand_w, thr_w);
-    } else {
-        SYM_CUDA(cudaFuncSetAttribute(knn_scan_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-        knn_scan_tc_kernel<1><<<grid, 128 + 128 * 1, p.smem, st>>>(qpack, pk.tc, N, q_perm, q_code, cl_tile, M, p.kp, p.kc, p.stages, p.nbuf,
-                                                                  p.tiles_per_split, p.ntiles, cand_w, thr_w);
-    }
+#define SYM_TC_LAUNCH(QT, H)                                                                                          \
+    do {                                                                                                              \
+        SYM_CUDA(cudaFuncSetAttribute(knn_scan_tc_kernel<QT, H>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                      (int)p.smem));                                                                  \
+        knn_scan_tc_kernel<QT, H><<<grid, 128 + 128 * QT * H, p.smem, st>>>(qpack, pk.tc, N, q_perm, q_code, cl_tile, \
+                                                                          M, p.kp, p.kc, p.stages, p.nbuf,           \
+                                                                          p.tiles_per_split, p.ntiles, cand_w,       \
+                                                                          thr_w);                                    \
+    } while (0)
+    if (p.qt == 2 && p.halves == 2) SYM_TC_LAUNCH(2, 2);
+    else if (p.qt == 2) SYM_TC_LAUNCH(2, 1);
+    else if (p.halves == 2) SYM_TC_LAUNCH(1, 2);
+    else SYM_TC_LAUNCH(1, 1);
+#undef SYM_TC_LAUNCH
     SYM_LAUNCH_CHECK("knn_scan_tc_kernel");
     *cand = cand_w;
     *thr = thr_w;
-    *ncand = p.nsplit * p.kc;
-    *nsplit = p.nsplit;
+    *ncand = p.nsplit * p.halves * p.kc;
+    *nsplit = p.nsplit * p.halves;
     // BF16x3: dropped lo.lo / residual terms are <= ~3 * 2^-16 of |q_i r_i| each; FP32 accumulation on top
     *eps_rel = 6.0e-5;
     return SYM_OK;

@@ -280,8 +280,10 @@ def knn_fit(ref: torch.Tensor, locality: bool = True) -> KnnIndex:
     return KnnIndex(ref=ref, packed=packed, M=M, d=d, centroids=centroids, cl_tile=cl_tile)
 
 
-def knn_search(index: KnnIndex, Q: torch.Tensor, k: int, method: int = KNN_AUTO, want_unsafe: bool = True):
-    """idx [N,k] int32 (ascending by (distance, index)), dist2 [N,k] f32, unsafe [N] uint8 | None."""
+def knn_search(index: KnnIndex, Q: torch.Tensor, k: int, method: int = KNN_AUTO, want_unsafe: bool = True,
+               events: list | None = None):
+    """idx [N,k] int32 (ascending by (distance, index)), dist2 [N,k] f32, unsafe [N] uint8 | None.
+    `events`, if given, receives a (start, end) pair of CUDA events bracketing the scan + re-rank launches."""
     lib = _lib.load()
     Q = _f32c(Q)
     N, d = Q.shape
@@ -301,18 +303,24 @@ def knn_search(index: KnnIndex, Q: torch.Tensor, k: int, method: int = KNN_AUTO,
     if ws is None or ws.numel() < ws_bytes or ws.device != dev:
         ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
         index.workspace[key] = ws
+    if events is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     _lib.check(lib.sym_knn(Q.data_ptr(), Q.stride(0), N, index.ref.data_ptr(), index.ref.stride(0), index.M,
                            index.packed.data_ptr(), d, k, method, _ptr(q_perm), _ptr(q_code), _ptr(cl_tile),
                            idx.data_ptr(), dist2.data_ptr(), _ptr(unsafe), ws.data_ptr(), ws.numel(), _stream(dev)),
                "sym_knn")
+    if events is not None:
+        e1.record()
+        events.append((e0, e1))
     return idx, dist2, unsafe
 
 
-def knn_search_certified(index: KnnIndex, Q: torch.Tensor, k: int, method: int = KNN_AUTO):
+def knn_search_certified(index: KnnIndex, Q: torch.Tensor, k: int, method: int = KNN_AUTO, events: list | None = None):
     """`knn_search` plus the repair pass: rows whose over-selection margin could not be certified
     (possible with the reduced-precision tensor-core scan, or with many exactly tied neighbours) are
     re-run with the FP32 FFMA scan.  Returns (idx, dist2, n_repaired)."""
-    idx, dist2, unsafe = knn_search(index, Q, k, method)
+    idx, dist2, unsafe = knn_search(index, Q, k, method, events=events)
     n_bad = int(unsafe.sum().item())
     if n_bad and os.environ.get("SYM_KNN_NO_REPAIR") != "1":  # (the switch exists for kernel timing experiments only)
         rows = torch.nonzero(unsafe, as_tuple=False).flatten()
