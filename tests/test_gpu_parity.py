@@ -421,3 +421,109 @@ def test_knn_locality_order_does_not_change_results(cuda_device):
         i1, d1, _ = engine.knn_search_certified(local, Q, k, method)
         assert torch.equal(i0, i1) and torch.equal(d0, d1)
     _check_knn(i1.cpu().numpy(), d1.cpu().numpy(), ref, q, k)
+
+
+# ------------------------------------------------------------------------------ edge cases
+def test_empty_and_single_cell_query(cuda_device):
+    quiet()
+    query, ref = synth.small_case(N=64, M=400, G=128, d=20, K=10, L=4, levels=(2,), seed=13)
+    for n in (0, 1):
+        sub = query[np.arange(n), :]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            if n == 0:
+                # pandas cannot describe() an empty frame in the reference either; key=None is the empty-safe path
+                tl.map_embedding(sub, ref, key=None)
+            else:
+                tl.map_embedding(sub, ref, key="batch0")
+            tl.transfer_labels_kNN(sub, ref, "cell_type", n_neighbors=3)
+        assert sub.obsm["X_pca_harmony"].shape == (n, 20) and len(sub.obs["cell_type"]) == n
+    if True:
+        one = query[np.arange(1), :]
+        qo = copy.deepcopy(one)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            tl.map_embedding(one, ref, key="batch0")
+            so.map_embedding(qo, ref, key="batch0")
+        assert row_rel_err(one.obsm["X_pca_harmony"], qo.obsm["X_pca_harmony"]) < EMB_TOL
+
+
+@pytest.mark.parametrize("kind", ["float64", "fortran", "csc", "cuda_tensor", "int_counts"])
+def test_input_container_variants(cuda_device, kind):
+    import scipy.sparse as sp
+
+    quiet()
+    query, ref = synth.small_case(N=300, M=500, G=160, d=20, K=12, L=4, levels=(3,), seed=17, missing_frac=0.1,
+                                  extra_query_genes=20)
+    qo = copy.deepcopy(query)
+    X = np.asarray(query.X)
+    if kind == "int_counts":
+        X = np.floor(X * 3).astype(np.int32)
+        qo.X = X.astype(np.float64)
+        query.X = X
+    elif kind == "float64":
+        query.X = X.astype(np.float64)
+    elif kind == "fortran":
+        query.X = np.asfortranarray(X)
+    elif kind == "csc":
+        query.X = sp.csc_matrix(X)
+    elif kind == "cuda_tensor":
+        query.X = torch.from_numpy(X).to(cuda_device)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        so.map_embedding(qo, ref, key="batch0")
+        if kind == "cuda_tensor":
+            # AnnDataLite slices X with numpy semantics; a device tensor is only valid when no column gather is needed
+            query2, ref2 = synth.small_case(N=300, M=500, G=160, d=20, K=12, L=4, levels=(3,), seed=17)
+            qo = copy.deepcopy(query2)
+            so.map_embedding(qo, ref2, key="batch0")
+            query2.X = torch.from_numpy(np.asarray(query2.X)).to(cuda_device)
+            tl.map_embedding(query2, ref2, key="batch0")
+            query = query2
+        else:
+            tl.map_embedding(query, ref, key="batch0")
+    assert row_rel_err(query.obsm["X_pca_reference"], qo.obsm["X_pca_reference"]) < EMB_TOL
+    assert row_rel_err(query.obsm["X_pca_harmony"], qo.obsm["X_pca_harmony"]) < EMB_TOL
+
+
+def test_many_batch_levels_and_large_k_clusters(cuda_device):
+    """B = 140 levels (the largest ridge system the shared-memory solver takes at d = 20) and K = 300 clusters."""
+    quiet()
+    query, ref = synth.small_case(N=6000, M=1500, G=128, d=20, K=300, L=5, levels=(140,), seed=19)
+    qo = copy.deepcopy(query)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        so.map_embedding(qo, ref, key="batch0", lamb=0.5)
+        tl.map_embedding(query, ref, key="batch0", lamb=0.5)
+    assert row_rel_err(query.obsm["X_pca_harmony"], qo.obsm["X_pca_harmony"]) < EMB_TOL
+    assert np.abs(query.obsm["X_pca_harmony_symphony_R"] - qo.obsm["X_pca_harmony_symphony_R"]).max() < R_TOL
+
+
+def test_numeric_labels_and_k_equal_m(cuda_device):
+    quiet()
+    query, ref = synth.small_case(N=200, M=60, G=64, d=20, K=6, L=3, levels=(1,), seed=23)
+    ref.obs["cluster_id"] = np.arange(60) % 7            # integer labels: classes_ sorted numerically
+    qo = copy.deepcopy(query)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        tl.map_embedding(query, ref)
+        qo.obsm["X_pca_harmony"] = query.obsm["X_pca_harmony"].astype(np.float64)
+        so.transfer_labels_knn(qo, ref, "cluster_id", n_neighbors=60)
+        tl.transfer_labels_kNN(query, ref, "cluster_id", n_neighbors=60)
+    assert (np.asarray(query.obs["cluster_id"]) == np.asarray(qo.obs["cluster_id"])).all()
+
+
+def test_nan_query_rows_do_not_crash(cuda_device):
+    rng = np.random.default_rng(5)
+    ref = rng.normal(size=(40000, 24)).astype(np.float32)
+    q = rng.normal(size=(9000, 24)).astype(np.float32)
+    q[7] = np.nan
+    q[100, 3] = np.inf
+    index = engine.knn_fit(torch.from_numpy(ref).to(cuda_device))
+    idx, dist2, n_rep = engine.knn_search_certified(index, torch.from_numpy(q).to(cuda_device), 5)
+    torch.cuda.synchronize()
+    ok = np.ones(9000, dtype=bool)
+    ok[[7, 100]] = False
+    _check_knn(idx.cpu().numpy()[ok][:500], dist2.cpu().numpy()[ok][:500], ref, q[ok][:500], 5)
+    lab, conf = engine.vote(idx, torch.zeros(40000, dtype=torch.int32, device=cuda_device))
+    assert lab.shape == (9000,)
