@@ -281,22 +281,25 @@ constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((TC_BN >> 3)
 // its votes and shuffles serialise on the critical path.  Deferring the updates into the wait for the next
 // accumulator was slower too: the selection warps have no such slack once updates are frequent.)
 __device__ __noinline__ float tc_insert(unsigned long long *heap, int kc, float s, uint32_t id) {
-    const unsigned long long key = knn_make_key(s, id);
+    // entries are (raw float score bits << 32 | position); only the scores are compared (one FSETP per level) —
+    // equal scores may settle in either order, the float64 re-rank orders the survivors by (distance, index)
+    const unsigned long long key = ((unsigned long long)__float_as_uint(s) << 32) | id;
     int i = 0;
     while (true) {
         const int l = 2 * i + 1;
         if (l >= kc) break;
         const int r = l + 1;
         const unsigned long long vl = heap[l];
-        const unsigned long long vr = r < kc ? heap[r] : 0ull;
-        const bool right = vr > vl;
-        const unsigned long long vc = right ? vr : vl;
-        if (!(vc > key)) break;
-        heap[i] = vc;
+        const unsigned long long vr = r < kc ? heap[r] : 0xff800000ull << 32;  // -inf: never the larger child
+        const float fl = __uint_as_float((uint32_t)(vl >> 32)), fr = __uint_as_float((uint32_t)(vr >> 32));
+        const bool right = fr > fl;
+        const float fc = right ? fr : fl;
+        if (!(fc > s)) break;
+        heap[i] = right ? vr : vl;
         i = right ? r : l;
     }
     heap[i] = key;
-    return knn_key_score(heap[0]);
+    return __uint_as_float((uint32_t)(heap[0] >> 32));
 }
 
 // walk one group of 8 scores of a lane that has a hit in it (plain divergent branches: when no lane of the
@@ -305,10 +308,7 @@ __device__ __noinline__ float tc_insert(unsigned long long *heap, int kc, float 
     if (g##G < thr) {                                                                                 \
         _Pragma("unroll") for (int j = 0; j < 8; ++j) {                                               \
             const float sv = __uint_as_float(v[(G) * 8 + j]);                                         \
-            if (sv < thr) {                                                                           \
-                const int64_t id = ref0 + (G) * 8 + j;                                                \
-                if (id < M) thr = tc_insert(heap, kc, sv, (uint32_t)id);                              \
-            }                                                                                         \
+            if (sv < thr) thr = tc_insert(heap, kc, sv, ref0 + (uint32_t)((G) * 8 + j));              \
         }                                                                                             \
     }
 
@@ -320,8 +320,10 @@ __device__ __forceinline__ float tc_min8(const uint32_t *v) {
 }
 
 // one 32-column chunk of the warp's 32 rows against the rows' thresholds
-__device__ __forceinline__ float tc_select32(const uint32_t (&v)[32], float thr, int64_t ref0, int64_t M,
-                                             unsigned long long *heap, int kc) {
+// (Padding needs no bounds check: padded reference rows carry ||r||^2 = +inf and padded query rows are all-zero
+// operands, so their scores are +inf / NaN and never pass `sv < thr`.)
+__device__ __forceinline__ float tc_select32(const uint32_t (&v)[32], float thr, uint32_t ref0, unsigned long long *heap,
+                                             int kc) {
     const float g0 = tc_min8(v), g1 = tc_min8(v + 8), g2 = tc_min8(v + 16), g3 = tc_min8(v + 24);
     const float m = fminf(fmin3(g0, g1, g2), g3);
 #ifndef TC_EXPERIMENT_NO_WALK
@@ -392,7 +394,7 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
     }
     if (warp >= 4) {  // selection threads initialise their row's heap (all slots empty = the largest key)
         const int list = (warp - 4) >> 2, row = (warp & 3) * 32 + lane;
-        for (int e = 0; e < kc; ++e) heap_s[((size_t)list * TC_BM + row) * ks + e] = ~0ull;
+        for (int e = 0; e < kc; ++e) heap_s[((size_t)list * TC_BM + row) * ks + e] = (0x7f800000ull << 32) | 0xffffffffull;
     }
     tc_fence_before();
     __syncthreads();
@@ -485,7 +487,7 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
             mbar_wait(&t_full[buf], use & 1);
 #endif
             tc_fence_after();
-            const int64_t ref0 = (int64_t)t_cur * TC_BN + half * COLS;
+            const uint32_t ref0 = (uint32_t)(t_cur * TC_BN + half * COLS);
             if (++t_cur == t_end) t_cur = t_beg;
             const uint32_t acc = lane_base + (uint32_t)(buf * TC_BN);
 #ifdef TC_EXPERIMENT_NO_SELECT
@@ -505,16 +507,16 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
                 tc_wait_ld();
                 tc_fence_before();
                 if (lane == 0) mbar_arrive(&t_empty[buf]);
-                thr = tc_select32(v0, thr, ref0, M, heap, kc);
-                thr = tc_select32(v1, thr, ref0 + 32, M, heap, kc);
-                thr = tc_select32(v2, thr, ref0 + 64, M, heap, kc);
-                thr = tc_select32(v3, thr, ref0 + 96, M, heap, kc);
+                thr = tc_select32(v0, thr, ref0, heap, kc);
+                thr = tc_select32(v1, thr, ref0 + 32, heap, kc);
+                thr = tc_select32(v2, thr, ref0 + 64, heap, kc);
+                thr = tc_select32(v3, thr, ref0 + 96, heap, kc);
             } else {
                 tc_wait_ld();
                 tc_fence_before();
                 if (lane == 0) mbar_arrive(&t_empty[buf]);
-                thr = tc_select32(v0, thr, ref0, M, heap, kc);
-                thr = tc_select32(v1, thr, ref0 + 32, M, heap, kc);
+                thr = tc_select32(v0, thr, ref0, heap, kc);
+                thr = tc_select32(v1, thr, ref0 + 32, heap, kc);
             }
             __syncwarp();
 #endif
@@ -526,7 +528,11 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
         const int64_t n = ((int64_t)blockIdx.x * TC_QT + qt) * TC_BM + row;
         if (n < N) {
             const int64_t slot = (n * nsplit + split) * TC_H + half;
-            for (int e = 0; e < kc; ++e) cand_out[slot * kc + e] = heap[e];
+            for (int e = 0; e < kc; ++e) {
+                const unsigned long long h = heap[e];
+                const uint32_t pos = (uint32_t)h;
+                cand_out[slot * kc + e] = pos == 0xffffffffu ? ~0ull : knn_make_key(__uint_as_float((uint32_t)(h >> 32)), pos);
+            }
             const int64_t split_refs = min(M, (int64_t)t_end * TC_BN) - (int64_t)t_beg * TC_BN;
             thr_out[slot] = split_refs <= kc ? INFINITY : thr;  // nothing was left out of such a split
         }
