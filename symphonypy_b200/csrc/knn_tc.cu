@@ -34,6 +34,9 @@ constexpr int TC_BN = 128;        // reference rows per tile (UMMA N)
 // TMEM accumulator buffers per query tile: 4 / QT  (QT * ACC * 128 = 512 columns)
 constexpr int TC_MAX_STAGES = 6;
 constexpr int TC_PAD = 8;         // over-selection: kc = k + TC_PAD
+#ifndef TC_FLUSH
+#define TC_FLUSH 4               // tiles between flushes of the pending hits (power of two)
+#endif
 
 __host__ __device__ inline int tc_kp(int d) { return (3 * d + 3 + 15) / 16 * 16; }
 __host__ __device__ inline size_t tc_tile_bytes(int kp) { return (size_t)kp * 256; }  // 128 rows x kp bf16
@@ -308,7 +311,11 @@ __device__ __noinline__ float tc_insert(unsigned long long *heap, int kc, float 
     if (g##G < thr) {                                                                                 \
         _Pragma("unroll") for (int j = 0; j < 8; ++j) {                                               \
             const float sv = __uint_as_float(v[(G) * 8 + j]);                                         \
-            if (sv < thr) thr = tc_insert(heap, kc, sv, ref0 + (uint32_t)((G) * 8 + j));              \
+            if (sv < thr) {                                                                           \
+                if (pend_id != 0xffffffffu) thr = tc_insert(heap, kc, pend_s, pend_id);               \
+                pend_s = sv;                                                                          \
+                pend_id = ref0 + (uint32_t)((G) * 8 + j);                                             \
+            }                                                                                         \
         }                                                                                             \
     }
 
@@ -322,8 +329,12 @@ __device__ __forceinline__ float tc_min8(const uint32_t *v) {
 // one 32-column chunk of the warp's 32 rows against the rows' thresholds
 // (Padding needs no bounds check: padded reference rows carry ||r||^2 = +inf and padded query rows are all-zero
 // operands, so their scores are +inf / NaN and never pass `sv < thr`.)
+// A hit is parked in a one-entry pending slot (registers) and only goes into the heap when the lane's next hit
+// arrives or at the periodic flush, where all lanes that have something pending update their rows TOGETHER: in
+// the sparse phase of the scan (about one hit per warp and tile) this turns several serial ~400-cycle heap
+// updates into one.  The threshold of a lane with a pending hit is stale by that one entry (never too small).
 __device__ __forceinline__ float tc_select32(const uint32_t (&v)[32], float thr, uint32_t ref0, unsigned long long *heap,
-                                             int kc) {
+                                             int kc, float &pend_s, uint32_t &pend_id) {
     const float g0 = tc_min8(v), g1 = tc_min8(v + 8), g2 = tc_min8(v + 16), g3 = tc_min8(v + 24);
     const float m = fminf(fmin3(g0, g1, g2), g3);
 #ifndef TC_EXPERIMENT_NO_WALK
@@ -477,6 +488,8 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
         const int row = quad * 32 + lane;
         unsigned long long *heap = heap_s + ((size_t)list * TC_BM + row) * ks;   // this thread's row
         float thr = INFINITY;
+        float pend_s = 0.f;
+        uint32_t pend_id = 0xffffffffu;   // no pending hit
         const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + acc0 + (uint32_t)(half * COLS);
         int buf = qt % nbuf, use = qt / nbuf;   // chain (i, qt) = sequence number i*QT + qt
         int t_cur = t_home;
@@ -507,16 +520,20 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
                 tc_wait_ld();
                 tc_fence_before();
                 if (lane == 0) mbar_arrive(&t_empty[buf]);
-                thr = tc_select32(v0, thr, ref0, heap, kc);
-                thr = tc_select32(v1, thr, ref0 + 32, heap, kc);
-                thr = tc_select32(v2, thr, ref0 + 64, heap, kc);
-                thr = tc_select32(v3, thr, ref0 + 96, heap, kc);
+                thr = tc_select32(v0, thr, ref0, heap, kc, pend_s, pend_id);
+                thr = tc_select32(v1, thr, ref0 + 32, heap, kc, pend_s, pend_id);
+                thr = tc_select32(v2, thr, ref0 + 64, heap, kc, pend_s, pend_id);
+                thr = tc_select32(v3, thr, ref0 + 96, heap, kc, pend_s, pend_id);
             } else {
                 tc_wait_ld();
                 tc_fence_before();
                 if (lane == 0) mbar_arrive(&t_empty[buf]);
-                thr = tc_select32(v0, thr, ref0, heap, kc);
-                thr = tc_select32(v1, thr, ref0 + 32, heap, kc);
+                thr = tc_select32(v0, thr, ref0, heap, kc, pend_s, pend_id);
+                thr = tc_select32(v1, thr, ref0 + 32, heap, kc, pend_s, pend_id);
+            }
+            if ((i & (TC_FLUSH - 1)) == TC_FLUSH - 1 && pend_id != 0xffffffffu) {   // periodic flush, lanes in lock-step
+                thr = tc_insert(heap, kc, pend_s, pend_id);
+                pend_id = 0xffffffffu;
             }
             __syncwarp();
 #endif
@@ -524,6 +541,8 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
             buf += TC_QT;
             while (buf >= nbuf) { buf -= nbuf; ++use; }
         }
+        if (pend_id != 0xffffffffu) thr = tc_insert(heap, kc, pend_s, pend_id);
+        __syncwarp();
         // results: the row's candidates as (score, position) keys (unordered) and its final threshold
         const int64_t n = ((int64_t)blockIdx.x * TC_QT + qt) * TC_BM + row;
         if (n < N) {
@@ -626,7 +645,8 @@ struct TcPlan {
 TcPlan tc_plan(int64_t N, int64_t M, int d, int k) {
     TcPlan p{};
     p.kp = tc_kp(d);
-    int kc = k + TC_PAD;
+    const char *force_pad = getenv("SYM_TC_PAD");   // tuning / experiments only
+    int kc = k + (force_pad ? atoi(force_pad) : TC_PAD);
     if (kc > M) kc = (int)M;
     p.kc = kc;
     const size_t tile = tc_tile_bytes(p.kp);
