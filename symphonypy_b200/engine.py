@@ -266,7 +266,7 @@ def knn_fit(ref: torch.Tensor, locality: bool = True) -> KnnIndex:
     M, d = ref.shape
     centroids = cl_tile = order = None
     if locality and M >= LOCALITY_MIN_REF:
-        C = int(min(1024, max(16, M // 2048)))
+        C = int(min(1024, max(16, M // int(os.environ.get("SYM_KNN_CLUSTER_ROWS", "2048")))))
         centroids = _coarse_centroids(ref, C)
         code = nearest_centroid(ref, centroids)
         bo = batch_order(code, C)          # counting sort of the reference rows by cluster
