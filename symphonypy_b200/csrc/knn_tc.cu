@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(128 + 128 * TC_QT * TC_H, 1)
 knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char *__restrict__ rpack, int64_t N,
                    const int32_t *__restrict__ q_perm, const int32_t *__restrict__ q_code,
                    const int32_t *__restrict__ cl_tile, int64_t M, int kp, int kc, int stages, int nbuf,
-                   int tiles_per_split, int ntiles_all,
+                   int tiles_per_split, int ntiles_all, int ss_mode,
                    unsigned long long *__restrict__ cand_out, float *__restrict__ thr_out) {
     extern __shared__ __align__(1024) unsigned char smraw[];
     const uint32_t tile_bytes = (uint32_t)tc_tile_bytes(kp);
@@ -372,6 +372,8 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
     uint64_t *t_empty = t_full + 4;               // [4]
     uint32_t *tmem_slot = (uint32_t *)(t_empty + 4);
     volatile uint32_t *turn = tmem_slot + 1;      // sequence number of the next chain allowed to issue
+    // SS experiment: the query operand stays in shared memory (UMMA tile layout) instead of tensor memory
+    unsigned char *q_s = (unsigned char *)(((uintptr_t)(tmem_slot + 4) + 1023) & ~(uintptr_t)1023);   // [TC_QT][tile_bytes]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int split = blockIdx.y, nsplit = gridDim.y;
@@ -388,7 +390,7 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
         t_home = min(max(t, t_beg), t_end - 1);
     }
     // tensor memory map: A operand of query tile q in columns [q*kp/2, (q+1)*kp/2); accumulator b at acc0 + b*128
-    const uint32_t a_cols = (uint32_t)(kp / 2);
+    const uint32_t a_cols = ss_mode ? 0u : (uint32_t)(kp / 2);
     const uint32_t acc0 = 512u - (uint32_t)nbuf * TC_BN;
 
     if (threadIdx.x == 0) {
@@ -417,8 +419,15 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
         const int64_t n = ((int64_t)blockIdx.x * TC_QT + qt) * TC_BM + quad * 32 + lane;
         const uint4 *src = reinterpret_cast<const uint4 *>(qrows + (size_t)n * kp * 2);
         const uint32_t dst = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)qt * a_cols;
-        for (int k = 0; k < kp / 16; ++k) tc_st8(dst + k * 8, __ldg(src + 2 * k), __ldg(src + 2 * k + 1));
-        tc_wait_st();
+        if (ss_mode) {
+            const int r = quad * 32 + lane;
+            unsigned char *qt_s = q_s + (size_t)qt * tile_bytes + (r / 8) * 128 + (r % 8) * 16;
+            for (int j = 0; j < kp / 8; ++j) *reinterpret_cast<uint4 *>(qt_s + (size_t)j * 2048) = __ldg(src + j);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        } else {
+            for (int k = 0; k < kp / 16; ++k) tc_st8(dst + k * 8, __ldg(src + 2 * k), __ldg(src + 2 * k + 1));
+            tc_wait_st();
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -447,6 +456,9 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
         const int q = warp - 1;
         const int ksteps = kp / 16;
         const bool leader = elect_one();
+        // when every query tile owns its accumulators outright (nbuf multiple of QT) the issuers are independent
+        const bool ordered = TC_QT > 1 && (nbuf % TC_QT) != 0;
+        const uint64_t q_desc = umma_desc(smem_u32(q_s + (size_t)q * tile_bytes));
         int buf = q % nbuf, use = q / nbuf;  // chain (tile i, query tile q) = sequence number i*QT + q
         int s = 0;
         uint32_t ph = 0;
@@ -456,7 +468,7 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
         for (int i = 0; i < ntiles; ++i) {
             mbar_wait(&r_full[s], ph);
             mbar_wait(&t_empty[buf], (use & 1) ^ 1);
-            if (TC_QT > 1) {
+            if (ordered) {
                 const uint32_t seq = (uint32_t)(i * TC_QT + q);
                 while (*turn != seq) {}
             }
@@ -467,11 +479,12 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
                 const uint32_t d_tmem = tmem_base + acc0 + (uint32_t)(buf * TC_BN);
 #pragma unroll 2
                 for (int k = 0; k < ksteps; ++k)   // one K=16 slice: 8 TMEM columns of A, 4096 B (256 units) of B
-                    tc_mma_bf16_ts(d_tmem, a_tmem + (uint32_t)(k * 8), r_desc + (uint64_t)(k * 256), TC_IDESC, k > 0);
+                    if (ss_mode) tc_mma_bf16(d_tmem, q_desc + (uint64_t)(k * 256), r_desc + (uint64_t)(k * 256), TC_IDESC, k > 0);
+                    else tc_mma_bf16_ts(d_tmem, a_tmem + (uint32_t)(k * 8), r_desc + (uint64_t)(k * 256), TC_IDESC, k > 0);
 #endif
                 tc_commit(&t_full[buf]);    // this chain's accumulator is complete
                 tc_commit(&r_empty[s]);     // and this issuer is done with the shared-memory stage
-                if (TC_QT > 1) *turn = (uint32_t)(i * TC_QT + q) + 1u;
+                if (ordered) *turn = (uint32_t)(i * TC_QT + q) + 1u;
             }
             __syncwarp();
             if (++s == stages) { s = 0; ph ^= 1; }
@@ -636,7 +649,7 @@ tc_debug_kernel(const unsigned char *__restrict__ qpack, const unsigned char *__
 // ------------------------------------------------------------------------------------------ host side
 namespace {
 struct TcPlan {
-    int kp, kc, qt, halves, stages, nbuf, nsplit, tiles_per_split, ntiles;
+    int kp, kc, qt, halves, stages, nbuf, nsplit, tiles_per_split, ntiles, ss;
     int64_t qtiles;
     size_t smem, qpack_bytes, cand_bytes, thr_bytes;
     bool ok;
@@ -656,6 +669,7 @@ TcPlan tc_plan(int64_t N, int64_t M, int d, int k) {
     const char *force_qt = getenv("SYM_TC_QT");      // tuning / experiments only
     const char *force_nbuf = getenv("SYM_TC_NBUF");
     const char *force_h = getenv("SYM_TC_HALVES");
+    p.ss = getenv("SYM_TC_SS") && atoi(getenv("SYM_TC_SS")) ? 1 : 0;   // experiment: query operand in shared memory
     // preference: 256 rows per CTA, then 128.  Two selection warps per quadrant (64 columns each, two heaps per
     // row) are implemented but measured ~8% slower at config 2, so they are only used when asked for.
     const int cfg[4][2] = {{2, 1}, {1, 1}, {2, 2}, {1, 2}};
@@ -663,12 +677,13 @@ TcPlan tc_plan(int64_t N, int64_t M, int d, int k) {
         const int qt = cfg[c][0], h = cfg[c][1];
         if (force_qt && atoi(force_qt) != qt) continue;
         if (force_h ? atoi(force_h) != h : h != 1) continue;
-        fixed = (size_t)qt * h * (kc | 1) * TC_BM * 8 + 256 /* barriers */ + 1024 /* alignment slack */;
+        fixed = (size_t)qt * h * (kc | 1) * TC_BM * 8 + 256 /* barriers */ + 1024 /* alignment slack */ +
+                (p.ss ? (size_t)qt * tile + 1024 : 0);
         stages = budget > fixed ? (int)((budget - fixed) / tile) : 0;
         if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
         p.qt = qt;
         p.halves = h;
-        p.nbuf = (512 - qt * p.kp / 2) / TC_BN;  // accumulators that fit beside the A operands in tensor memory
+        p.nbuf = (512 - (p.ss ? 0 : qt * p.kp / 2)) / TC_BN;  // accumulators that fit beside the A operands in tensor memory
         if (p.nbuf > 4) p.nbuf = 4;
         if (force_nbuf && atoi(force_nbuf) >= 1 && atoi(force_nbuf) <= p.nbuf) p.nbuf = atoi(force_nbuf);
         if (stages >= 3 && p.nbuf >= 2) break;
@@ -747,7 +762,7 @@ int knn_tc_scan(const float *Q, int ldq, int64_t N, const int32_t *q_perm, const
                                       (int)p.smem));                                                                  \
         knn_scan_tc_kernel<QT, H><<<grid, 128 + 128 * QT * H, p.smem, st>>>(qpack, pk.tc, N, q_perm, q_code, cl_tile, \
                                                                           M, p.kp, p.kc, p.stages, p.nbuf,           \
-                                                                          p.tiles_per_split, p.ntiles, cand_w,       \
+                                                                          p.tiles_per_split, p.ntiles, p.ss, cand_w, \
                                                                           thr_w);                                    \
     } while (0)
     if (p.qt == 2 && p.halves == 2) SYM_TC_LAUNCH(2, 2);
