@@ -66,6 +66,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--knn-method", type=int, default=0)
+    ap.add_argument("--extras", action="store_true", help="also time the next-row kernels (per_cell_confidence)")
     ap.add_argument("--cpu-n-map", type=int, default=20_000)
     ap.add_argument("--cpu-n-knn", type=int, default=5_000)
     return ap.parse_args()
@@ -360,6 +361,28 @@ def main():
                "api": "symphonypy_b200.tl.map_embedding + tl.transfer_labels_kNN, pinned numpy X in, numpy obsm/obs out"}
         del Xh, q
 
+    extras = None
+    if args.extras and rank == 0:
+        # next row: R-weighted Mahalanobis confidence, device resident
+        Zr2, _, _, _, R_ref = synth.make_reference(model, M, K, 0, keep_R=True)
+        t0e, t1e, t2e = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        Zq = engine.project_dense(X, ld)
+        Rq = engine.assign(Zq, Y, inv_sigma)
+        Rk = R_ref.T.float().contiguous()
+        torch.cuda.synchronize()
+        t0e.record()
+        inv_cov, mean = engine.cluster_covariances(Zr2, Rk)
+        t1e.record()
+        for _ in range(3):
+            conf = engine.cell_confidence(Zq, Rq, mean, inv_cov)
+        t2e.record()
+        torch.cuda.synchronize()
+        extras = {"per_cell_confidence": {"reference_covariances_ms": t0e.elapsed_time(t1e),
+                                          "query_ms": t1e.elapsed_time(t2e) / 3.0, "cells": N, "ref_cells": M,
+                                          "algorithmic_flops_query": 2.0 * N * K * (d * d + d),
+                                          "tflops_query": 2.0 * N * K * (d * d + d) / (t1e.elapsed_time(t2e) / 3.0) / 1e9}}
+        del Zr2, R_ref, Rk
+
     cpu = None
     if rank == 0 and not args.no_cpu:
         cpu = cpu_baseline(w, args.cpu_n_map, args.cpu_n_knn, ref_host=(Zref, comp, C, Nr))
@@ -376,6 +399,8 @@ def main():
             "stage_ms": stage_ms, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if extras is not None:
+            line["extras"] = extras
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -165,6 +165,22 @@ int sym_knn(const float *Q, int32_t ldq, int64_t N, const float *Ref, int32_t ld
 int sym_vote(const int32_t *idx, int64_t N, int32_t k, const int32_t *ref_codes, int64_t M, int32_t *label,
              float *conf, sym_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * (5) per-cell mapping confidence — replaces symphonypy/tl.py:88-111 and _utils.py:468-496
+ *     (next row after the hot path).
+ * sym_cluster_moments: sums [K, d+2] f64 = {sum_m R_km, sum_m R_km^2, sum_m R_km x_m[0..d)} over the
+ *   reference (X [M,ldx], R [K,M] as uns["harmony"]["R"] stores it, float32).
+ * sym_cluster_cov: cov [K,d,d] f64 = sum_m R_km (x_m - mean_k)(x_m - mean_k)^T  (mean [K,d] f32; d <= 64).
+ *   The caller applies the v1/(v1^2 - v2) factor of _utils.py:493 and inverts the K small matrices.
+ * sym_cell_confidence: out[n] = sum_k Rq[n,k] * sqrt((x_n - mean_k)^T inv_cov_k (x_n - mean_k))   (d <= 64).
+ */
+int sym_cluster_moments(const float *X, int32_t ldx, int64_t M, int32_t d, const float *R, int32_t K, double *sums,
+                        sym_stream_t stream);
+int sym_cluster_cov(const float *X, int32_t ldx, int64_t M, int32_t d, const float *R, int32_t K, const float *mean,
+                    double *cov, sym_stream_t stream);
+int sym_cell_confidence(const float *Xq, int32_t ldq, int64_t N, int32_t d, const float *Rq, int32_t K,
+                        const float *mean, const float *inv_cov, float *out, sym_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,5 +65,21 @@ def main():
         print(name, os.path.getsize(path) // 1024, "KiB")
 
 
+def confidence_fixture():
+    """per_cell_confidence (tl.py:33-111): inputs at the function's boundary and the reference's output."""
+    tl, _ = ref_loader.load()
+    query, ref = synth.small_case(N=200, M=500, G=160, d=20, K=10, L=5, levels=(2,), seed=41, keep_R=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        tl.map_embedding(query, ref, key="batch0")
+        tl.per_cell_confidence(query, ref)
+    path = os.path.join(OUT, "confidence_small.npz")
+    np.savez_compressed(path, Xq=query.obsm["X_pca_reference"], Rq=query.obsm["X_pca_harmony_symphony_R"],
+                        Xref=ref.obsm["X_pca_harmony"], Rref=ref.uns["harmony"]["R"],
+                        dist=np.asarray(query.obs["symphony_per_cell_dist"]))
+    print("confidence_small", os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     main()
+    confidence_fixture()

@@ -168,6 +168,46 @@ def map_embedding(adata_query, adata_ref, key=None, lamb=None, sigma=0.1,
     adata_query.obsm[f"{transferred_adjusted_basis}_symphony_R"] = R.T
 
 
+# --------------------------------------------------------------------------- per-cell confidence (next row)
+def cluster_covs(X_ref, R, K):
+    """`_utils.py:468-496`: inverse R-weighted covariance [K, d, d] and weighted mean [K, d, 1] of every
+    reference cluster.  Same arithmetic; the [K, d, N_ref] temporaries of the reference are built per cluster
+    so that a 500k-cell reference does not need 12 GB."""
+    R = np.asarray(R)
+    X_ref = np.asarray(X_ref)
+    v1 = R.sum(axis=1, keepdims=True)
+    v2 = (R ** 2).sum(axis=1, keepdims=True)
+    d = X_ref.shape[1]
+    mean = np.empty((K, d, 1))
+    covs = np.empty((K, d, d))
+    for k in range(K):
+        mean[k, :, 0] = (R[k][None, :] * X_ref.T).sum(axis=1) / v1[k]
+        centered = X_ref.T - mean[k]                       # [d, N_ref]
+        covs[k] = (R[k][None, :] * centered) @ centered.T  # einsum("pq,rq->pr")
+    covs = covs * v1[..., None] / (v1 ** 2 - v2)[..., None]
+    return np.linalg.inv(covs), mean
+
+
+def per_cell_confidence(adata_query, adata_ref, ref_basis_adjusted="X_pca_harmony", query_basis_adjusted="X_pca_harmony",
+                        transferred_primary_basis="X_pca_reference", obs="symphony_per_cell_dist"):
+    """`tl.py:33-111`: R-weighted Mahalanobis distance of every query cell to the reference clusters."""
+    assert "harmony" in adata_ref.uns, \
+        "Harmony object not found in adata_ref.uns['harmony']. First, run standard symphony query mapping."
+    h = adata_ref.uns["harmony"]
+    R = h["R"]
+    K = R.shape[0]
+    if ("inv_cluster_covs" not in h) or ("cluster_centers" not in h):
+        h["inv_cluster_covs"], h["cluster_centers"] = cluster_covs(adata_ref.obsm[ref_basis_adjusted], R, K)
+    inv_covs, centers = h["inv_cluster_covs"], h["cluster_centers"]
+    Xq = adata_query.obsm[transferred_primary_basis]
+    Rq = adata_query.obsm[f"{query_basis_adjusted}_symphony_R"].T
+    out = np.zeros(Xq.shape[0])
+    for k in range(K):  # the reference materialises [K, Nq, d]; same numbers cluster by cluster
+        c = Xq - centers[k, :, 0][None, :]
+        out += Rq[k] * np.sum((c @ inv_covs[k]) * c, axis=1) ** 0.5
+    adata_query.obs[obs] = out
+
+
 # --------------------------------------------------------------------------- kNN transfer
 def transfer_labels_knn(adata_query, adata_ref, ref_labels, *knn_args, query_labels=None,
                         ref_basis="X_pca_harmony", query_basis="X_pca_harmony", **knn_kwargs):

@@ -342,3 +342,40 @@ def vote(idx: torch.Tensor, ref_codes: torch.Tensor, want_conf: bool = True):
                             _stream(dev)),
                "sym_vote")
     return label, conf
+
+
+# ------------------------------------------------------------------------------------- per-cell confidence
+def cluster_covariances(X_ref: torch.Tensor, R_ref: torch.Tensor):
+    """`_cluster_covs` (`symphonypy/_utils.py:468-496`) on the device: inverse R-weighted covariance
+    [K, d, d] and weighted mean [K, d] of every reference cluster, both float64.
+    X_ref [M, d] f32, R_ref [K, M] f32 (the layout of `uns["harmony"]["R"]`)."""
+    lib = _lib.load()
+    X_ref, R_ref = _f32c(X_ref), _f32c(R_ref)
+    M, d = X_ref.shape
+    K = R_ref.shape[0]
+    assert R_ref.shape[1] == M
+    dev = X_ref.device
+    sums = torch.empty((K, d + 2), device=dev, dtype=torch.float64)
+    _lib.check(lib.sym_cluster_moments(X_ref.data_ptr(), X_ref.stride(0), M, d, R_ref.data_ptr(), K, sums.data_ptr(),
+                                       _stream(dev)), "sym_cluster_moments")
+    v1, v2 = sums[:, 0], sums[:, 1]
+    mean = sums[:, 2:] / v1[:, None]
+    cov = torch.empty((K, d, d), device=dev, dtype=torch.float64)
+    mean32 = mean.float().contiguous()
+    _lib.check(lib.sym_cluster_cov(X_ref.data_ptr(), X_ref.stride(0), M, d, R_ref.data_ptr(), K, mean32.data_ptr(),
+                                   cov.data_ptr(), _stream(dev)), "sym_cluster_cov")
+    cov = cov * (v1 / (v1 * v1 - v2))[:, None, None]          # `_utils.py:493`
+    return torch.linalg.inv(cov), mean                          # K tiny d x d inverses (`_utils.py:494`)
+
+
+def cell_confidence(Xq: torch.Tensor, Rq: torch.Tensor, mean: torch.Tensor, inv_cov: torch.Tensor) -> torch.Tensor:
+    """out[n] = sum_k Rq[n,k] * Mahalanobis(x_n; mean_k, cov_k)   (`symphonypy/tl.py:88-111`)."""
+    lib = _lib.load()
+    Xq, Rq = _f32c(Xq), _f32c(Rq)
+    N, d = Xq.shape
+    K = Rq.shape[1]
+    mean32, inv32 = _f32c(mean), _f32c(inv_cov)
+    out = torch.empty(N, device=Xq.device, dtype=torch.float32)
+    _lib.check(lib.sym_cell_confidence(Xq.data_ptr(), Xq.stride(0), N, d, Rq.data_ptr(), K, mean32.data_ptr(),
+                                       inv32.data_ptr(), out.data_ptr(), _stream(Xq.device)), "sym_cell_confidence")
+    return out

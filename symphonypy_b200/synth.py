@@ -97,8 +97,9 @@ def make_model(G: int, d: int, L: int, seed: int, device) -> SynthModel:
     return m
 
 
-def make_reference(model: SynthModel, M: int, K: int, seed: int, chunk: int = 32768):
-    """Reference embedding [M, d], type codes [M], and the Harmony summary."""
+def make_reference(model: SynthModel, M: int, K: int, seed: int, chunk: int = 32768, keep_R: bool = False):
+    """Reference embedding [M, d], type codes [M], and the Harmony summary (plus the reference's own soft
+    assignment R_ref [M, K] when `keep_R`: `uns["harmony"]["R"]`, needed by `per_cell_confidence`)."""
     dev = model.device
     g = _gen(dev, seed + 2)
     Z = torch.empty((M, model.d), device=dev, dtype=torch.float32)
@@ -112,6 +113,7 @@ def make_reference(model: SynthModel, M: int, K: int, seed: int, chunk: int = 32
     Y = cent / cent.norm(dim=1, keepdim=True)
     Nr = torch.zeros(K, device=dev, dtype=torch.float64)
     C = torch.zeros((K, model.d), device=dev, dtype=torch.float64)
+    R_all = torch.empty((M, K), device=dev, dtype=torch.float64) if keep_R else None
     for s in range(0, M, chunk):
         e = min(M, s + chunk)
         z = Z[s:e]
@@ -120,6 +122,10 @@ def make_reference(model: SynthModel, M: int, K: int, seed: int, chunk: int = 32
         r = torch.softmax(-2.0 * (1.0 - zc @ Y.T) / 0.1, dim=1).double()
         Nr += r.sum(0)
         C += r.T @ z.double()
+        if keep_R:
+            R_all[s:e] = r
+    if keep_R:
+        return Z, comp, C, Nr, R_all
     return Z, comp, C, Nr
 
 
@@ -150,7 +156,7 @@ def level_names(v: int, levels: int) -> np.ndarray:
     return np.array([f"b{v}_{i}" for i in range(levels)], dtype=object)
 
 
-def to_anndata(model: SynthModel, Zref, ref_comp, C, Nr, X, codes, K: int,
+def to_anndata(model: SynthModel, Zref, ref_comp, C, Nr, X, codes, K: int, R_ref=None,
                missing_frac: float = 0.0, zero_std_frac: float = 0.0, extra_ref_genes: int = 0,
                extra_query_genes: int = 0, sparse: bool = False, seed: int = 0,
                second_label: bool = False, dtype64: bool = True):
@@ -206,6 +212,8 @@ def to_anndata(model: SynthModel, Zref, ref_comp, C, Nr, X, codes, K: int,
                          "ref_basis_adjusted": "X_pca_harmony", "vars_use": None, "harmony_kwargs": {},
                          "converged": True}},
     )
+    if R_ref is not None:  # [K, M] as `_utils.py:44-61` stores it
+        ref.uns["harmony"]["R"] = R_ref.cpu().numpy().astype(np.float64).T.copy()
 
     # query var table: a shuffled subset of the HVGs plus query-only genes
     keep = np.ones(G, dtype=bool)
@@ -238,6 +246,8 @@ def to_anndata(model: SynthModel, Zref, ref_comp, C, Nr, X, codes, K: int,
 def small_case(N=3000, M=10000, G=2000, d=20, K=100, L=12, levels=(1,), seed=0, device="cpu", **kw):
     """BASELINE config 1 by default: tutorial shape, CPU-runnable."""
     model = make_model(G, d, L, seed, device)
-    Zref, comp, C, Nr = make_reference(model, M, K, seed)
+    keep_R = kw.pop("keep_R", False)
+    parts = make_reference(model, M, K, seed, keep_R=keep_R)
+    Zref, comp, C, Nr = parts[:4]
     X, codes, _ = make_query(model, N, list(levels), seed)
-    return to_anndata(model, Zref, comp, C, Nr, X, codes, K, seed=seed, **kw)
+    return to_anndata(model, Zref, comp, C, Nr, X, codes, K, R_ref=parts[4] if keep_R else None, seed=seed, **kw)

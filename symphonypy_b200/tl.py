@@ -343,6 +343,42 @@ def map_embedding(
             _remember(r_h, R)
 
 
+# ----------------------------------------------------------------------------- per-cell confidence
+def per_cell_confidence(
+    adata_query,
+    adata_ref,
+    ref_basis_adjusted: str = "X_pca_harmony",
+    query_basis_adjusted: str = "X_pca_harmony",
+    transferred_primary_basis: str = "X_pca_reference",
+    obs: str = "symphony_per_cell_dist",
+) -> None:
+    """R-weighted Mahalanobis distance of every query cell to the reference clusters
+    (`symphonypy/tl.py:33-111`); higher = less confident.  Writes `adata_query.obs[obs]`.
+
+    As in the reference, the inverse cluster covariances and centres of the reference are computed on first
+    use (`symphonypy/_utils.py:468-496`) and cached in `adata_ref.uns["harmony"]` under `inv_cluster_covs`
+    [K, d, d] and `cluster_centers` [K, d, 1]."""
+    assert "harmony" in adata_ref.uns, \
+        "Harmony object not found in adata_ref.uns['harmony']. First, run standard symphony query mapping."
+    harmony = adata_ref.uns["harmony"]
+    dev = engine.require_cuda(settings.device)
+    with torch.cuda.device(dev):
+        if ("inv_cluster_covs" not in harmony) or ("cluster_centers" not in harmony):
+            R_ref = torch.from_numpy(np.ascontiguousarray(harmony["R"], dtype=np.float32)).to(dev)
+            X_ref = _device_copy(adata_ref.obsm[ref_basis_adjusted], dev)
+            inv_cov, mean = engine.cluster_covariances(X_ref, R_ref)
+            harmony["inv_cluster_covs"] = inv_cov.cpu().numpy()
+            harmony["cluster_centers"] = mean.cpu().numpy()[..., np.newaxis]
+        else:
+            logger.info("Using precomputed reference's clusters covariance matrices from the Harmony object")
+        inv_cov = torch.from_numpy(np.ascontiguousarray(harmony["inv_cluster_covs"], dtype=np.float32)).to(dev)
+        mean = torch.from_numpy(np.ascontiguousarray(np.asarray(harmony["cluster_centers"])[..., 0], dtype=np.float32)).to(dev)
+        Xq = _device_copy(adata_query.obsm[transferred_primary_basis], dev)
+        Rq = _device_copy(adata_query.obsm[f"{query_basis_adjusted}_symphony_R"], dev)
+        out = engine.cell_confidence(Xq, Rq, mean, inv_cov)
+        adata_query.obs[obs] = _to_host(out)
+
+
 # ----------------------------------------------------------------------------- kNN transfer
 _KNN_DEFAULTS = dict(n_neighbors=5, weights="uniform", algorithm="auto", leaf_size=30, p=2, metric="minkowski",
                      metric_params=None, n_jobs=None)

@@ -18,7 +18,8 @@ from oracle import golden_io, symphony_oracle as so
 from symphonypy_b200 import engine, synth, tl
 
 pytestmark = pytest.mark.gpu
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
+                if not os.path.basename(p).startswith("confidence_"))
 EMB_TOL = 1e-4
 R_TOL = 1e-5
 
@@ -527,3 +528,28 @@ def test_nan_query_rows_do_not_crash(cuda_device):
     _check_knn(idx.cpu().numpy()[ok][:500], dist2.cpu().numpy()[ok][:500], ref, q[ok][:500], 5)
     lab, conf = engine.vote(idx, torch.zeros(40000, dtype=torch.int32, device=cuda_device))
     assert lab.shape == (9000,)
+
+
+# ------------------------------------------------------------------------------ per-cell confidence (next row)
+@pytest.mark.parametrize("d,K", [(20, 12), (30, 40), (50, 25)])
+def test_per_cell_confidence_matches_oracle(cuda_device, d, K):
+    quiet()
+    query, ref = synth.small_case(N=700, M=3000, G=256, d=d, K=K, L=6, levels=(3,), seed=29, keep_R=True)
+    ref_o = copy.deepcopy(ref)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        tl.map_embedding(query, ref, key="batch0")
+        qo = copy.deepcopy(query)
+        for k in list(qo.obsm):
+            qo.obsm[k] = np.asarray(qo.obsm[k], dtype=np.float64)
+        so.per_cell_confidence(qo, ref_o)
+        tl.per_cell_confidence(query, ref)
+    want = np.asarray(qo.obs["symphony_per_cell_dist"])
+    got = np.asarray(query.obs["symphony_per_cell_dist"], dtype=np.float64)
+    assert np.abs(got / want - 1).max() < EMB_TOL
+    np.testing.assert_allclose(ref.uns["harmony"]["inv_cluster_covs"], ref_o.uns["harmony"]["inv_cluster_covs"],
+                               rtol=2e-4, atol=1e-6)
+    assert ref.uns["harmony"]["cluster_centers"].shape == ref_o.uns["harmony"]["cluster_centers"].shape
+    # second call takes the cached covariances, as the reference does
+    tl.per_cell_confidence(query, ref, obs="again")
+    np.testing.assert_allclose(np.asarray(query.obs["again"]), np.asarray(query.obs["symphony_per_cell_dist"]), rtol=1e-6)

@@ -12,7 +12,8 @@ import pytest
 from oracle import golden_io, ref_loader, symphony_oracle as so
 from symphonypy_b200 import synth
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
+                if not os.path.basename(p).startswith("confidence_"))
 
 
 def _run_oracle(query, ref, call):
@@ -91,3 +92,34 @@ def test_assign_sign_flip_quirk():
     Y = np.eye(3)
     R = so.assign_clusters(X, 0.1, Y, 3)
     np.testing.assert_allclose(R[:, 0], R[:, 1])
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present (GPU box)")
+def test_per_cell_confidence_oracle_matches_live_reference():
+    tl, _ = ref_loader.load()
+    logging.getLogger("symphonypy").setLevel(logging.ERROR)
+    query, ref = synth.small_case(N=300, M=900, G=200, d=20, K=12, L=5, levels=(3,), seed=31, keep_R=True)
+    r1, r2 = copy.deepcopy(ref), copy.deepcopy(ref)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        tl.map_embedding(query, r1, key="batch0")
+        q2 = copy.deepcopy(query)
+        tl.per_cell_confidence(query, r1)
+        so.per_cell_confidence(q2, r2)
+    np.testing.assert_allclose(np.asarray(q2.obs["symphony_per_cell_dist"]), np.asarray(query.obs["symphony_per_cell_dist"]),
+                               rtol=1e-10)
+    np.testing.assert_allclose(r2.uns["harmony"]["inv_cluster_covs"], r1.uns["harmony"]["inv_cluster_covs"], rtol=1e-9)
+
+
+def test_per_cell_confidence_golden():
+    """Fixture made by the unmodified reference (oracle/gen_golden.py)."""
+    path = os.path.join(os.path.dirname(__file__), "golden", "confidence_small.npz")
+    z = np.load(path)
+    from symphonypy_b200.anndata_lite import AnnDataLite
+    import pandas as pd
+    q = AnnDataLite(np.zeros((z["Xq"].shape[0], 1), np.float32),
+                    obsm={"X_pca_reference": z["Xq"], "X_pca_harmony_symphony_R": z["Rq"]})
+    r = AnnDataLite(np.zeros((z["Xref"].shape[0], 1), np.float32), obsm={"X_pca_harmony": z["Xref"]},
+                    uns={"harmony": {"R": z["Rref"]}})
+    so.per_cell_confidence(q, r)
+    np.testing.assert_allclose(np.asarray(q.obs["symphony_per_cell_dist"]), z["dist"], rtol=1e-10)
