@@ -150,7 +150,8 @@ int sym_moe_apply(const float *Zin, int32_t ldzin, const float *R, int64_t N, in
  *   that holds rows of cluster c.  Results do not depend on them.
  * sym_vote (predict / predict_proba): label[n] = lowest class code among the most frequent
  *   codes of the k neighbours; conf[n] = winning votes / k.  ref_codes [M]; entries of idx outside [0, M) are
- *   ignored (label -1 if a row has no valid neighbour).
+ *   ignored (label -1 if a row has no valid neighbour).  dist2 NULL: weights="uniform"; dist2 [N,k] (squared
+ *   distances from sym_knn): weights="distance" (1/distance, sklearn's zero-distance rule), conf = winning weight share.
  */
 size_t sym_knn_packed_bytes(int64_t M, int32_t d);
 int sym_knn_fit(const float *Ref, int32_t ldr, int64_t M, int32_t d, const int32_t *order, void *packed,
@@ -162,8 +163,8 @@ int sym_knn(const float *Q, int32_t ldq, int64_t N, const float *Ref, int32_t ld
             const void *packed, int32_t d, int32_t k, int32_t method, const int32_t *q_perm, const int32_t *q_code,
             const int32_t *cl_tile, int32_t *idx, float *dist2, uint8_t *unsafe, void *workspace,
             size_t workspace_bytes, sym_stream_t stream);
-int sym_vote(const int32_t *idx, int64_t N, int32_t k, const int32_t *ref_codes, int64_t M, int32_t *label,
-             float *conf, sym_stream_t stream);
+int sym_vote(const int32_t *idx, const float *dist2, int64_t N, int32_t k, const int32_t *ref_codes, int64_t M,
+             int32_t *label, float *conf, sym_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * (5) per-cell mapping confidence — replaces symphonypy/tl.py:88-111 and _utils.py:468-496

@@ -37,7 +37,7 @@ SIGNATURES = {
     "sym_knn_workspace": (c_size_t, [c_int64, c_int64, c_int32, c_int32, c_int32]),
     "sym_knn": (c_int32, [_P, c_int32, c_int64, _P, c_int32, c_int64, _P, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P,
                           _P, _P, c_size_t, _P]),
-    "sym_vote": (c_int32, [_P, c_int64, c_int32, _P, c_int64, _P, _P, _P]),
+    "sym_vote": (c_int32, [_P, _P, c_int64, c_int32, _P, c_int64, _P, _P, _P]),
     "sym_cluster_moments": (c_int32, [_P, c_int32, c_int64, c_int32, _P, c_int32, _P, _P]),
     "sym_cluster_cov": (c_int32, [_P, c_int32, c_int64, c_int32, _P, c_int32, _P, _P, _P]),
     "sym_cell_confidence": (c_int32, [_P, c_int32, c_int64, c_int32, _P, c_int32, _P, _P, _P, _P]),

@@ -423,8 +423,8 @@ nearest_centroid_kernel(const float *__restrict__ X, int ldx, int64_t N, int d, 
 // code (sklearn: classes_ sorted, argmax takes the first maximum); conf = votes / k.
 constexpr int VT_KMAX = 128;
 __global__ void __launch_bounds__(128)
-knn_vote_kernel(const int32_t *__restrict__ idx, int64_t N, int k, const int32_t *__restrict__ ref_codes, int64_t M,
-                int32_t *__restrict__ label, float *__restrict__ conf) {
+knn_vote_kernel(const int32_t *__restrict__ idx, const float *__restrict__ dist2, int64_t N, int k,
+                const int32_t *__restrict__ ref_codes, int64_t M, int32_t *__restrict__ label, float *__restrict__ conf) {
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     int32_t code[VT_KMAX];
@@ -432,16 +432,43 @@ knn_vote_kernel(const int32_t *__restrict__ idx, int64_t N, int k, const int32_t
         const int32_t id = idx[n * k + j];
         code[j] = (id >= 0 && id < M) ? ref_codes[id] : -1;
     }
-    int best = -1, bestc = 0;
+    if (dist2 == nullptr) {  // weights="uniform"
+        int best = -1, bestc = 0;
+        for (int j = 0; j < k; ++j) {
+            const int32_t cj = code[j];
+            if (cj < 0) continue;
+            int cnt = 0;
+            for (int l = 0; l < k; ++l) cnt += code[l] == cj;
+            if (cnt > bestc || (cnt == bestc && cj < best)) { bestc = cnt; best = cj; }
+        }
+        label[n] = best;
+        if (conf) conf[n] = (float)bestc / (float)k;
+        return;
+    }
+    // weights="distance" (sklearn _get_weights): w = 1/dist; a row with zero distances gives weight 1 to those
+    // neighbours and 0 to the others.  Class with the largest total weight, ties to the lowest class code.
+    bool any_zero = false;
+    for (int j = 0; j < k; ++j) any_zero |= (code[j] >= 0 && dist2[n * k + j] == 0.f);
+    double bestw = -1.0, total = 0.0;
+    int best = -1;
     for (int j = 0; j < k; ++j) {
         const int32_t cj = code[j];
         if (cj < 0) continue;
-        int cnt = 0;
-        for (int l = 0; l < k; ++l) cnt += code[l] == cj;
-        if (cnt > bestc || (cnt == bestc && cj < best)) { bestc = cnt; best = cj; }
+        double w = 0.0;
+        for (int l = 0; l < k; ++l) {
+            if (code[l] != cj) continue;
+            const float d2 = dist2[n * k + l];
+            w += any_zero ? (d2 == 0.f ? 1.0 : 0.0) : 1.0 / sqrt((double)d2);
+        }
+        if (w > bestw || (w == bestw && cj < best)) { bestw = w; best = cj; }
+    }
+    for (int l = 0; l < k; ++l) {
+        if (code[l] < 0) continue;
+        const float d2 = dist2[n * k + l];
+        total += any_zero ? (d2 == 0.f ? 1.0 : 0.0) : 1.0 / sqrt((double)d2);
     }
     label[n] = best;
-    if (conf) conf[n] = (float)bestc / (float)k;
+    if (conf) conf[n] = total > 0.0 ? (float)(bestw / total) : 0.f;
 }
 
 }  // namespace sym
@@ -575,11 +602,12 @@ extern "C" int sym_knn(const float *Q, int32_t ldq, int64_t N, const float *Ref,
     return SYM_OK;
 }
 
-extern "C" int sym_vote(const int32_t *idx, int64_t N, int32_t k, const int32_t *ref_codes, int64_t M, int32_t *label,
-                        float *conf, sym_stream_t stream) {
+extern "C" int sym_vote(const int32_t *idx, const float *dist2, int64_t N, int32_t k, const int32_t *ref_codes, int64_t M,
+                        int32_t *label, float *conf, sym_stream_t stream) {
     SYM_REQUIRE(N >= 0 && k >= 1 && k <= VT_KMAX, SYM_ERR_INVALID_ARGUMENT, "sym_vote: bad sizes (k <= %d)", VT_KMAX);
     if (N == 0) return SYM_OK;
-    knn_vote_kernel<<<(unsigned)ceil_div(N, 128), 128, 0, (cudaStream_t)stream>>>(idx, N, k, ref_codes, M, label, conf);
+    knn_vote_kernel<<<(unsigned)ceil_div(N, 128), 128, 0, (cudaStream_t)stream>>>(idx, dist2, N, k, ref_codes, M, label,
+                                                                                    conf);
     SYM_LAUNCH_CHECK("knn_vote_kernel");
     return SYM_OK;
 }

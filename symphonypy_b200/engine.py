@@ -330,16 +330,17 @@ def knn_search_certified(index: KnnIndex, Q: torch.Tensor, k: int, method: int =
     return idx, dist2, n_bad
 
 
-def vote(idx: torch.Tensor, ref_codes: torch.Tensor, want_conf: bool = True):
-    """Majority vote with sklearn's tie rule (lowest class code); conf = winning fraction."""
+def vote(idx: torch.Tensor, ref_codes: torch.Tensor, want_conf: bool = True, dist2: torch.Tensor | None = None):
+    """Majority vote with sklearn's tie rule (lowest class code); conf = winning fraction.
+    With `dist2` (squared distances of the same neighbours) the vote is weighted by 1/distance."""
     lib = _lib.load()
     N, k = idx.shape
     dev = idx.device
     label = torch.empty(N, device=dev, dtype=torch.int32)
     conf = torch.empty(N, device=dev, dtype=torch.float32) if want_conf else None
     assert ref_codes.dtype == torch.int32 and idx.is_contiguous()
-    _lib.check(lib.sym_vote(idx.data_ptr(), N, k, ref_codes.data_ptr(), ref_codes.numel(), label.data_ptr(), _ptr(conf),
-                            _stream(dev)),
+    _lib.check(lib.sym_vote(idx.data_ptr(), _ptr(dist2), N, k, ref_codes.data_ptr(), ref_codes.numel(), label.data_ptr(),
+                            _ptr(conf), _stream(dev)),
                "sym_vote")
     return label, conf
 

@@ -10,7 +10,7 @@ Differences a user can observe (all documented in DESIGN.md):
     relative against the reference's float64);
   * the no-Harmony fallback (`tl.py:320-335`, reference *building*) is out of scope and
     raises `NotImplementedError`;
-  * kNN options that change the arithmetic (non-Euclidean metric, non-uniform weights)
+  * kNN options the kernels do not implement (non-Euclidean metric, callable weights)
     raise `NotImplementedError` — there is no CPU fallback;
   * opt-in extras (keyword only): `confidence_key=` / `neighbors_key=` on
     `transfer_labels_kNN`;
@@ -403,8 +403,9 @@ def _knn_params(args, kwargs) -> dict:
     if not isinstance(k, numbers.Integral) or isinstance(k, bool) or k < 1:
         raise ValueError(f"The 'n_neighbors' parameter of KNeighborsClassifier must be an int in the range "
                          f"[1, inf) or None. Got {k!r} instead.")
-    if p["weights"] not in ("uniform", None):
-        raise NotImplementedError("symphonypy_b200 implements weights='uniform' only (no CPU fallback)")
+    if p["weights"] not in ("uniform", "distance", None):
+        raise NotImplementedError("symphonypy_b200 implements weights='uniform' and 'distance' (no CPU fallback "
+                                  "for callables)")
     if p["algorithm"] not in ("auto", "brute", "kd_tree", "ball_tree"):
         raise ValueError(f"The 'algorithm' parameter of KNeighborsClassifier must be a str among "
                          f"{{'auto', 'ball_tree', 'brute', 'kd_tree'}}. Got {p['algorithm']!r} instead.")
@@ -489,7 +490,8 @@ def transfer_labels_kNN(
         preds, confs = [], []
         for col in label_cols:
             classes, codes = _encode_labels(adata_ref, col, dev)  # sklearn: classes_ = sorted unique labels
-            lab, conf = engine.vote(idx, codes, want_conf=confidence_key is not None)
+            lab, conf = engine.vote(idx, codes, want_conf=confidence_key is not None,
+                                    dist2=dist2 if params["weights"] == "distance" else None)
             preds.append(classes[_to_host(lab)])
             if conf is not None:
                 confs.append(_to_host(conf))

@@ -553,3 +553,24 @@ def test_per_cell_confidence_matches_oracle(cuda_device, d, K):
     # second call takes the cached covariances, as the reference does
     tl.per_cell_confidence(query, ref, obs="again")
     np.testing.assert_allclose(np.asarray(query.obs["again"]), np.asarray(query.obs["symphony_per_cell_dist"]), rtol=1e-6)
+
+
+def test_distance_weighted_vote_matches_sklearn(cuda_device):
+    from sklearn.neighbors import KNeighborsClassifier
+
+    quiet()
+    query, ref = synth.small_case(N=1500, M=4000, G=200, d=20, K=10, L=9, levels=(1,), seed=37)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        tl.map_embedding(query, ref)
+        # a few query cells that coincide with reference cells: sklearn's zero-distance rule
+        emb = query.obsm["X_pca_harmony"].copy()
+        emb[:20] = ref.obsm["X_pca_harmony"][:20].astype(np.float32)
+        query.obsm["X_pca_harmony"] = emb
+        tl.transfer_labels_kNN(query, ref, "cell_type", n_neighbors=12, weights="distance", confidence_key="p")
+    knn = KNeighborsClassifier(n_neighbors=12, weights="distance").fit(
+        ref.obsm["X_pca_harmony"].astype(np.float32).astype(np.float64), np.asarray(ref.obs["cell_type"]))
+    want = knn.predict(emb.astype(np.float64))
+    proba = knn.predict_proba(emb.astype(np.float64)).max(axis=1)
+    assert (np.asarray(query.obs["cell_type"]) == want).mean() >= 0.999
+    np.testing.assert_allclose(np.asarray(query.obs["p"]), proba, rtol=2e-4, atol=1e-5)

@@ -60,8 +60,9 @@ def test_knn_params_surface():
     assert tl._knn_params((), {})["n_neighbors"] == 5
     assert tl._knn_params((7,), {"algorithm": "kd_tree", "n_jobs": 4})["n_neighbors"] == 7
     assert tl._knn_params((), {"metric": "euclidean", "n_neighbors": 3})["n_neighbors"] == 3
+    assert tl._knn_params((), {"weights": "distance"})["weights"] == "distance"
     with pytest.raises(NotImplementedError):
-        tl._knn_params((), {"weights": "distance"})
+        tl._knn_params((), {"weights": lambda d: d})
     with pytest.raises(NotImplementedError):
         tl._knn_params((), {"metric": "cosine"})
     with pytest.raises(NotImplementedError):
