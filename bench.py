@@ -382,6 +382,28 @@ def main():
                                           "algorithmic_flops_query": 2.0 * N * K * (d * d + d),
                                           "tflops_query": 2.0 * N * K * (d * d + d) / (t1e.elapsed_time(t2e) / 3.0) / 1e9}}
         del Zr2, R_ref, Rk
+        # the same query as a scipy CSR matrix in host memory (the usual AnnData.X container): map_embedding end to end
+        import pandas as pd
+        import scipy.sparse as sp
+        nz = X != 0
+        indptr = torch.zeros(N + 1, dtype=torch.int64, device=dev)
+        indptr[1:] = nz.sum(1).cumsum(0)
+        cols = nz.nonzero()[:, 1].int()
+        csr = sp.csr_matrix((X[nz].cpu().numpy(), cols.cpu().numpy(), indptr.cpu().numpy()), shape=(N, G))
+        del nz, cols
+        qs = AnnDataLite(csr, obs=pd.DataFrame(index=pd.RangeIndex(N).astype(str)),
+                         var=pd.DataFrame(index=pd.Index([f"g{i}" for i in range(G)])), uns={"log1p": {}})
+        _, ref_s = synth.to_anndata(model, Zref, comp, C, Nr, X[:8], codes[:, :8], K, seed=0)
+        ts = []
+        for i in range(4):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            tl.map_embedding(qs, ref_s, key=None)
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        extras["map_embedding_csr_host"] = {"ms": 1000.0 * float(np.mean(ts[2:])), "nnz": int(csr.nnz),
+                                            "h2d_bytes": int(csr.nnz * 8 + (N + 1) * 8)}
+        del qs, csr
 
     cpu = None
     if rank == 0 and not args.no_cpu:
