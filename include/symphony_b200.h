@@ -182,6 +182,21 @@ int sym_cluster_cov(const float *X, int32_t ldx, int64_t M, int32_t d, const flo
 int sym_cell_confidence(const float *Xq, int32_t ldq, int64_t N, int32_t d, const float *Rq, int32_t K,
                         const float *mean, const float *inv_cov, float *out, sym_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * (6) per-cluster mapping confidence — replaces the per-group numpy of symphonypy/_utils.py:422-465
+ *     (tl.per_cluster_confidence, tl.py:114-179).  Cells are grouped by a user-given
+ *     cluster code with sym_batch_order (perm, seg, chunk_start; all NULL when G == 1).
+ * sym_group_sums: sums [G,d] f64 = column sums of the members of every group (d <= 128).
+ * sym_group_cov:  cov [G,d,d] f64 = sum over members of (x - mean_g)(x - mean_g)^T   (mean [G,d] f32; d <= 64).
+ *   The caller divides by (n_g - 1), adds lamb*I, inverts the G small matrices and evaluates
+ *   _utils.py:446-463 on them.
+ */
+int sym_group_sums(const float *X, int32_t ldx, int64_t N, int32_t d, int32_t G, const int32_t *perm,
+                   const int64_t *seg, const int32_t *chunk_start, double *sums, sym_stream_t stream);
+int sym_group_cov(const float *X, int32_t ldx, int64_t N, int32_t d, int32_t G, const int32_t *perm,
+                  const int64_t *seg, const int32_t *chunk_start, const float *mean, double *cov,
+                  sym_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

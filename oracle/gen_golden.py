@@ -80,6 +80,32 @@ def confidence_fixture():
     print("confidence_small", os.path.getsize(path) // 1024, "KiB")
 
 
+def cluster_confidence_fixture():
+    """per_cluster_confidence (tl.py:114-179) on clusters = transferred labels; `obs=None` because the
+    reference's per-cell broadcast (`tl.py:179`) raises KeyError under the pandas of this image."""
+    tl, _ = ref_loader.load()
+    query, ref = synth.small_case(N=400, M=700, G=160, d=12, K=10, L=4, levels=(2,), seed=43)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        tl.map_embedding(query, ref, key="batch0")
+        tl.transfer_labels_kNN(query, ref, "cell_type", n_neighbors=5)
+        query.obs.loc[query.obs.index[:7], "cell_type"] = "rare"      # a cluster below u*d cells
+        tl.per_cluster_confidence(query, ref, "cell_type", obs=None)
+        a = dict(query.uns["symphony_per_cluster_dist"])
+        tl.per_cluster_confidence(query, ref, ["cell_type", "batch0"], lamb=0.5, u=1, obs=None)
+        b = dict(query.uns["symphony_per_cluster_dist"])
+    path = os.path.join(OUT, "confidence_cluster_small.npz")
+    np.savez_compressed(path, Xq=query.obsm["X_pca_reference"], C=ref.uns["harmony"]["C"], Nr=ref.uns["harmony"]["Nr"],
+                        cell_type=np.asarray(query.obs["cell_type"], dtype=str),
+                        batch0=np.asarray(query.obs["batch0"], dtype=str),
+                        dist_a=np.asarray(a["dist"], dtype=np.float64),
+                        labels_a=np.asarray(a["cluster_labels"], dtype=str),
+                        dist_b=np.asarray(b["dist"], dtype=np.float64),
+                        labels_b=np.asarray(["|".join(t) for t in b["cluster_labels"]], dtype=str))
+    print("confidence_cluster_small", os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     main()
     confidence_fixture()
+    cluster_confidence_fixture()

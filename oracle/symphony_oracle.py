@@ -208,6 +208,75 @@ def per_cell_confidence(adata_query, adata_ref, ref_basis_adjusted="X_pca_harmon
     adata_query.obs[obs] = out
 
 
+# --------------------------------------------------------------------------- per-cluster confidence (next row)
+def cluster_maha_dist(query_coords, reference_cluster_centroids, reference_cluster_centroids_norm, u, lamb):
+    """`_utils.py:422-465` for one query cluster given its coordinates [Nq, d]; None when Nq < u*d."""
+    query_coords = np.asarray(query_coords)
+    d = reference_cluster_centroids.shape[1]
+    centroid = query_coords.mean(axis=0)
+    centered = query_coords - centroid
+    with np.errstate(divide="ignore", invalid="ignore"):
+        cov = centered.T @ centered / (centered.shape[0] - 1)
+    closest = reference_cluster_centroids[np.argmax(reference_cluster_centroids_norm @ centroid)]
+    if query_coords.shape[0] < u * d:
+        return None
+    cov = cov + np.diag([lamb] * d)
+    dif = closest - centroid
+    return float((dif @ np.linalg.inv(cov) @ dif) ** 0.5)
+
+
+def per_cluster_confidence(adata_query, adata_ref, cluster_key, u=2, lamb=0,
+                           transferred_primary_basis="X_pca_reference", obs="symphony_per_cluster_dist",
+                           uns="symphony_per_cluster_dist"):
+    """`tl.py:114-179`.  The per-cell column is the broadcast the reference intends at `tl.py:179` (its
+    `dists[x[0]]` raises KeyError under pandas >= 3, so the pinned part is `uns`)."""
+    assert "harmony" in adata_ref.uns, \
+        "Harmony object not found in adata_ref.uns['harmony']. First, run standard symphony query mapping."
+    h = adata_ref.uns["harmony"]
+    cent = h["C"] / h["Nr"][..., np.newaxis]
+    cent_norm = cent / np.linalg.norm(cent, ord=2, axis=1, keepdims=True)
+    X = np.asarray(adata_query.obsm[transferred_primary_basis])
+    grouped = adata_query.obs.groupby(cluster_key)
+    pos = grouped.indices  # label -> row positions
+    labels = grouped.size().index
+    dists = [cluster_maha_dist(X[pos[lab]], cent, cent_norm, u, lamb) for lab in labels]
+    dist = np.array([np.nan if v is None else v for v in dists], dtype=np.float64)
+    if uns is not None:
+        adata_query.uns[uns] = {"key": cluster_key, "dist": dist, "cluster_labels": labels.to_numpy()}
+    if obs is not None:
+        code = grouped.ngroup().to_numpy()
+        adata_query.obs[obs] = np.where(code >= 0, dist[np.clip(code, 0, len(dist) - 1)], np.nan)
+
+
+# --------------------------------------------------------------------------- no-Harmony fallback (next row, SURVEY §8f rank 3)
+def soft_kmeans_summary(Z, C, sigma=0.1, ref_basis="X_pca", ref_basis_loadings="PCs"):
+    """`_utils.py:327-352`: everything `_run_soft_kmeans` stores once the k-means centres C are known
+    (the KMeans call itself, `_utils.py:323-325`, is unseeded sklearn and not reproducible)."""
+    Z = np.asarray(Z)
+    K = C.shape[0]
+    Z_cos = Z.copy()
+    Z_cos /= Z_cos.max(axis=1, keepdims=True)
+    Z_cos /= np.linalg.norm(Z_cos, ord=2, axis=1, keepdims=True)
+    Y = C / np.linalg.norm(C, ord=2, axis=1, keepdims=True)
+    R = assign_clusters(Z_cos, sigma, Y, K)
+    return {"Nr": R.sum(axis=1), "C": C, "K": K, "sigma": None, "ref_basis_loadings": ref_basis_loadings,
+            "ref_basis_adjusted": ref_basis, "vars_use": None, "harmony_kwargs": {}, "converged": True, "R": R}
+
+
+def run_soft_kmeans(adata_ref, ref_basis="X_pca", K=None, ref_basis_loadings="PCs", sigma=0.1, random_state=None):
+    """`_utils.py:311-352` with the reference's estimator call (random_state is ours, for repeatable tests)."""
+    from sklearn.cluster import KMeans
+
+    N = adata_ref.shape[0]
+    if K is None:
+        K = np.min([np.round(N / 30.0), 100]).astype(int)
+    model = KMeans(n_clusters=K, init="k-means++", n_init=10, max_iter=25, random_state=random_state)
+    model.fit(adata_ref.obsm[ref_basis])
+    adata_ref.uns["harmony"] = soft_kmeans_summary(adata_ref.obsm[ref_basis], model.cluster_centers_, sigma,
+                                                   ref_basis, ref_basis_loadings)
+    return model.inertia_
+
+
 # --------------------------------------------------------------------------- kNN transfer
 def transfer_labels_knn(adata_query, adata_ref, ref_labels, *knn_args, query_labels=None,
                         ref_basis="X_pca_harmony", query_basis="X_pca_harmony", **knn_kwargs):

@@ -41,6 +41,8 @@ SIGNATURES = {
     "sym_cluster_moments": (c_int32, [_P, c_int32, c_int64, c_int32, _P, c_int32, _P, _P]),
     "sym_cluster_cov": (c_int32, [_P, c_int32, c_int64, c_int32, _P, c_int32, _P, _P, _P]),
     "sym_cell_confidence": (c_int32, [_P, c_int32, c_int64, c_int32, _P, c_int32, _P, _P, _P, _P]),
+    "sym_group_sums": (c_int32, [_P, c_int32, c_int64, c_int32, c_int32, _P, _P, _P, _P, _P]),
+    "sym_group_cov": (c_int32, [_P, c_int32, c_int64, c_int32, c_int32, _P, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

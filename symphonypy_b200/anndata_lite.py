@@ -52,8 +52,8 @@ class AnnDataLite:
         return self.X.shape[0]
 
     def __getitem__(self, key):
-        """Supports ``adata[:, genes]`` with a list / Index of gene names (the
-        only indexing form the hot path uses, `_utils.py:242,284`)."""
+        """Supports ``adata[:, genes]`` with a list / Index of gene names (the only indexing form the hot path
+        uses, `_utils.py:242,284`) and ``adata[cells, :]`` with positions, a mask or obs names (`_utils.py:431`)."""
         if not (isinstance(key, tuple) and len(key) == 2):
             raise IndexError("AnnDataLite supports adata[rows, genes] indexing only")
         rows, cols = key
@@ -73,6 +73,10 @@ class AnnDataLite:
             row_idx = np.asarray(rows)
             if row_idx.dtype == bool:
                 row_idx = np.flatnonzero(row_idx)
+            elif row_idx.dtype.kind not in "iu":  # obs names (`_utils.py:431` slices a cluster this way)
+                row_idx = self.obs.index.get_indexer(pd.Index(rows))
+                if (row_idx < 0).any():
+                    raise KeyError("some requested cells are not in obs_names")
         X = self.X[row_idx][:, col_idx]
         return AnnDataLite(
             X,

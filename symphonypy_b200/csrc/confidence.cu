@@ -9,6 +9,7 @@
 // BASELINE shapes); here the sums are streamed, FP32 partials with FP64 atomics on the reference side, and the
 // query side is one pass over the cells with the K inverse covariances staged through shared memory.
 #include "common.cuh"
+#include "work_chunks.cuh"
 
 namespace sym {
 
@@ -140,6 +141,82 @@ cell_confidence_kernel(const float *__restrict__ Xq, int ldq, int64_t N, int d, 
     if (n < N) out[n] = total;
 }
 
+// ------------------------------------------------------------------------------------------
+// per-cluster confidence                    — symphonypy/_utils.py:422-465
+// Query cells grouped by a user-given cluster code (sym_batch_order): per group the column sums and the centred
+// scatter matrix sum (x - mean)(x - mean)^T; one chunk of <= 256 members of ONE group per block, FP32 partials,
+// FP64 atomics.  The reference slices the AnnData per group and runs numpy on each slice.
+constexpr int GC_THREADS = 256;
+
+__global__ void __launch_bounds__(GC_THREADS)
+group_sum_kernel(const float *__restrict__ X, int ldx, int64_t N, int d, int G, const int32_t *__restrict__ perm,
+                 const int64_t *__restrict__ seg, const int32_t *__restrict__ chunk_start,
+                 double *__restrict__ sums /*[G][d]*/) {
+    const Chunk ch = find_chunk(blockIdx.x, G, seg, chunk_start, N);
+    if (ch.n == 0) return;
+    extern __shared__ __align__(16) float csm[];   // [GC_THREADS/32][d] warp partials
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = warp; c < ch.n; c += GC_THREADS / 32) {
+        const int64_t id = perm ? (int64_t)perm[ch.pos + c] : ch.pos + c;
+        const float *x = X + id * ldx;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (lane + 32 * q < d) acc[q] += x[lane + 32 * q];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (lane + 32 * q < d) csm[warp * d + lane + 32 * q] = acc[q];
+    __syncthreads();
+    for (int j = threadIdx.x; j < d; j += GC_THREADS) {
+        double t = 0.0;
+        for (int w = 0; w < GC_THREADS / 32; ++w) t += (double)csm[w * d + j];
+        atomicAdd(&sums[(int64_t)ch.level * d + j], t);
+    }
+}
+
+__global__ void __launch_bounds__(GC_THREADS)
+group_cov_kernel(const float *__restrict__ X, int ldx, int64_t N, int d, int G, const int32_t *__restrict__ perm,
+                 const int64_t *__restrict__ seg, const int32_t *__restrict__ chunk_start,
+                 const float *__restrict__ mean /*[G][d]*/, double *__restrict__ cov /*[G][d][d]*/) {
+    const Chunk ch = find_chunk(blockIdx.x, G, seg, chunk_start, N);
+    if (ch.n == 0) return;
+    extern __shared__ __align__(16) float csm[];
+    float *xs = csm;                                                    // [32][d+1] centred members
+    int32_t *ids = reinterpret_cast<int32_t *>(csm + 32 * (d + 1));     // [MOE_CH] member cell ids
+    const int tid = threadIdx.x;
+    for (int c = tid; c < ch.n; c += GC_THREADS) ids[c] = perm ? perm[ch.pos + c] : (int32_t)(ch.pos + c);
+    const int nent = d * d;
+    const float *mu = mean + (int64_t)ch.level * d;
+    float acc[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+    for (int s0 = 0; s0 < ch.n; s0 += 32) {
+        __syncthreads();
+        for (int i = tid; i < 32 * d; i += GC_THREADS) {
+            const int c = i / d, j = i - c * d;
+            xs[c * (d + 1) + j] = (s0 + c < ch.n) ? X[(int64_t)ids[s0 + c] * ldx + j] - mu[j] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            const int ent = tid + e * GC_THREADS;
+            if (ent < nent) {
+                const int i = ent / d, j = ent - i * d;
+                float a = acc[e];
+#pragma unroll 8
+                for (int c = 0; c < 32; ++c) a = fmaf(xs[c * (d + 1) + i], xs[c * (d + 1) + j], a);
+                acc[e] = a;
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+        const int ent = tid + e * GC_THREADS;
+        if (ent < nent) atomicAdd(&cov[(int64_t)ch.level * nent + ent], (double)acc[e]);
+    }
+}
+
 }  // namespace sym
 
 extern "C" int sym_cluster_moments(const float *X, int32_t ldx, int64_t M, int32_t d, const float *R, int32_t K,
@@ -181,5 +258,44 @@ extern "C" int sym_cell_confidence(const float *Xq, int32_t ldq, int64_t N, int3
     else
         cell_confidence_kernel<64, 64><<<(unsigned)ceil_div(N, 64), 64, 0, st>>>(Xq, ldq, N, d, Rq, K, mean, inv_cov, out);
     SYM_LAUNCH_CHECK("cell_confidence_kernel");
+    return SYM_OK;
+}
+
+static int group_args_ok(const int32_t *perm, const int64_t *seg, const int32_t *chunk_start, int32_t G) {
+    return ((perm == nullptr) == (seg == nullptr)) && ((perm == nullptr) == (chunk_start == nullptr)) &&
+           (perm != nullptr || G == 1);
+}
+
+extern "C" int sym_group_sums(const float *X, int32_t ldx, int64_t N, int32_t d, int32_t G, const int32_t *perm,
+                              const int64_t *seg, const int32_t *chunk_start, double *sums, sym_stream_t stream) {
+    using namespace sym;
+    SYM_REQUIRE(N >= 0 && d > 0 && d <= 128 && G > 0 && ldx >= d, SYM_ERR_INVALID_ARGUMENT, "sym_group_sums: bad sizes");
+    SYM_REQUIRE(group_args_ok(perm, seg, chunk_start, G), SYM_ERR_INVALID_ARGUMENT,
+                "sym_group_sums: several groups need the perm, seg and chunk_start of sym_batch_order");
+    cudaStream_t st = (cudaStream_t)stream;
+    SYM_CUDA(cudaMemsetAsync(sums, 0, (size_t)G * d * sizeof(double), st));
+    if (N == 0) return SYM_OK;
+    const int64_t grid = ceil_div(N, MOE_CH) + (perm ? G : 0);
+    group_sum_kernel<<<(unsigned)grid, GC_THREADS, (size_t)(GC_THREADS / 32) * d * sizeof(float), st>>>(
+        X, ldx, N, d, G, perm, seg, chunk_start, sums);
+    SYM_LAUNCH_CHECK("group_sum_kernel");
+    return SYM_OK;
+}
+
+extern "C" int sym_group_cov(const float *X, int32_t ldx, int64_t N, int32_t d, int32_t G, const int32_t *perm,
+                             const int64_t *seg, const int32_t *chunk_start, const float *mean, double *cov,
+                             sym_stream_t stream) {
+    using namespace sym;
+    SYM_REQUIRE(N >= 0 && d > 0 && d <= 64 && G > 0 && ldx >= d, SYM_ERR_INVALID_ARGUMENT,
+                "sym_group_cov: bad sizes (d <= 64)");
+    SYM_REQUIRE(group_args_ok(perm, seg, chunk_start, G), SYM_ERR_INVALID_ARGUMENT,
+                "sym_group_cov: several groups need the perm, seg and chunk_start of sym_batch_order");
+    cudaStream_t st = (cudaStream_t)stream;
+    SYM_CUDA(cudaMemsetAsync(cov, 0, (size_t)G * d * d * sizeof(double), st));
+    if (N == 0) return SYM_OK;
+    const int64_t grid = ceil_div(N, MOE_CH) + (perm ? G : 0);
+    const size_t smem = (size_t)(32 * (d + 1)) * sizeof(float) + MOE_CH * sizeof(int32_t);
+    group_cov_kernel<<<(unsigned)grid, GC_THREADS, smem, st>>>(X, ldx, N, d, G, perm, seg, chunk_start, mean, cov);
+    SYM_LAUNCH_CHECK("group_cov_kernel");
     return SYM_OK;
 }

@@ -11,10 +11,10 @@
 // All K clusters are handled together, and the statistics are a [K,B1,B1+d] FP64 block that a
 // multi-GPU run all-reduces between stats and solve.
 #include "common.cuh"
+#include "work_chunks.cuh"
 
 namespace sym {
 
-constexpr int MOE_CH = 256;       // cells per work chunk (must match the header: "ceil(group/256)")
 constexpr int BO_THREADS = 256;
 constexpr int BO_ITEMS = 4096;    // cells per CTA in the ordering kernels
 constexpr int BO_SMEM_BINS = 4096;
@@ -94,39 +94,6 @@ __global__ void bo_scatter_kernel(const int32_t *__restrict__ codes, int64_t N, 
         c = c < 0 ? 0 : (c >= B ? B - 1 : c);
         perm[atomicAdd(&h[c], 1)] = (int32_t)i;
     }
-}
-
-// ------------------------------------------------------------------------------------------
-// work-list lookup shared by stats and apply: block -> (level, first position, count)
-struct Chunk {
-    int level;
-    int64_t pos;  // first position in perm (or first cell id when perm == nullptr)
-    int n;        // cells in this chunk (0 = nothing to do)
-};
-
-__device__ __forceinline__ Chunk find_chunk(int64_t blk, int n_levels, const int64_t *__restrict__ seg,
-                                            const int32_t *__restrict__ chunk_start, int64_t N) {
-    Chunk c{0, 0, 0};
-    if (seg == nullptr) {  // single level, identity order
-        const int64_t p = blk * MOE_CH;
-        if (p < N) {
-            c.pos = p;
-            c.n = (int)(N - p < MOE_CH ? N - p : MOE_CH);
-        }
-        return c;
-    }
-    if (blk >= chunk_start[n_levels]) return c;
-    int lo = 0, hi = n_levels;  // last level with chunk_start[level] <= blk
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (chunk_start[mid] <= blk) lo = mid; else hi = mid;
-    }
-    const int64_t p = seg[lo] + (blk - chunk_start[lo]) * MOE_CH;
-    const int64_t e = seg[lo + 1];
-    c.level = lo;
-    c.pos = p;
-    c.n = (int)(e - p < MOE_CH ? e - p : MOE_CH);
-    return c;
 }
 
 // ------------------------------------------------------------------------------------------

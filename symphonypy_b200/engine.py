@@ -369,6 +369,104 @@ def cluster_covariances(X_ref: torch.Tensor, R_ref: torch.Tensor):
     return torch.linalg.inv(cov), mean                          # K tiny d x d inverses (`_utils.py:494`)
 
 
+def _group_sums(X: torch.Tensor, order: "BatchOrder", n_groups: int):
+    """size [G] int64, column sums [G, d] float64 of the rows of X per group of `order`."""
+    lib = _lib.load()
+    N, d = X.shape
+    dev = X.device
+    if order.perm is None:
+        size = torch.tensor([N], device=dev, dtype=torch.int64)
+        ptrs = (None, None, None)
+    else:
+        size = order.seg[1:] - order.seg[:-1]
+        ptrs = (order.perm.data_ptr(), order.seg.data_ptr(), order.chunk_start.data_ptr())
+    sums = torch.empty((n_groups, d), device=dev, dtype=torch.float64)
+    _lib.check(lib.sym_group_sums(X.data_ptr(), X.stride(0), N, d, n_groups, *ptrs, sums.data_ptr(), _stream(dev)),
+               "sym_group_sums")
+    return size, sums, ptrs
+
+
+def group_moments(X: torch.Tensor, codes: torch.Tensor, n_groups: int):
+    """Per-group size [G] (int64), mean [G, d] and centred scatter matrix sum (x-mean)(x-mean)^T [G, d, d]
+    (float64) of the rows of X grouped by `codes` in [0, G) — the per-slice numpy of
+    `symphonypy/_utils.py:436-444`, for all groups in two passes over X."""
+    lib = _lib.load()
+    X = _f32c(X)
+    N, d = X.shape
+    dev = X.device
+    assert codes.dtype == torch.int32 and codes.shape == (N,)
+    order = batch_order(codes, n_groups)
+    size, sums, ptrs = _group_sums(X, order, n_groups)
+    mean = sums / size.clamp_min(1)[:, None].double()
+    mean32 = mean.float().contiguous()
+    scatter = torch.empty((n_groups, d, d), device=dev, dtype=torch.float64)
+    _lib.check(lib.sym_group_cov(X.data_ptr(), X.stride(0), N, d, n_groups, *ptrs, mean32.data_ptr(),
+                                 scatter.data_ptr(), _stream(dev)), "sym_group_cov")
+    return size, mean, scatter
+
+
+# ------------------------------------------------------------------------------------- k-means (no-Harmony fallback)
+def _kmeanspp(X: torch.Tensor, Xd: torch.Tensor, x2: torch.Tensor, K: int, gen: torch.Generator) -> torch.Tensor:
+    """Greedy k-means++ seeding (Arthur & Vassilvitskii; 2 + log K candidate draws per centre, the variant
+    sklearn's `init="k-means++"` uses).  K sequential D^2 draws, all on the device, no host synchronisation."""
+    N, d = X.shape
+    dev = X.device
+    trials = 2 + int(np.log(K))
+    cent = torch.empty((K, d), device=dev, dtype=torch.float32)
+    first = torch.randint(N, (1,), generator=gen, device=dev)
+    cent[0] = X[first[0]]
+    c0 = Xd[first]
+    closest = (x2 - 2.0 * (Xd @ c0.T)[:, 0] + (c0 ** 2).sum()).clamp_min_(0.0)
+    pot = closest.sum()
+    for c in range(1, K):
+        r = torch.rand(trials, generator=gen, device=dev, dtype=torch.float64) * pot
+        ids = torch.searchsorted(torch.cumsum(closest, 0), r).clamp_max_(N - 1)
+        cand = Xd[ids]                                                       # [trials, d]
+        dc = (x2[:, None] - 2.0 * (Xd @ cand.T) + (cand ** 2).sum(1)[None, :]).clamp_min_(0.0)
+        dc = torch.minimum(dc, closest[:, None])
+        pots = dc.sum(0)
+        b = torch.argmin(pots)
+        closest = dc[:, b].contiguous()
+        pot = pots[b]
+        cent[c] = X[ids[b]]
+    return cent
+
+
+def kmeans(X: torch.Tensor, K: int, n_init: int = 10, max_iter: int = 25, tol: float = 1e-4, seed: int | None = None):
+    """Lloyd k-means, k-means++ seeding, best of `n_init` runs by inertia: the estimator
+    `KMeans(n_clusters=K, init="k-means++", n_init=10, max_iter=25)` of `symphonypy/_utils.py:323-325`.
+    Assignment step = `sym_nearest_centroid`, update step = `sym_batch_order` + `sym_group_sums` (FP64 sums);
+    a run stops when the squared centre shift falls below tol * mean feature variance (sklearn's rule).
+    Returns (centres [K, d] float64, inertia)."""
+    X = _f32c(X)
+    N, d = X.shape
+    assert 0 < K <= N, "kmeans: need 1 <= K <= number of rows"
+    dev = X.device
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(int(seed) if seed is not None else int.from_bytes(os.urandom(4), "little"))
+    Xd = X.double()
+    x2 = (Xd ** 2).sum(1)
+    total_x2 = x2.sum()
+    tol_abs = float(tol * Xd.var(dim=0, unbiased=False).mean())
+    best_inertia, best_cent = None, None
+    for _ in range(max(1, n_init)):
+        cent32 = _kmeanspp(X, Xd, x2, K, gen)
+        cent = cent32.double()
+        inertia = None
+        for _it in range(max_iter):
+            code = nearest_centroid(X, cent32)
+            size, sums, _ = _group_sums(X, batch_order(code, K), K)
+            new = torch.where(size[:, None] > 0, sums / size.clamp_min(1)[:, None].double(), cent)  # empty: keep
+            shift = float(((new - cent) ** 2).sum())
+            # sum ||x - mean of its cluster||^2 = sum ||x||^2 - sum n_g ||mean_g||^2
+            inertia = float(total_x2 - (size.double() * (new ** 2).sum(1) * (size > 0)).sum())
+            cent, cent32 = new, new.float().contiguous()
+            if shift <= tol_abs:
+                break
+        if best_inertia is None or inertia < best_inertia:
+            best_inertia, best_cent = inertia, cent
+    return best_cent, best_inertia
+
 def cell_confidence(Xq: torch.Tensor, Rq: torch.Tensor, mean: torch.Tensor, inv_cov: torch.Tensor) -> torch.Tensor:
     """out[n] = sum_k Rq[n,k] * Mahalanobis(x_n; mean_k, cov_k)   (`symphonypy/tl.py:88-111`)."""
     lib = _lib.load()

@@ -1,4 +1,5 @@
-"""Drop-in `tl` namespace: `map_embedding` and `transfer_labels_kNN` on B200.
+"""Drop-in `tl` namespace: `map_embedding`, `transfer_labels_kNN`, `per_cell_confidence` and
+`per_cluster_confidence` on B200.
 
 Mirrors `symphonypy/tl.py:271-436` — same signatures, defaults, `obsm` / `obs` keys,
 assertion messages, warnings and logger name — with the numerics of
@@ -8,8 +9,8 @@ replaced by the CUDA kernels behind `include/symphony_b200.h`.
 Differences a user can observe (all documented in DESIGN.md):
   * arrays written to `obsm` are float32 (the kernels compute in FP32; tolerance 1e-4
     relative against the reference's float64);
-  * the no-Harmony fallback (`tl.py:320-335`, reference *building*) is out of scope and
-    raises `NotImplementedError`;
+  * the no-Harmony fallback (`tl.py:320-335`, `_utils.py:311-352`) clusters the reference with a GPU
+    k-means; like the reference's unseeded sklearn call its centres are random;
   * kNN options the kernels do not implement (non-Euclidean metric, callable weights)
     raise `NotImplementedError` — there is no CPU fallback;
   * opt-in extras (keyword only): `confidence_key=` / `neighbors_key=` on
@@ -267,6 +268,41 @@ def _to_host(t: torch.Tensor) -> np.ndarray:
     return arr
 
 
+# ----------------------------------------------------------------------------- no-Harmony fallback
+def _run_soft_kmeans(adata_ref, ref_basis: str = "X_pca", K: int | None = None, ref_basis_loadings: str = "PCs",
+                     sigma: float = 0.1, random_state: int | None = None) -> None:
+    """Reference summary for a reference that was never Harmony-integrated (`symphonypy/_utils.py:311-352`):
+    k-means (k-means++, best of 10 runs, 25 iterations) on `obsm[ref_basis]`, soft assignment of the reference
+    cells to the unit-norm centres, and the same `uns["harmony"]` fields.  Quirks kept: `C` holds the k-means
+    centres (not the R-weighted sums Harmony stores) while `Nr` is the soft count.
+
+    Like the reference (which does not seed sklearn's KMeans) the result is random unless `random_state` is
+    given; the clustering runs on the GPU (`engine.kmeans`)."""
+    N = adata_ref.shape[0]
+    if K is None:
+        K = np.min([np.round(N / 30.0), 100]).astype(int)
+    K = int(K)
+    dev = engine.require_cuda(settings.device)
+    with torch.cuda.device(dev):
+        Z = _device_copy(adata_ref.obsm[ref_basis], dev)
+        C, _ = engine.kmeans(Z, K, n_init=10, max_iter=25, seed=random_state)
+        Y = C / C.norm(dim=1, keepdim=True)
+        R = engine.assign(Z, Y.float().contiguous(), _inv_sigma(sigma, K, dev))     # [N, K]
+        Rt = R.double().T.contiguous()                                             # stored [K, N], as Harmony's R
+        adata_ref.uns["harmony"] = {
+            "Nr": Rt.sum(dim=1).cpu().numpy(),
+            "C": C.cpu().numpy(),
+            "K": K,
+            "sigma": None,
+            "ref_basis_loadings": ref_basis_loadings,
+            "ref_basis_adjusted": ref_basis,
+            "vars_use": None,
+            "harmony_kwargs": {},
+            "converged": True,
+            "R": Rt.cpu().numpy(),
+        }
+
+
 def map_embedding(
     adata_query,
     adata_ref,
@@ -292,10 +328,15 @@ def map_embedding(
     assert "mean" in adata_ref.var, "Gene expression means are expected to be saved in adata_ref.var"
     assert "std" in adata_ref.var, "Gene expression stds are expected to be saved in adata_ref.var"
     if "harmony" not in adata_ref.uns:
-        raise NotImplementedError(
-            "adata_ref.uns['harmony'] not found. The k-means fallback of symphonypy (tl.py:320-335) builds a "
-            "reference and is outside this package's scope: run symphonypy.pp.harmony_integrate (or "
-            "symphonypy's own map_embedding once) on the reference first.")
+        warnings.warn(
+            f"Not found `harmony` object in adata_ref.uns.\n"
+            f"Assuming that adata_ref doesn't have any batches, "
+            f"and using '{reference_primary_basis}' representation of adata_ref for clustering.\n"
+            f"Otherwise, firstly run symphonypy.pp.harmony_integrate "
+            f"on adata_ref to account for them."
+        )
+        _run_soft_kmeans(adata_ref, ref_basis=reference_primary_basis, ref_basis_loadings=ref_basis_loadings,
+                         K=K, sigma=sigma)
     if use_genes_column is not None:
         assert use_genes_column in adata_ref.var, \
             f"Column `{use_genes_column}` not found in adata_ref.var. Set `use_genes_column` parameter properly"
@@ -377,6 +418,68 @@ def per_cell_confidence(
         Rq = _device_copy(adata_query.obsm[f"{query_basis_adjusted}_symphony_R"], dev)
         out = engine.cell_confidence(Xq, Rq, mean, inv_cov)
         adata_query.obs[obs] = _to_host(out)
+
+
+# ----------------------------------------------------------------------------- per-cluster confidence
+def per_cluster_confidence(
+    adata_query,
+    adata_ref,
+    cluster_key,
+    u: float = 2,
+    lamb: float = 0,
+    transferred_primary_basis: str = "X_pca_reference",
+    obs: str | None = "symphony_per_cluster_dist",
+    uns: str | None = "symphony_per_cluster_dist",
+) -> None:
+    """Mahalanobis distance from every user-defined query cluster to its nearest reference centroid
+    (`symphonypy/tl.py:114-179`, `_utils.py:422-465`); higher = less confident.  Clusters with fewer than
+    `u * d` cells get no score (NaN).  Writes `adata_query.uns[uns]` = {key, dist, cluster_labels} and, per cell,
+    `adata_query.obs[obs]`.
+
+    The size, centroid and covariance of all clusters come from two passes over the embedding on the GPU
+    (`engine.group_moments`); the reference slices the AnnData once per cluster.  The G small d x d systems are
+    finished on the host with `np.linalg.inv`, so a singular covariance raises `LinAlgError` as the reference does.
+
+    Quirk: the reference's per-cell broadcast (`tl.py:179`, `dists[x[0]]`) relies on positional `Series[0]`, which
+    raises `KeyError` under pandas >= 3; the intended result (every cell gets its cluster's score) is written."""
+    assert "harmony" in adata_ref.uns, \
+        "Harmony object not found in adata_ref.uns['harmony']. First, run standard symphony query mapping."
+    harmony = adata_ref.uns["harmony"]
+    C_ = np.asarray(harmony["C"], dtype=np.float64)
+    Nr = np.asarray(harmony["Nr"], dtype=np.float64)
+    centroids = C_ / Nr[..., np.newaxis]
+    centroids_norm = centroids / np.linalg.norm(centroids, ord=2, axis=1, keepdims=True)
+
+    grouped = adata_query.obs.groupby(cluster_key)
+    labels = grouped.size().index
+    codes_h = grouped.ngroup().to_numpy()
+    G = len(labels)
+    assert G > 0 and codes_h.max(initial=-1) < G, "per_cluster_confidence: no clusters found"
+    dev = engine.require_cuda(settings.device)
+    with torch.cuda.device(dev):
+        Xq = _device_copy(adata_query.obsm[transferred_primary_basis], dev)
+        d = Xq.shape[1]
+        # cells with a missing key (ngroup == -1) go to an extra group that is dropped
+        codes = torch.from_numpy(np.where(codes_h < 0, G, codes_h).astype(np.int32)).to(dev)
+        size, mean, scatter = engine.group_moments(Xq, codes, G + 1)
+        size_h = size[:G].cpu().numpy()
+        mean_h = mean[:G].cpu().numpy()
+        scatter_h = scatter[:G].cpu().numpy()
+
+    dist = np.full(G, np.nan)
+    for g in range(G):
+        if size_h[g] < u * d:
+            logger.info("cluster contains too few cells to estimate confidence: ', query_cluster_labels_unique[c])")
+            continue
+        cov = scatter_h[g] / (size_h[g] - 1) + np.diag([lamb] * d)
+        closest = centroids[np.argmax(centroids_norm @ mean_h[g])]
+        dif = closest - mean_h[g]
+        dist[g] = float((dif @ np.linalg.inv(cov) @ dif) ** 0.5)
+
+    if uns is not None:
+        adata_query.uns[uns] = {"key": cluster_key, "dist": dist, "cluster_labels": labels.to_numpy()}
+    if obs is not None:
+        adata_query.obs[obs] = np.where(codes_h >= 0, dist[np.clip(codes_h, 0, G - 1)], np.nan)
 
 
 # ----------------------------------------------------------------------------- kNN transfer

@@ -555,6 +555,120 @@ def test_per_cell_confidence_matches_oracle(cuda_device, d, K):
     np.testing.assert_allclose(np.asarray(query.obs["again"]), np.asarray(query.obs["symphony_per_cell_dist"]), rtol=1e-6)
 
 
+# ------------------------------------------------------------------------------ per-cluster confidence (next row)
+def _cluster_conf_query(z):
+    import pandas as pd
+    from symphonypy_b200.anndata_lite import AnnDataLite
+    n = z["Xq"].shape[0]
+    q = AnnDataLite(np.zeros((n, 1), np.float32),
+                    obs=pd.DataFrame({"cell_type": z["cell_type"], "batch0": z["batch0"]},
+                                     index=pd.RangeIndex(n).astype(str)),
+                    obsm={"X_pca_reference": z["Xq"]})
+    r = AnnDataLite(np.zeros((2, 1), np.float32), uns={"harmony": {"C": z["C"], "Nr": z["Nr"]}})
+    return q, r
+
+
+def test_per_cluster_confidence_matches_reference_golden(cuda_device):
+    """Fixture written by the unmodified reference (oracle/gen_golden.py::cluster_confidence_fixture)."""
+    quiet()
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "confidence_cluster_small.npz"))
+    q, r = _cluster_conf_query(z)
+    tl.per_cluster_confidence(q, r, "cell_type")
+    out = q.uns["symphony_per_cluster_dist"]
+    assert out["key"] == "cell_type" and list(out["cluster_labels"]) == list(z["labels_a"])
+    np.testing.assert_allclose(out["dist"], z["dist_a"], rtol=EMB_TOL, equal_nan=True)
+    per_cell = np.asarray(q.obs["symphony_per_cluster_dist"])
+    want = dict(zip(z["labels_a"], z["dist_a"]))
+    np.testing.assert_allclose(per_cell, [want[c] for c in z["cell_type"]], rtol=EMB_TOL, equal_nan=True)
+    tl.per_cluster_confidence(q, r, ["cell_type", "batch0"], lamb=0.5, u=1, obs=None, uns="two_keys")
+    out = q.uns["two_keys"]
+    assert ["|".join(t) for t in out["cluster_labels"]] == list(z["labels_b"])
+    np.testing.assert_allclose(out["dist"], z["dist_b"], rtol=EMB_TOL, equal_nan=True)
+
+
+@pytest.mark.parametrize("d,groups", [(20, 1), (30, 37), (50, 300)])
+def test_per_cluster_confidence_matches_oracle(cuda_device, d, groups):
+    """Many clusters of ragged size (some empty-ish, some below u*d), offset far from the origin so that the
+    centring matters; single-cluster case takes the unsorted path."""
+    import pandas as pd
+    from symphonypy_b200.anndata_lite import AnnDataLite
+    quiet()
+    rng = np.random.default_rng(d + groups)
+    n = 20000
+    code = np.minimum((rng.pareto(1.2, n) * 3).astype(np.int64), groups - 1)
+    A = rng.normal(size=(groups, d, d)) / np.sqrt(d)
+    X = (np.einsum("nij,nj->ni", A[code], rng.normal(size=(n, d))) + 25.0 + rng.normal(size=(groups, d))[code])
+    X = X.astype(np.float32)
+    obs = pd.DataFrame({"cl": pd.Categorical([f"g{c:03d}" for c in code])}, index=pd.RangeIndex(n).astype(str))
+    K = 15
+    h = {"C": rng.normal(size=(K, d)) * 40 + 100, "Nr": rng.uniform(3, 9, K)}
+    q = AnnDataLite(np.zeros((n, 1), np.float32), obs=obs, obsm={"X_pca_reference": X})
+    r = AnnDataLite(np.zeros((2, 1), np.float32), uns={"harmony": h})
+    qo = copy.deepcopy(q)
+    so.per_cluster_confidence(qo, r, "cl", lamb=1e-3)
+    tl.per_cluster_confidence(q, r, "cl", lamb=1e-3)
+    a, b = q.uns["symphony_per_cluster_dist"], qo.uns["symphony_per_cluster_dist"]
+    assert list(a["cluster_labels"]) == list(b["cluster_labels"])
+    assert np.isnan(a["dist"]).sum() == np.isnan(b["dist"]).sum()
+    np.testing.assert_allclose(a["dist"], b["dist"], rtol=EMB_TOL, equal_nan=True)
+    np.testing.assert_allclose(np.asarray(q.obs["symphony_per_cluster_dist"]),
+                               np.asarray(qo.obs["symphony_per_cluster_dist"]), rtol=EMB_TOL, equal_nan=True)
+
+# ------------------------------------------------------------------------------ no-Harmony fallback (next row)
+@pytest.mark.parametrize("M,d,K", [(6000, 20, 30), (40000, 30, 100)])
+def test_kmeans_quality_matches_sklearn(cuda_device, M, d, K):
+    """The reference's estimator is unseeded, so parity is on the objective: best-of-10 inertia within 2 % of
+    sklearn's `KMeans(n_clusters=K, init="k-means++", n_init=10, max_iter=25)` on the same rows, and the reported
+    inertia equal to the directly computed one."""
+    from sklearn.cluster import KMeans
+
+    rng = np.random.default_rng(M)
+    centres = rng.normal(size=(K // 2, d)) * 3
+    X = (centres[rng.integers(0, K // 2, M)] + rng.normal(size=(M, d))).astype(np.float32)
+    C, inertia = engine.kmeans(torch.from_numpy(X).to(cuda_device), K, seed=7)
+    C = C.cpu().numpy()
+    assert C.shape == (K, d)
+    direct = ((X.astype(np.float64)[:, None, :] - C[None]) ** 2).sum(-1).min(1).sum() if M * K < 5e6 else None
+    if direct is not None:
+        assert abs(direct / inertia - 1) < 1e-3          # final E-step may only lower it slightly
+        assert direct <= inertia * (1 + 1e-9)
+    sk = KMeans(n_clusters=K, init="k-means++", n_init=10, max_iter=25, random_state=0).fit(X.astype(np.float64))
+    assert inertia <= sk.inertia_ * 1.02
+
+
+def test_map_embedding_without_harmony_uses_soft_kmeans(cuda_device):
+    quiet()
+    query, ref = synth.small_case(N=500, M=3000, G=200, d=20, K=10, L=6, levels=(2,), seed=47)
+    ref.obsm["X_pca"] = ref.obsm["X_pca_harmony"]
+    del ref.uns["harmony"]
+    with pytest.warns(UserWarning, match="Not found `harmony` object in adata_ref.uns"):
+        tl.map_embedding(query, ref, key="batch0")
+    h = ref.uns["harmony"]
+    assert h["K"] == 100 and h["C"].shape == (100, 20) and h["R"].shape == (100, 3000)
+    assert h["ref_basis_loadings"] == "PCs" and h["ref_basis_adjusted"] == "X_pca" and h["converged"] is True
+    want = so.soft_kmeans_summary(np.asarray(ref.obsm["X_pca"], dtype=np.float64), h["C"], 0.1)
+    assert np.abs(h["R"] - want["R"]).max() < R_TOL
+    np.testing.assert_allclose(h["Nr"], want["Nr"], rtol=EMB_TOL)
+    assert set(h) == set(want)
+    # with the summary the product built, the mapping itself equals the oracle's
+    qo = copy.deepcopy(query)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        so.map_embedding(qo, ref, key="batch0")
+    assert row_rel_err(query.obsm["X_pca_harmony"], qo.obsm["X_pca_harmony"]) < EMB_TOL
+    # explicit K and a second call (harmony now present: no warning, no re-clustering)
+    C_before = h["C"].copy()
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        tl.map_embedding(query, ref, key="batch0")
+    assert not any("Not found `harmony`" in str(w.message) for w in rec)
+    assert np.array_equal(ref.uns["harmony"]["C"], C_before)
+    r2 = copy.deepcopy(ref)
+    del r2.uns["harmony"]
+    with pytest.warns(UserWarning):
+        tl.map_embedding(query, r2, K=17)
+    assert r2.uns["harmony"]["K"] == 17 and r2.uns["harmony"]["R"].shape == (17, 3000)
+
 def test_distance_weighted_vote_matches_sklearn(cuda_device):
     from sklearn.neighbors import KNeighborsClassifier
 

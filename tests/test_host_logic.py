@@ -80,9 +80,18 @@ def test_map_embedding_asserts_like_reference():
         tl.map_embedding(q, bad)
     with pytest.raises(AssertionError, match="not found in adata_ref.var"):
         tl.map_embedding(q, r, use_genes_column="nope")
+
+
+def test_missing_harmony_warns_like_reference_then_needs_the_gpu(monkeypatch):
+    """`tl.py:320-335`: the k-means fallback is announced with the reference's warning; it runs on the GPU only."""
+    import torch
+
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: False)
+    q, r = synth.small_case(N=20, M=50, G=32, d=20, K=4, L=3, seed=1)
     no_h = AnnDataLite(r.X, obs=r.obs, var=r.var, obsm=r.obsm, varm=r.varm, uns={})
-    with pytest.raises(NotImplementedError):
-        tl.map_embedding(q, no_h)
+    with pytest.warns(UserWarning, match="Not found `harmony` object in adata_ref.uns"):
+        with pytest.raises(_lib.SymphonyLibraryError, match="no CPU path"):
+            tl.map_embedding(q, no_h)
 
 
 def test_no_cpu_fallback(monkeypatch):

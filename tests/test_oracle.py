@@ -123,3 +123,64 @@ def test_per_cell_confidence_golden():
                     uns={"harmony": {"R": z["Rref"]}})
     so.per_cell_confidence(q, r)
     np.testing.assert_allclose(np.asarray(q.obs["symphony_per_cell_dist"]), z["dist"], rtol=1e-10)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present (GPU box)")
+def test_per_cluster_confidence_oracle_matches_live_reference():
+    import pandas as pd
+    from symphonypy_b200.anndata_lite import AnnDataLite
+    tl, _ = ref_loader.load()
+    logging.getLogger("symphonypy").setLevel(logging.ERROR)
+    rng = np.random.default_rng(5)
+    n, d, K = 900, 6, 9
+    obs = pd.DataFrame({"cl": rng.integers(0, 5, n).astype(str), "b": rng.integers(0, 2, n).astype(str)},
+                       index=[f"c{i}" for i in range(n)])
+    obs.loc[obs.index[:4], "cl"] = "tiny"
+    q = AnnDataLite(np.zeros((n, 1), np.float32), obs=obs, obsm={"X_pca_reference": rng.normal(size=(n, d)) + 2})
+    r = AnnDataLite(np.zeros((2, 1), np.float32),
+                    uns={"harmony": {"C": rng.normal(size=(K, d)) * 10, "Nr": rng.uniform(5, 20, K)}})
+    for key, lamb in (("cl", 0), (["cl", "b"], 0.25)):
+        q1, q2 = copy.deepcopy(q), copy.deepcopy(q)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            tl.per_cluster_confidence(q1, r, key, lamb=lamb, obs=None)   # obs: KeyError under pandas >= 3 (tl.py:179)
+            so.per_cluster_confidence(q2, r, key, lamb=lamb)
+        a, b = q1.uns["symphony_per_cluster_dist"], q2.uns["symphony_per_cluster_dist"]
+        assert list(a["cluster_labels"]) == list(b["cluster_labels"])
+        np.testing.assert_allclose(np.asarray(a["dist"], dtype=np.float64), b["dist"], rtol=1e-12, equal_nan=True)
+        assert np.isnan(b["dist"]).any()
+
+
+def test_per_cluster_confidence_golden():
+    """Fixture made by the unmodified reference (oracle/gen_golden.py::cluster_confidence_fixture)."""
+    import pandas as pd
+    from symphonypy_b200.anndata_lite import AnnDataLite
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "confidence_cluster_small.npz"))
+    n = z["Xq"].shape[0]
+    q = AnnDataLite(np.zeros((n, 1), np.float32),
+                    obs=pd.DataFrame({"cell_type": z["cell_type"], "batch0": z["batch0"]}, index=pd.RangeIndex(n).astype(str)),
+                    obsm={"X_pca_reference": z["Xq"]})
+    r = AnnDataLite(np.zeros((2, 1), np.float32), uns={"harmony": {"C": z["C"], "Nr": z["Nr"]}})
+    so.per_cluster_confidence(q, r, "cell_type")
+    np.testing.assert_allclose(q.uns["symphony_per_cluster_dist"]["dist"], z["dist_a"], rtol=1e-10, equal_nan=True)
+    so.per_cluster_confidence(q, r, ["cell_type", "batch0"], lamb=0.5, u=1)
+    np.testing.assert_allclose(q.uns["symphony_per_cluster_dist"]["dist"], z["dist_b"], rtol=1e-10, equal_nan=True)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present (GPU box)")
+def test_soft_kmeans_summary_matches_live_reference():
+    """The reference's fallback (`_utils.py:311-352`) is random in its centres; given those centres every stored
+    field must be reproduced exactly."""
+    _, utils = ref_loader.load()
+    _, ref = synth.small_case(N=20, M=600, G=64, d=10, K=5, L=4, seed=3)
+    ref.obsm["X_pca"] = np.asarray(ref.obsm["X_pca_harmony"], dtype=np.float64)
+    del ref.uns["harmony"]
+    utils._run_soft_kmeans(ref, ref_basis="X_pca", K=None, sigma=0.1)
+    h = ref.uns["harmony"]
+    assert h["K"] == 20 and h["C"].shape == (20, 10)
+    mine = so.soft_kmeans_summary(ref.obsm["X_pca"], h["C"], 0.1)
+    assert set(mine) == set(h)
+    np.testing.assert_allclose(mine["R"], h["R"], rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(mine["Nr"], h["Nr"], rtol=1e-12)
+    for k in ("K", "sigma", "ref_basis_loadings", "ref_basis_adjusted", "vars_use", "harmony_kwargs", "converged"):
+        assert mine[k] == h[k]
