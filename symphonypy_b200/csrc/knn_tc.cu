@@ -22,6 +22,7 @@
 // and only on a hit walks the 32 values and updates the row's top-kc list in shared memory.
 // The scan over-selects (kc = k + 8); the float64 re-rank in knn.cu certifies the margin with the
 // scores recorded here and flags rows that need the FP32 scan.
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "knn_common.cuh"
@@ -38,7 +39,13 @@ constexpr int TC_PAD = 8;         // over-selection: kc = k + TC_PAD
 #define TC_FLUSH 4               // tiles between flushes of the pending hits (power of two)
 #endif
 
-__host__ __device__ inline int tc_kp(int d) { return (3 * d + 3 + 15) / 16 * 16; }
+// operand precision: 0 = BF16x3 (three split products, K' = 3d+3), 1 = single FP16 (K' = d+2)
+inline int tc_prec() {
+    static int prec = -1;
+    if (prec < 0) prec = getenv("SYM_TC_FP16") && atoi(getenv("SYM_TC_FP16")) ? 1 : 0;
+    return prec;
+}
+inline int tc_kp(int d) { return tc_prec() ? (d + 2 + 15) / 16 * 16 : (3 * d + 3 + 15) / 16 * 16; }
 __host__ __device__ inline size_t tc_tile_bytes(int kp) { return (size_t)kp * 256; }  // 128 rows x kp bf16
 
 // ------------------------------------------------------------------------------------------ packing
@@ -49,12 +56,14 @@ __device__ __forceinline__ unsigned short bf16_rn(float x) {
     return (unsigned short)(u >> 16);
 }
 __device__ __forceinline__ float bf16_to_f(unsigned short h) { return __uint_as_float((unsigned)h << 16); }
+__device__ __forceinline__ unsigned short f16_rn(float x) { return __half_as_ushort(__float2half_rn(x)); }
+__device__ __forceinline__ float f16_to_f(unsigned short h) { return __half2float(__ushort_as_half(h)); }
 
 // One thread = one row x one k-unit (8 consecutive K' indices, 16 bytes).
 // Element (r, kk) of a tile lives at  (kk/8)*2048 + (r/8)*128 + (r%8)*16 + (kk%8)*2  bytes.
 __global__ void __launch_bounds__(256)
 tc_pack_kernel(const float *__restrict__ src, int ld, int64_t rows, int64_t rows_pad, int d, int kp, int is_query,
-               const int32_t *__restrict__ gather, unsigned char *__restrict__ dst) {
+               const int32_t *__restrict__ gather, unsigned char *__restrict__ dst, int prec) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;  // k-unit
     if (r >= rows_pad) return;
@@ -63,14 +72,29 @@ tc_pack_kernel(const float *__restrict__ src, int ld, int64_t rows, int64_t rows
     const float *x = src + ((real && gather) ? (int64_t)gather[r] : (real ? r : 0)) * ld;
     float nrm = 0.f;
     const int k0 = j * 8;
-    if (real && !is_query && k0 + 8 > 3 * d && k0 < 3 * d + 3) {
+    const int nk = prec ? d : 3 * d;   // first K' index of the ||r||^2 pieces
+    if (real && !is_query && k0 + 8 > nk && k0 < nk + 3) {
         for (int c = 0; c < d; ++c) nrm = fmaf(x[c], x[c], nrm);
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         const int kk = k0 + e;
         unsigned short v = 0;
-        if (kk < 3 * d) {
+        if (prec) {   // single FP16: [x (d) | two fp16 pieces of ||r||^2  /  1 1]
+            if (kk < d) {
+                if (real) v = f16_rn(is_query ? -2.f * x[kk] : x[kk]);
+            } else if (kk < d + 2) {
+                const int p = kk - d;
+                if (is_query) {
+                    v = real ? 0x3c00 : 0;  // 1.0
+                } else if (real) {
+                    const unsigned short n1 = f16_rn(nrm);
+                    v = p == 0 ? n1 : f16_rn(nrm - f16_to_f(n1));
+                } else {
+                    v = p == 0 ? 0x7c00 : 0;  // +inf
+                }
+            }
+        } else if (kk < 3 * d) {
             if (real) {
                 const int seg = kk / d, c = kk - seg * d;
                 const float val = is_query ? -2.f * x[c] : x[c];
@@ -109,7 +133,7 @@ tc_pack_kernel(const float *__restrict__ src, int ld, int64_t rows, int64_t rows
 // loads its own row).  One thread = one row x one k-unit, as above.
 __global__ void __launch_bounds__(256)
 tc_pack_rows_kernel(const float *__restrict__ src, int ld, int64_t rows, int64_t rows_pad, int d, int kp,
-                    const int32_t *__restrict__ gather, unsigned char *__restrict__ dst) {
+                    const int32_t *__restrict__ gather, unsigned char *__restrict__ dst, int prec) {
     const int64_t r = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;  // a warp walks the k-units of a row
     if (r >= rows_pad) return;
     const bool real = r < rows;
@@ -120,7 +144,10 @@ tc_pack_rows_kernel(const float *__restrict__ src, int ld, int64_t rows, int64_t
         for (int e = 0; e < 8; ++e) {
             const int kk = j * 8 + e;
             unsigned short v = 0;
-            if (real && kk < 3 * d) {
+            if (prec) {
+                if (real && kk < d) v = f16_rn(-2.f * x[kk]);
+                else if (real && kk < d + 2) v = 0x3c00;
+            } else if (real && kk < 3 * d) {
                 const int seg = kk / d, c = kk - seg * d;
                 const float val = -2.f * x[c];
                 const unsigned short hi = bf16_rn(val);
@@ -262,7 +289,21 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3ffff) >> 4) | (LBO << 16) | (SBO << 32) | (1ull << 46);
 }
 // kind::f16 instruction descriptor: D=F32 (bit 4), A=B=BF16 (bits 7, 10), K-major both, N>>3 at 17, M>>4 at 24
-constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((TC_BN >> 3) << 17) | ((TC_BM >> 4) << 24);
+constexpr uint32_t TC_IDESC_BF16 = (1u << 4) | (1u << 7) | (1u << 10) | ((TC_BN >> 3) << 17) | ((TC_BM >> 4) << 24);
+constexpr uint32_t TC_IDESC_F16 = (1u << 4) | ((TC_BN >> 3) << 17) | ((TC_BM >> 4) << 24);   // A = B = F16 (format 0)
+
+#ifdef TC_PROFILE
+// Cycle accounting of the scan (build with -DTC_PROFILE; read back with sym_debug_tc_profile):
+//  [0] selection: wait for a finished accumulator   [1] tcgen05.ld + wait   [2] examine (4 chunks)   [3] flush
+//  [4] selection warp-tiles   [5] warp-tiles in which some lane walked a chunk   [6] lane heap updates
+//  [8] issuer: wait reference tile   [9] wait free accumulator   [10] wait turn   [11] issue   [12] issuer tiles
+__device__ unsigned long long tc_prof[16];
+#define TC_CLK(x) const long long x = clock64()
+#define TC_ACC(slot, val) prof_##slot += (val)
+#else
+#define TC_CLK(x)
+#define TC_ACC(slot, val)
+#endif
 
 // ------------------------------------------------------------------------------------------ scan kernel
 // A CTA owns TC_QT query tiles (256 rows) and streams the reference tiles once for both.
@@ -283,40 +324,48 @@ constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((TC_BN >> 3)
 // (A warp-cooperative variant — one row at a time, REDUX for the maximum — was measured 2x slower end to end:
 // its votes and shuffles serialise on the critical path.  Deferring the updates into the wait for the next
 // accumulator was slower too: the selection warps have no such slack once updates are frequent.)
+__host__ __device__ inline int tc_heap_stride(int kc) { return 1 + 4 * ((kc - 1 + 3) / 4); }   // odd, >= kc
+
 __device__ __noinline__ float tc_insert(unsigned long long *heap, int kc, float s, uint32_t id) {
     // entries are (raw float score bits << 32 | position); only the scores are compared (one FSETP per level) —
-    // equal scores may settle in either order, the float64 re-rank orders the survivors by (distance, index)
+    // equal scores may settle in either order, the float64 re-rank orders the survivors by (distance, index).
+    // 4-ary: node i has children 4i+1..4i+4, so kc = 18 is two levels below the root instead of four; the four
+    // child loads of a level are independent.  Slots kc..stride-1 hold -inf sentinels (never the largest child).
     const unsigned long long key = ((unsigned long long)__float_as_uint(s) << 32) | id;
     int i = 0;
+    float root = s;   // score at the root after the update (no read-back of what was just stored)
     while (true) {
-        const int l = 2 * i + 1;
-        if (l >= kc) break;
-        const int r = l + 1;
-        const unsigned long long vl = heap[l];
-        const unsigned long long vr = r < kc ? heap[r] : 0xff800000ull << 32;  // -inf: never the larger child
-        const float fl = __uint_as_float((uint32_t)(vl >> 32)), fr = __uint_as_float((uint32_t)(vr >> 32));
-        const bool right = fr > fl;
-        const float fc = right ? fr : fl;
+        const int c = 4 * i + 1;
+        if (c >= kc) break;
+        const unsigned long long v0 = heap[c], v1 = heap[c + 1], v2 = heap[c + 2], v3 = heap[c + 3];
+        const float f0 = __uint_as_float((uint32_t)(v0 >> 32)), f1 = __uint_as_float((uint32_t)(v1 >> 32));
+        const float f2 = __uint_as_float((uint32_t)(v2 >> 32)), f3 = __uint_as_float((uint32_t)(v3 >> 32));
+        const bool b01 = f1 > f0, b23 = f3 > f2;
+        const float fa = b01 ? f1 : f0, fb = b23 ? f3 : f2;
+        const unsigned long long va = b01 ? v1 : v0, vb = b23 ? v3 : v2;
+        const bool bab = fb > fa;
+        const float fc = bab ? fb : fa;
         if (!(fc > s)) break;
-        heap[i] = right ? vr : vl;
-        i = right ? r : l;
+        heap[i] = bab ? vb : va;
+        if (i == 0) root = fc;
+        i = c + (bab ? 2 + (int)b23 : (int)b01);
     }
     heap[i] = key;
-    return __uint_as_float((uint32_t)(heap[0] >> 32));
+    return root;
 }
 
-// walk one group of 8 scores of a lane that has a hit in it (plain divergent branches: when no lane of the
-// warp hits, the hardware skips the block at the cost of one predicated branch — cheaper than a vote)
+// Lanes whose group of 8 holds a hit: locate the group minimum with compare/select pairs (no data-dependent
+// branch per element: the 8 sequential branches of a plain walk cost more than the heap update), record it,
+// blank it and look again — one round in all but a few cases.
 #define TC_WALK8(G)                                                                                   \
-    if (g##G < thr) {                                                                                 \
-        _Pragma("unroll") for (int j = 0; j < 8; ++j) {                                               \
-            const float sv = __uint_as_float(v[(G) * 8 + j]);                                         \
-            if (sv < thr) {                                                                           \
-                if (pend_id != 0xffffffffu) thr = tc_insert(heap, kc, pend_s, pend_id);               \
-                pend_s = sv;                                                                          \
-                pend_id = ref0 + (uint32_t)((G) * 8 + j);                                             \
-            }                                                                                         \
-        }                                                                                             \
+    while (g##G < thr) {                                                                              \
+        int j = 7;                                                                                    \
+        _Pragma("unroll") for (int e = 6; e >= 0; --e) j = __uint_as_float(v[(G) * 8 + e]) == g##G ? e : j; \
+        if (pend_id != 0xffffffffu) thr = tc_insert(heap, kc, pend_s, pend_id);                       \
+        pend_s = g##G;                                                                                \
+        pend_id = ref0 + (uint32_t)((G) * 8) + (uint32_t)j;                                           \
+        _Pragma("unroll") for (int e = 0; e < 8; ++e) v[(G) * 8 + e] = j == e ? 0x7f800000u : v[(G) * 8 + e]; \
+        g##G = tc_min8(v + (G) * 8);                                                                  \
     }
 
 __device__ __forceinline__ float tc_min8(const uint32_t *v) {
@@ -333,17 +382,35 @@ __device__ __forceinline__ float tc_min8(const uint32_t *v) {
 // arrives or at the periodic flush, where all lanes that have something pending update their rows TOGETHER: in
 // the sparse phase of the scan (about one hit per warp and tile) this turns several serial ~400-cycle heap
 // updates into one.  The threshold of a lane with a pending hit is stale by that one entry (never too small).
-__device__ __forceinline__ float tc_select32(const uint32_t (&v)[32], float thr, uint32_t ref0, unsigned long long *heap,
-                                             int kc, float &pend_s, uint32_t &pend_id) {
-    const float g0 = tc_min8(v), g1 = tc_min8(v + 8), g2 = tc_min8(v + 16), g3 = tc_min8(v + 24);
+struct TcProf {
+    long long walked_cyc = 0, plain_cyc = 0;
+    int walked = 0;
+};
+__device__ __forceinline__ float tc_select32(uint32_t (&v)[32], float thr, uint32_t ref0, unsigned long long *heap,
+                                             int kc, float &pend_s, uint32_t &pend_id, TcProf &pf) {
+#ifdef TC_PROFILE
+    const long long pc0 = clock64();
+#endif
+    float g0 = tc_min8(v), g1 = tc_min8(v + 8), g2 = tc_min8(v + 16), g3 = tc_min8(v + 24);
     const float m = fminf(fmin3(g0, g1, g2), g3);
 #ifndef TC_EXPERIMENT_NO_WALK
+#ifdef TC_PROFILE
+    const bool walked = __any_sync(0xffffffffu, m < thr);
+#endif
     if (m < thr) {
         TC_WALK8(0)
         TC_WALK8(1)
         TC_WALK8(2)
         TC_WALK8(3)
     }
+#ifdef TC_PROFILE
+    __syncwarp();
+    {
+        const long long dt = clock64() - pc0;
+        if (walked) { pf.walked += 1; pf.walked_cyc += dt; }
+        else pf.plain_cyc += dt;
+    }
+#endif
 #else
     if (m < -1e30f) thr = m;
 #endif
@@ -355,11 +422,11 @@ __global__ void __launch_bounds__(128 + 128 * TC_QT * TC_H, 1)
 knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char *__restrict__ rpack, int64_t N,
                    const int32_t *__restrict__ q_perm, const int32_t *__restrict__ q_code,
                    const int32_t *__restrict__ cl_tile, int64_t M, int kp, int kc, int stages, int nbuf,
-                   int tiles_per_split, int ntiles_all, int ss_mode,
+                   int tiles_per_split, int ntiles_all, int ss_mode, uint32_t idesc,
                    unsigned long long *__restrict__ cand_out, float *__restrict__ thr_out) {
     extern __shared__ __align__(1024) unsigned char smraw[];
     const uint32_t tile_bytes = (uint32_t)tc_tile_bytes(kp);
-    const int ks = kc | 1;  // odd row stride: the 32 rows of a warp hit 32 different banks
+    const int ks = tc_heap_stride(kc);  // odd row stride: the 32 rows of a warp hit 32 different banks
     unsigned char *r_s = smraw;                                        // [stages][tile_bytes]
     // TC_H = 1: one selection warp per (query tile, TMEM lane quadrant) examines all 128 columns of a tile;
     // TC_H = 2: two warps share a quadrant, 64 columns each, each with its own heap per row (the re-rank merges
@@ -407,7 +474,8 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
     }
     if (warp >= 4) {  // selection threads initialise their row's heap (all slots empty = the largest key)
         const int list = (warp - 4) >> 2, row = (warp & 3) * 32 + lane;
-        for (int e = 0; e < kc; ++e) heap_s[((size_t)list * TC_BM + row) * ks + e] = (0x7f800000ull << 32) | 0xffffffffull;
+        for (int e = 0; e < ks; ++e)
+            heap_s[((size_t)list * TC_BM + row) * ks + e] = ((e < kc ? 0x7f800000ull : 0xff800000ull) << 32) | 0xffffffffull;
     }
     tc_fence_before();
     __syncthreads();
@@ -465,13 +533,20 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
         const uint64_t r_desc0 = umma_desc(smem_u32(r_s));
         const uint32_t r_step = tile_bytes >> 4;
         const uint32_t a_tmem = tmem_base + (uint32_t)q * a_cols;
+#ifdef TC_PROFILE
+        long long prof_8 = 0, prof_9 = 0, prof_10 = 0, prof_11 = 0;
+#endif
         for (int i = 0; i < ntiles; ++i) {
+            TC_CLK(c0);
             mbar_wait(&r_full[s], ph);
+            TC_CLK(c1);
             mbar_wait(&t_empty[buf], (use & 1) ^ 1);
+            TC_CLK(c2);
             if (ordered) {
                 const uint32_t seq = (uint32_t)(i * TC_QT + q);
                 while (*turn != seq) {}
             }
+            TC_CLK(c3);
             tc_fence_after();
             if (leader) {
 #ifndef TC_EXPERIMENT_NO_MMA
@@ -479,18 +554,27 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
                 const uint32_t d_tmem = tmem_base + acc0 + (uint32_t)(buf * TC_BN);
 #pragma unroll 2
                 for (int k = 0; k < ksteps; ++k)   // one K=16 slice: 8 TMEM columns of A, 4096 B (256 units) of B
-                    if (ss_mode) tc_mma_bf16(d_tmem, q_desc + (uint64_t)(k * 256), r_desc + (uint64_t)(k * 256), TC_IDESC, k > 0);
-                    else tc_mma_bf16_ts(d_tmem, a_tmem + (uint32_t)(k * 8), r_desc + (uint64_t)(k * 256), TC_IDESC, k > 0);
+                    if (ss_mode) tc_mma_bf16(d_tmem, q_desc + (uint64_t)(k * 256), r_desc + (uint64_t)(k * 256), idesc, k > 0);
+                    else tc_mma_bf16_ts(d_tmem, a_tmem + (uint32_t)(k * 8), r_desc + (uint64_t)(k * 256), idesc, k > 0);
 #endif
                 tc_commit(&t_full[buf]);    // this chain's accumulator is complete
                 tc_commit(&r_empty[s]);     // and this issuer is done with the shared-memory stage
                 if (ordered) *turn = (uint32_t)(i * TC_QT + q) + 1u;
             }
             __syncwarp();
+            TC_CLK(c4);
+            TC_ACC(8, c1 - c0); TC_ACC(9, c2 - c1); TC_ACC(10, c3 - c2); TC_ACC(11, c4 - c3);
             if (++s == stages) { s = 0; ph ^= 1; }
             buf += TC_QT;
             while (buf >= nbuf) { buf -= nbuf; ++use; }
         }
+#ifdef TC_PROFILE
+        if (lane == 0) {
+            atomicAdd(&tc_prof[8], (unsigned long long)prof_8); atomicAdd(&tc_prof[9], (unsigned long long)prof_9);
+            atomicAdd(&tc_prof[10], (unsigned long long)prof_10); atomicAdd(&tc_prof[11], (unsigned long long)prof_11);
+            atomicAdd(&tc_prof[12], (unsigned long long)ntiles);
+        }
+#endif
     } else if (warp < 4) {
         // spare warp(s): nothing to do until the final barrier
     } else {
@@ -506,7 +590,12 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
         const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + acc0 + (uint32_t)(half * COLS);
         int buf = qt % nbuf, use = qt / nbuf;   // chain (i, qt) = sequence number i*QT + qt
         int t_cur = t_home;
+#ifdef TC_PROFILE
+        long long prof_0 = 0, prof_1 = 0, prof_2 = 0, prof_3 = 0, prof_5 = 0, prof_6 = 0;
+#endif
+        TcProf pf;
         for (int i = 0; i < ntiles; ++i) {
+            TC_CLK(c0);
 #ifdef TC_SLEEPY_SELECT
             mbar_wait_sleepy(&t_full[buf], use & 1);
 #else
@@ -524,6 +613,12 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
             // pull this warp's share of the accumulator row into registers and hand the TMEM buffer straight
             // back: the next chain can then run while this tile is examined (the buffer is held for one load latency)
             uint32_t v0[32], v1[32];
+            TC_CLK(c1);
+#ifdef TC_PROFILE
+            long long c2 = 0;
+            float thr_before = 0.f;
+            uint32_t pend_before = 0;
+#endif
             tc_ld32(acc, v0);
             tc_ld32(acc + 32, v1);
             if (TC_H == 1) {
@@ -533,22 +628,40 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
                 tc_wait_ld();
                 tc_fence_before();
                 if (lane == 0) mbar_arrive(&t_empty[buf]);
-                thr = tc_select32(v0, thr, ref0, heap, kc, pend_s, pend_id);
-                thr = tc_select32(v1, thr, ref0 + 32, heap, kc, pend_s, pend_id);
-                thr = tc_select32(v2, thr, ref0 + 64, heap, kc, pend_s, pend_id);
-                thr = tc_select32(v3, thr, ref0 + 96, heap, kc, pend_s, pend_id);
+#ifdef TC_PROFILE
+                c2 = clock64();
+                prof_0 += c1 - c0; prof_1 += c2 - c1;
+                thr_before = thr;
+                pend_before = pend_id;
+#endif
+                thr = tc_select32(v0, thr, ref0, heap, kc, pend_s, pend_id, pf);
+                thr = tc_select32(v1, thr, ref0 + 32, heap, kc, pend_s, pend_id, pf);
+                thr = tc_select32(v2, thr, ref0 + 64, heap, kc, pend_s, pend_id, pf);
+                thr = tc_select32(v3, thr, ref0 + 96, heap, kc, pend_s, pend_id, pf);
             } else {
                 tc_wait_ld();
                 tc_fence_before();
                 if (lane == 0) mbar_arrive(&t_empty[buf]);
-                thr = tc_select32(v0, thr, ref0, heap, kc, pend_s, pend_id);
-                thr = tc_select32(v1, thr, ref0 + 32, heap, kc, pend_s, pend_id);
+                thr = tc_select32(v0, thr, ref0, heap, kc, pend_s, pend_id, pf);
+                thr = tc_select32(v1, thr, ref0 + 32, heap, kc, pend_s, pend_id, pf);
             }
+#ifdef TC_PROFILE
+            const long long c3 = clock64();
+            if (TC_H == 1) {
+                prof_2 += c3 - c2;
+                const bool touched = (pend_id != pend_before) || (thr != thr_before);
+                prof_5 += __any_sync(0xffffffffu, touched) ? 1 : 0;
+                prof_6 += __popc(__ballot_sync(0xffffffffu, touched));
+            }
+#endif
             if ((i & (TC_FLUSH - 1)) == TC_FLUSH - 1 && pend_id != 0xffffffffu) {   // periodic flush, lanes in lock-step
                 thr = tc_insert(heap, kc, pend_s, pend_id);
                 pend_id = 0xffffffffu;
             }
             __syncwarp();
+#ifdef TC_PROFILE
+            prof_3 += clock64() - c3;
+#endif
 #endif
             // advance the rotation by TC_QT chains
             buf += TC_QT;
@@ -556,6 +669,16 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
         }
         if (pend_id != 0xffffffffu) thr = tc_insert(heap, kc, pend_s, pend_id);
         __syncwarp();
+#ifdef TC_PROFILE
+        if (lane == 0) {
+            atomicAdd(&tc_prof[0], (unsigned long long)prof_0); atomicAdd(&tc_prof[1], (unsigned long long)prof_1);
+            atomicAdd(&tc_prof[2], (unsigned long long)prof_2); atomicAdd(&tc_prof[3], (unsigned long long)prof_3);
+            atomicAdd(&tc_prof[4], (unsigned long long)ntiles); atomicAdd(&tc_prof[5], (unsigned long long)prof_5);
+            atomicAdd(&tc_prof[6], (unsigned long long)prof_6);
+            atomicAdd(&tc_prof[13], (unsigned long long)pf.walked); atomicAdd(&tc_prof[14], (unsigned long long)pf.walked_cyc);
+            atomicAdd(&tc_prof[15], (unsigned long long)pf.plain_cyc);
+        }
+#endif
         // results: the row's candidates as (score, position) keys (unordered) and its final threshold
         const int64_t n = ((int64_t)blockIdx.x * TC_QT + qt) * TC_BM + row;
         if (n < N) {
@@ -580,7 +703,7 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
 // ------------------------------------------------------------------------------------------ debug
 // One query tile x one reference tile: dumps the 128x128 FP32 accumulator (test-only entry point).
 __global__ void __launch_bounds__(128, 1)
-tc_debug_kernel(const unsigned char *__restrict__ qpack, const unsigned char *__restrict__ rpack, int kp,
+tc_debug_kernel(const unsigned char *__restrict__ qpack, const unsigned char *__restrict__ rpack, int kp, uint32_t idesc,
                 float *__restrict__ out, const unsigned char *__restrict__ qrows) {
     extern __shared__ __align__(1024) unsigned char smraw[];
     const uint32_t tile_bytes = (uint32_t)tc_tile_bytes(kp);
@@ -620,9 +743,9 @@ tc_debug_kernel(const unsigned char *__restrict__ qpack, const unsigned char *__
         tc_fence_after();
         for (int k = 0; k < kp / 16; ++k) {
             if (qrows != nullptr)
-                tc_mma_bf16_ts(tmem_base, tmem_base + 256 + k * 8, umma_desc(smem_u32(r_s) + k * 4096), TC_IDESC, k > 0);
+                tc_mma_bf16_ts(tmem_base, tmem_base + 256 + k * 8, umma_desc(smem_u32(r_s) + k * 4096), idesc, k > 0);
             else
-                tc_mma_bf16(tmem_base, umma_desc(smem_u32(q_s) + k * 4096), umma_desc(smem_u32(r_s) + k * 4096), TC_IDESC,
+                tc_mma_bf16(tmem_base, umma_desc(smem_u32(q_s) + k * 4096), umma_desc(smem_u32(r_s) + k * 4096), idesc,
                             k > 0);
         }
         tc_commit(&done);
@@ -677,7 +800,7 @@ TcPlan tc_plan(int64_t N, int64_t M, int d, int k) {
         const int qt = cfg[c][0], h = cfg[c][1];
         if (force_qt && atoi(force_qt) != qt) continue;
         if (force_h ? atoi(force_h) != h : h != 1) continue;
-        fixed = (size_t)qt * h * (kc | 1) * TC_BM * 8 + 256 /* barriers */ + 1024 /* alignment slack */ +
+        fixed = (size_t)qt * h * tc_heap_stride(kc) * TC_BM * 8 + 256 /* barriers */ + 1024 /* alignment slack */ +
                 (p.ss ? (size_t)qt * tile + 1024 : 0);
         stages = budget > fixed ? (int)((budget - fixed) / tile) : 0;
         if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
@@ -733,7 +856,7 @@ int knn_tc_fit(const float *Ref, int ldr, int64_t M, int d, const int32_t *order
     const int kp = tc_kp(d);
     const int64_t rows_pad = knn_mpad(M);
     dim3 grid((unsigned)ceil_div(rows_pad, 256), (unsigned)(kp / 8));
-    tc_pack_kernel<<<grid, 256, 0, st>>>(Ref, ldr, M, rows_pad, d, kp, 0, order, pk.tc);
+    tc_pack_kernel<<<grid, 256, 0, st>>>(Ref, ldr, M, rows_pad, d, kp, 0, order, pk.tc, tc_prec());
     SYM_LAUNCH_CHECK("tc_pack_kernel(ref)");
     return SYM_OK;
 }
@@ -752,7 +875,8 @@ int knn_tc_scan(const float *Q, int ldq, int64_t N, const int32_t *q_perm, const
     float *thr_w = (float *)w;
     {
         const int64_t rows_pad = p.qtiles * p.qt * TC_BM;
-        tc_pack_rows_kernel<<<(unsigned)ceil_div(rows_pad, 8), 256, 0, st>>>(Q, ldq, N, rows_pad, d, p.kp, q_perm, qpack);
+        tc_pack_rows_kernel<<<(unsigned)ceil_div(rows_pad, 8), 256, 0, st>>>(Q, ldq, N, rows_pad, d, p.kp, q_perm, qpack,
+                                                                                 tc_prec());
         SYM_LAUNCH_CHECK("tc_pack_rows_kernel(query)");
     }
     dim3 grid((unsigned)p.qtiles, (unsigned)p.nsplit);
@@ -762,8 +886,9 @@ int knn_tc_scan(const float *Q, int ldq, int64_t N, const int32_t *q_perm, const
                                       (int)p.smem));                                                                  \
         knn_scan_tc_kernel<QT, H><<<grid, 128 + 128 * QT * H, p.smem, st>>>(qpack, pk.tc, N, q_perm, q_code, cl_tile, \
                                                                           M, p.kp, p.kc, p.stages, p.nbuf,           \
-                                                                          p.tiles_per_split, p.ntiles, p.ss, cand_w, \
-                                                                          thr_w);                                    \
+                                                                          p.tiles_per_split, p.ntiles, p.ss,         \
+                                                                          tc_prec() ? TC_IDESC_F16 : TC_IDESC_BF16,  \
+                                                                          cand_w, thr_w);                            \
     } while (0)
     if (p.qt == 2 && p.halves == 2) SYM_TC_LAUNCH(2, 2);
     else if (p.qt == 2) SYM_TC_LAUNCH(2, 1);
@@ -776,7 +901,9 @@ int knn_tc_scan(const float *Q, int ldq, int64_t N, const int32_t *q_perm, const
     *ncand = p.nsplit * p.halves * p.kc;
     *nsplit = p.nsplit * p.halves;
     // BF16x3: dropped lo.lo / residual terms are <= ~3 * 2^-16 of |q_i r_i| each; FP32 accumulation on top
-    *eps_rel = 6.0e-5;
+    // single FP16: each operand is rounded once (2^-11 relative), so |error| <= 2 * 2^-10 (1 + 2^-11) sum|q_i r_i|
+    // <= 2^-9 ||q|| ||r||; the bound used by the re-rank is eps_rel * (2 ||q|| rmax + rmax^2)
+    *eps_rel = tc_prec() ? 1.0e-3 : 6.0e-5;
     return SYM_OK;
 }
 
@@ -793,19 +920,31 @@ extern "C" int sym_debug_tc_scores(const float *Q, int32_t nq, const float *Ref,
     const int kp = tc_kp(d);
     unsigned char *qp = (unsigned char *)scratch, *rp = qp + tc_tile_bytes(kp);
     dim3 grid(1, (unsigned)(kp / 8));
-    tc_pack_kernel<<<grid, 256, 0, st>>>(Q, d, nq, 128, d, kp, 1, nullptr, qp);
+    tc_pack_kernel<<<grid, 256, 0, st>>>(Q, d, nq, 128, d, kp, 1, nullptr, qp, tc_prec());
     SYM_LAUNCH_CHECK("tc_pack_kernel");
-    tc_pack_kernel<<<grid, 256, 0, st>>>(Ref, d, nr, 128, d, kp, 0, nullptr, rp);
+    tc_pack_kernel<<<grid, 256, 0, st>>>(Ref, d, nr, 128, d, kp, 0, nullptr, rp, tc_prec());
     SYM_LAUNCH_CHECK("tc_pack_kernel");
     unsigned char *qrows = rp + tc_tile_bytes(kp);
     if (a_in_tmem) {
-        tc_pack_rows_kernel<<<16, 256, 0, st>>>(Q, d, nq, 128, d, kp, nullptr, qrows);
+        tc_pack_rows_kernel<<<16, 256, 0, st>>>(Q, d, nq, 128, d, kp, nullptr, qrows, tc_prec());
         SYM_LAUNCH_CHECK("tc_pack_rows_kernel");
     }
     const size_t smem = 2 * tc_tile_bytes(kp) + 1024;
     SYM_CUDA(cudaFuncSetAttribute(tc_debug_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_debug_kernel<<<1, 128, smem, st>>>(qp, rp, kp, out, a_in_tmem ? qrows : nullptr);
+    tc_debug_kernel<<<1, 128, smem, st>>>(qp, rp, kp, tc_prec() ? TC_IDESC_F16 : TC_IDESC_BF16, out,
+                                          a_in_tmem ? qrows : nullptr);
     SYM_LAUNCH_CHECK("tc_debug_kernel");
     return SYM_OK;
 }
 
+
+#ifdef TC_PROFILE
+// Profiling builds only: read and clear the cycle counters of the scan (16 x u64, host memory).
+extern "C" int sym_debug_tc_profile(unsigned long long *out) {
+    SYM_CUDA(cudaDeviceSynchronize());
+    SYM_CUDA(cudaMemcpyFromSymbol(out, sym::tc_prof, sizeof(unsigned long long) * 16));
+    unsigned long long zero[16] = {0};
+    SYM_CUDA(cudaMemcpyToSymbol(sym::tc_prof, zero, sizeof(zero)));
+    return SYM_OK;
+}
+#endif
