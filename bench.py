@@ -46,9 +46,10 @@ WORKLOADS = {
 METRIC = "query cells mapped/sec (map_embedding + kNN transfer)"
 
 
-def kp_of(d: int) -> int:
-    """K extent of the BF16x3 tensor-core operands: 3 split terms of d values + 3 norm pieces, padded to 16."""
-    return (3 * d + 3 + 15) // 16 * 16
+def kp_of(d: int, fp16: bool = False) -> int:
+    """K extent of the tensor-core operands, padded to 16: BF16x3 = 3 split terms of d values + 3 norm pieces;
+    single FP16 = d values + 2 norm pieces."""
+    return (d + 2 + 15) // 16 * 16 if fp16 else (3 * d + 3 + 15) // 16 * 16
 
 
 def knn_mpad(M: int) -> int:
@@ -305,9 +306,15 @@ def main():
     flops = 2.0 * N * M * d  # algorithmic: one d-term dot product per (query, reference) pair
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     ach = flops / (knn_ms / 1000.0) / 1e12
+    # which scan ran as the first tier (engine.knn_search_certified): single-FP16 unless the index fell back
+    tier = args.knn_method if args.knn_method else index.first_tier.get(
+        k, engine.KNN_TC16 if os.environ.get("SYM_KNN_FP16", "1") != "0" else engine.KNN_TC)
+    tier_name = {engine.KNN_FFMA: "knn_scan_ffma_kernel, FP32", engine.KNN_TC: "knn_scan_tc_kernel, BF16x3 tcgen05",
+                 engine.KNN_TC16: "knn_scan_tc_kernel, single-FP16 tcgen05 (uncertified rows re-run with BF16x3)"}[tier]
     roofline = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                "traffic": None, "kernel": "knn_scan_tc_kernel (+ knn_rerank_kernel), BF16x3 tcgen05", "ms_per_launch": knn_ms,
-                "tensor_flops_issued_per_launch": 2.0 * N * knn_mpad(M) * kp_of(d), "rows_repaired_per_step": repaired[0] / args.steps,
+                "traffic": None, "kernel": tier_name + " (+ knn_rerank_kernel)", "ms_per_launch": knn_ms,
+                "tensor_flops_issued_per_launch": 2.0 * N * knn_mpad(M) * kp_of(d, tier == engine.KNN_TC16),
+                "rows_repaired_per_step": repaired[0] / args.steps,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400 (profiling guide)",
                 "fp32_ffma_peak_tflops": 74.4, "frac_of_ffma_peak": ach / 74.4,
                 "algorithmic_flops_per_launch": flops}

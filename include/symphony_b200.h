@@ -142,9 +142,12 @@ int sym_moe_apply(const float *Zin, int32_t ldzin, const float *R, int64_t N, in
  *   Candidates are selected by a float32 (or tensor-core) scan over-selecting k+pad per row and
  *   re-ranked in float64 with sklearn's formula ||x||^2 - 2x.y + ||y||^2 clamped at 0; ties go
  *   to the lower reference index.  k <= 120, d <= 128, k <= M.
- *   method: 0 = auto, 1 = FP32 FFMA scan, 2 = tcgen05 scan (sm_100a tensor cores).
+ *   method: 0 = auto (2 when the shape fits, else 1), 1 = FP32 FFMA scan, 2 = tcgen05 scan with BF16x3 split
+ *   operands (FP32-class scores), 3 = tcgen05 scan with single FP16 operands (a third of the MMAs; its score
+ *   error is bounded per row from the exact rounding residuals, so more rows may fail the certificate).
  *   unsafe [N] uint8 or NULL: rows whose over-selection margin could not be certified
- *   (tensor-core scan only; the caller re-runs those rows with method 1).
+ *   (the caller re-runs those rows with the next more accurate method: 3 -> 2 -> 1).
+ * sym_knn_method_supported: 1 if sym_knn accepts this shape with this method, else 0.
  *   Optional scan order (all three or none): q_perm [N] = query rows sorted by coarse cluster code,
  *   q_code [N] = cluster code of every query row, cl_tile [C] = first 128-row tile of the packed reference
  *   that holds rows of cluster c.  Results do not depend on them.
@@ -159,6 +162,7 @@ int sym_knn_fit(const float *Ref, int32_t ldr, int64_t M, int32_t d, const int32
 int sym_nearest_centroid(const float *X, int32_t ldx, int64_t N, int32_t d, const float *centroids, int32_t C,
                          int32_t *code, sym_stream_t stream);
 size_t sym_knn_workspace(int64_t N, int64_t M, int32_t d, int32_t k, int32_t method);
+int sym_knn_method_supported(int64_t N, int64_t M, int32_t d, int32_t k, int32_t method);
 int sym_knn(const float *Q, int32_t ldq, int64_t N, const float *Ref, int32_t ldr, int64_t M,
             const void *packed, int32_t d, int32_t k, int32_t method, const int32_t *q_perm, const int32_t *q_code,
             const int32_t *cl_tile, int32_t *idx, float *dist2, uint8_t *unsafe, void *workspace,

@@ -293,8 +293,8 @@ __global__ void __launch_bounds__(RR_THREADS)
 knn_rerank_kernel(const float *__restrict__ Q, int ldq, int64_t N, const float *__restrict__ Ref, int ldr, int64_t M,
                   int d, int k, const unsigned long long *__restrict__ cand, const float *__restrict__ thr, int ncand, int nsplit,
                   double eps_rel, const KnnHeader *__restrict__ hdr, const int32_t *__restrict__ order,
-                  const int32_t *__restrict__ q_perm, int32_t *__restrict__ idx_out, float *__restrict__ dist_out,
-                  uint8_t *__restrict__ unsafe) {
+                  const int32_t *__restrict__ q_perm, const float *__restrict__ dq16, int32_t *__restrict__ idx_out,
+                  float *__restrict__ dist_out, uint8_t *__restrict__ unsafe) {
     __shared__ double sd[RR_THREADS / 32][RR_MAXC];
     __shared__ int32_t si[RR_THREADS / 32][RR_MAXC];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -310,7 +310,17 @@ knn_rerank_kernel(const float *__restrict__ Q, int ldq, int64_t N, const float *
     double *wd = sd[warp];
     int32_t *wi = si[warp];
     const double rmax2 = (double)hdr->rmax2;
-    const double eps = eps_rel * (2.0 * sqrt(qn) * sqrt(rmax2) + rmax2);
+    double eps = eps_rel * (2.0 * sqrt(qn) * sqrt(rmax2) + rmax2);
+    double unscale = 1.0;   // scan scores and thresholds are in units of scale16^2 when the operands were single FP16
+    if (dq16 != nullptr) {
+        // single-FP16 scan, in scaled units Q' = 2 s q, R' = s r:  score' = ||R'||^2 - Q'.R',  computed from
+        // fp16(Q') = Q' - dQ, fp16(R') = R' - dR.  |error| <= ||Q'|| ||dR|| + ||dQ|| (||R'|| + ||dR||), with ||dQ|| of
+        // this row measured by the pack kernel and ||dR|| <= header.dr16 (max over the reference).
+        const double s = (double)hdr->scale16, dr = (double)hdr->dr16, dq = (double)dq16[row];
+        const double qs = 2.0 * s * sqrt(qn), rs = s * sqrt(rmax2);
+        unscale = 1.0 / (s * s);
+        eps += (qs * dr + dq * (rs + dr)) * unscale;
+    }
     int bad = 0;  // a recorded scan score further than eps from the exact score voids the certificate
     int nvalid = 0;
     for (int e = lane; e < k; e += 32) {  // slots that no candidate claims (fewer than k valid candidates) stay empty
@@ -333,7 +343,7 @@ knn_rerank_kernel(const float *__restrict__ Q, int ldq, int64_t N, const float *
                 dot = fma((double)q[c], rv, dot);
             }
             const double s_exact = rn - 2.0 * dot;
-            bad |= !(fabs((double)knn_key_score(key) - s_exact) <= eps);
+            bad |= !(fabs((double)knn_key_score(key) * unscale - s_exact) <= eps);
             dist = fmax(qn + s_exact, 0.0);  // sklearn: ||x||^2 - 2 x.y + ||y||^2, clamped at 0
         }
         nvalid += valid;
@@ -369,7 +379,7 @@ knn_rerank_kernel(const float *__restrict__ Q, int ldq, int64_t N, const float *
         if (lane == 0) {
             double tmin = INFINITY;
             for (int s = 0; s < nsplit; ++s) tmin = fmin(tmin, (double)thr[row * nsplit + s]);
-            unsafe[n] = (!bad && kth - qn + 2.0 * eps < tmin) ? 0 : 1;
+            unsafe[n] = (!bad && kth - qn + 2.0 * eps < tmin * unscale) ? 0 : 1;
         }
     }
 }
@@ -546,9 +556,17 @@ extern "C" size_t sym_knn_workspace(int64_t N, int64_t M, int32_t d, int32_t k, 
     ScanPlan p;
     plan_scan(N, M, d, k, p);
     size_t ffma = p.cand_bytes + p.thr_bytes + p.top_bytes + 256;
-    size_t tc = knn_tc_workspace(N, M, d, k);
+    const size_t tc0 = knn_tc_workspace(N, M, d, k, 0), tc1 = knn_tc_workspace(N, M, d, k, 1);
+    const size_t tc = tc0 > tc1 ? tc0 : tc1;
     (void)method;
     return ffma > tc ? ffma : tc;
+}
+
+extern "C" int sym_knn_method_supported(int64_t N, int64_t M, int32_t d, int32_t k, int32_t method) {
+    if (N < 0 || M <= 0 || d <= 0 || k < 1 || k > M || k > 120 || d > 128) return 0;
+    if (method == 0 || method == 1) return 1;
+    if (method == 2 || method == 3) return sym::knn_tc_supported(N > 0 ? N : 1, M, d, k, method == 3 ? 1 : 0) ? 1 : 0;
+    return 0;
 }
 
 extern "C" int sym_knn(const float *Q, int32_t ldq, int64_t N, const float *Ref, int32_t ldr, int64_t M,
@@ -560,23 +578,26 @@ extern "C" int sym_knn(const float *Q, int32_t ldq, int64_t N, const float *Ref,
                 "sym_knn: Expected n_neighbors <= n_samples_fit, but n_neighbors = %d, n_samples_fit = %lld", k,
                 (long long)M);
     SYM_REQUIRE(k <= 120 && d <= 128, SYM_ERR_UNSUPPORTED_SHAPE, "sym_knn: k=%d (<=120) d=%d (<=128) unsupported", k, d);
-    SYM_REQUIRE(method >= 0 && method <= 2, SYM_ERR_INVALID_ARGUMENT, "sym_knn: unknown method %d", method);
+    SYM_REQUIRE(method >= 0 && method <= 3, SYM_ERR_INVALID_ARGUMENT, "sym_knn: unknown method %d", method);
     SYM_REQUIRE(workspace_bytes >= sym_knn_workspace(N, M, d, k, method), SYM_ERR_WORKSPACE_TOO_SMALL,
                 "sym_knn: workspace too small");
     SYM_REQUIRE(((uintptr_t)workspace & 255) == 0, SYM_ERR_INVALID_ARGUMENT, "sym_knn: workspace must be 256-byte aligned");
     if (N == 0) return SYM_OK;
     cudaStream_t st = (cudaStream_t)stream;
     KnnPacked pk = knn_packed_layout(const_cast<void *>(packed), M, d);
-    if (method == 0) method = knn_tc_supported(N, M, d, k) ? 2 : 1;
+    if (method == 0) method = knn_tc_supported(N, M, d, k, 0) ? 2 : 1;
 
     int ncand = 0, nsplit = 1;
     double eps_rel = 0.0;
     const unsigned long long *cand = nullptr;
     const float *thr = nullptr;
-    if (method == 2) {
-        SYM_REQUIRE(knn_tc_supported(N, M, d, k), SYM_ERR_UNSUPPORTED_SHAPE, "sym_knn: tcgen05 scan does not support this shape");
-        int rc = knn_tc_scan(Q, ldq, N, q_perm, q_code, cl_tile, pk, M, d, k, workspace, workspace_bytes, st, &cand, &thr,
-                             &ncand, &nsplit, &eps_rel);
+    const float *dq16 = nullptr;
+    if (method >= 2) {
+        const int prec = method == 3 ? 1 : 0;
+        SYM_REQUIRE(knn_tc_supported(N, M, d, k, prec), SYM_ERR_UNSUPPORTED_SHAPE,
+                    "sym_knn: tcgen05 scan does not support this shape");
+        int rc = knn_tc_scan(Q, ldq, N, q_perm, q_code, cl_tile, pk, M, d, k, prec, workspace, workspace_bytes, st, &cand,
+                             &thr, &ncand, &nsplit, &eps_rel, &dq16);
         if (rc != SYM_OK) return rc;
     } else {
         ScanPlan p;
@@ -597,7 +618,8 @@ extern "C" int sym_knn(const float *Q, int32_t ldq, int64_t N, const float *Ref,
     }
     SYM_REQUIRE(ncand <= RR_MAXC, SYM_ERR_UNSUPPORTED_SHAPE, "sym_knn: internal: %d candidates per row", ncand);
     knn_rerank_kernel<<<(unsigned)ceil_div(N, RR_THREADS / 32), RR_THREADS, 0, st>>>(
-        Q, ldq, N, Ref, ldr, M, d, k, cand, thr, ncand, nsplit, eps_rel, pk.hdr, pk.order, q_perm, idx, dist2, unsafe);
+        Q, ldq, N, Ref, ldr, M, d, k, cand, thr, ncand, nsplit, eps_rel, pk.hdr, pk.order, q_perm, dq16, idx, dist2,
+        unsafe);
     SYM_LAUNCH_CHECK("knn_rerank_kernel");
     return SYM_OK;
 }

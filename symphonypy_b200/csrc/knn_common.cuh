@@ -7,16 +7,22 @@ namespace sym {
 struct KnnHeader {
     float rmax2;       // max ||ref||^2 (written by fit with an integer atomicMax: values are >= 0)
     int32_t has_order;  // 1 when the reference was packed in a caller-given (locality) order
-    int32_t pad[62];
+    // single-FP16 operand section (method 3): rows are scaled by the power of two `scale16` (largest norm in
+    // (8, 16], far from FP16 overflow and underflow); dr16 = max over rows of ||s r - fp16(s r)||, the exact
+    // rounding residual the re-rank's error bound is built from
+    float scale16;
+    float dr16;
+    int32_t pad[60];
 };
 
 // Layout of the opaque "packed reference" buffer produced by sym_knn_fit:
-//   [KnnHeader | norm2 f32[Mpad] | refT f32[d4][Mpad] | tensor-core section | order i32[Mpad]]
+//   [KnnHeader | norm2 f32[Mpad] | refT f32[d4][Mpad] | BF16x3 tiles | FP16 tiles | order i32[Mpad]]
 struct KnnPacked {
     KnnHeader *hdr;
     float *norm2;
     float *refT;
-    unsigned char *tc;  // tensor-core operand section (layout private to knn_tc.cu)
+    unsigned char *tc;    // tensor-core operand section, BF16x3 (layout private to knn_tc.cu)
+    unsigned char *tc16;  // tensor-core operand section, single FP16
     int32_t *order;     // [Mpad] packed position -> original reference row (identity when no order was given)
     int64_t Mpad;
     int d4;
@@ -25,7 +31,7 @@ struct KnnPacked {
 
 __host__ __device__ inline int64_t knn_mpad(int64_t M) { return (M + 255) / 256 * 256; }
 
-size_t knn_tc_packed_bytes(int64_t M, int d);
+size_t knn_tc_packed_bytes(int64_t M, int d, int prec);   // prec 0 = BF16x3, 1 = single FP16
 
 inline KnnPacked knn_packed_layout(void *base, int64_t M, int d) {
     KnnPacked p;
@@ -41,7 +47,10 @@ inline KnnPacked knn_packed_layout(void *base, int64_t M, int d) {
     off += (size_t)p.d4 * p.Mpad * sizeof(float);
     off = (off + 1023) & ~(size_t)1023;
     p.tc = b + off;
-    off += knn_tc_packed_bytes(M, d);
+    off += knn_tc_packed_bytes(M, d, 0);
+    off = (off + 1023) & ~(size_t)1023;
+    p.tc16 = b + off;
+    off += knn_tc_packed_bytes(M, d, 1);
     off = (off + 255) & ~(size_t)255;
     p.order = (int32_t *)(b + off);
     off += (size_t)p.Mpad * sizeof(int32_t);
@@ -70,12 +79,14 @@ __device__ __forceinline__ float knn_key_score(unsigned long long key) {
 }
 
 // tcgen05 scan entry points (knn_tc.cu)
-bool knn_tc_supported(int64_t N, int64_t M, int d, int k);
-size_t knn_tc_workspace(int64_t N, int64_t M, int d, int k);
+// `prec`: 0 = BF16x3 split operands (FP32-class scores), 1 = single FP16 operands (three times fewer MMAs;
+// the scan reports the exact rounding residual of every query row in *dq16 for the re-rank's error bound)
+bool knn_tc_supported(int64_t N, int64_t M, int d, int k, int prec);
+size_t knn_tc_workspace(int64_t N, int64_t M, int d, int k, int prec);
 int knn_tc_fit(const float *Ref, int ldr, int64_t M, int d, const int32_t *order, KnnPacked pk, cudaStream_t st);
 int knn_tc_scan(const float *Q, int ldq, int64_t N, const int32_t *q_perm, const int32_t *q_code,
-                const int32_t *cl_tile, KnnPacked pk, int64_t M, int d, int k, void *workspace,
+                const int32_t *cl_tile, KnnPacked pk, int64_t M, int d, int k, int prec, void *workspace,
                 size_t workspace_bytes, cudaStream_t st, const unsigned long long **cand, const float **thr, int *ncand,
-                int *nsplit, double *eps_rel);
+                int *nsplit, double *eps_rel, const float **dq16);
 
 }  // namespace sym

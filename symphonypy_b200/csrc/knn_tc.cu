@@ -40,12 +40,7 @@ constexpr int TC_PAD = 8;         // over-selection: kc = k + TC_PAD
 #endif
 
 // operand precision: 0 = BF16x3 (three split products, K' = 3d+3), 1 = single FP16 (K' = d+2)
-inline int tc_prec() {
-    static int prec = -1;
-    if (prec < 0) prec = getenv("SYM_TC_FP16") && atoi(getenv("SYM_TC_FP16")) ? 1 : 0;
-    return prec;
-}
-inline int tc_kp(int d) { return tc_prec() ? (d + 2 + 15) / 16 * 16 : (3 * d + 3 + 15) / 16 * 16; }
+__host__ __device__ inline int tc_kp(int d, int prec) { return prec ? (d + 2 + 15) / 16 * 16 : (3 * d + 3 + 15) / 16 * 16; }
 __host__ __device__ inline size_t tc_tile_bytes(int kp) { return (size_t)kp * 256; }  // 128 rows x kp bf16
 
 // ------------------------------------------------------------------------------------------ packing
@@ -63,7 +58,8 @@ __device__ __forceinline__ float f16_to_f(unsigned short h) { return __half2floa
 // Element (r, kk) of a tile lives at  (kk/8)*2048 + (r/8)*128 + (r%8)*16 + (kk%8)*2  bytes.
 __global__ void __launch_bounds__(256)
 tc_pack_kernel(const float *__restrict__ src, int ld, int64_t rows, int64_t rows_pad, int d, int kp, int is_query,
-               const int32_t *__restrict__ gather, unsigned char *__restrict__ dst, int prec) {
+               const int32_t *__restrict__ gather, unsigned char *__restrict__ dst, int prec,
+               KnnHeader *__restrict__ hdr) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;  // k-unit
     if (r >= rows_pad) return;
@@ -73,8 +69,18 @@ tc_pack_kernel(const float *__restrict__ src, int ld, int64_t rows, int64_t rows
     float nrm = 0.f;
     const int k0 = j * 8;
     const int nk = prec ? d : 3 * d;   // first K' index of the ||r||^2 pieces
+    const float sc = (prec && hdr) ? hdr->scale16 : 1.f;   // single FP16: rows scaled by a power of two
     if (real && !is_query && k0 + 8 > nk && k0 < nk + 3) {
         for (int c = 0; c < d; ++c) nrm = fmaf(x[c], x[c], nrm);
+        nrm *= sc * sc;
+    }
+    if (prec && hdr && real && !is_query && j == 0) {   // exact rounding residual of this row, max over rows -> header
+        float res = 0.f;
+        for (int c = 0; c < d; ++c) {
+            const float v = x[c] * sc, dl = v - f16_to_f(f16_rn(v));
+            res = fmaf(dl, dl, res);
+        }
+        atomicMax(reinterpret_cast<int *>(&hdr->dr16), __float_as_int(sqrtf(res) * 1.0000002f));
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -82,7 +88,7 @@ tc_pack_kernel(const float *__restrict__ src, int ld, int64_t rows, int64_t rows
         unsigned short v = 0;
         if (prec) {   // single FP16: [x (d) | two fp16 pieces of ||r||^2  /  1 1]
             if (kk < d) {
-                if (real) v = f16_rn(is_query ? -2.f * x[kk] : x[kk]);
+                if (real) v = f16_rn((is_query ? -2.f * x[kk] : x[kk]) * sc);
             } else if (kk < d + 2) {
                 const int p = kk - d;
                 if (is_query) {
@@ -133,11 +139,14 @@ tc_pack_kernel(const float *__restrict__ src, int ld, int64_t rows, int64_t rows
 // loads its own row).  One thread = one row x one k-unit, as above.
 __global__ void __launch_bounds__(256)
 tc_pack_rows_kernel(const float *__restrict__ src, int ld, int64_t rows, int64_t rows_pad, int d, int kp,
-                    const int32_t *__restrict__ gather, unsigned char *__restrict__ dst, int prec) {
+                    const int32_t *__restrict__ gather, unsigned char *__restrict__ dst, int prec,
+                    const KnnHeader *__restrict__ hdr, float *__restrict__ dq16) {
     const int64_t r = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;  // a warp walks the k-units of a row
     if (r >= rows_pad) return;
     const bool real = r < rows;
     const float *x = src + ((real && gather) ? (int64_t)gather[r] : (real ? r : 0)) * ld;
+    const float sc = (prec && hdr) ? hdr->scale16 : 1.f;
+    float res = 0.f;   // single FP16: squared rounding residual of this row's operand, summed over the lanes
     for (int j = threadIdx.x % 32; j < kp / 8; j += 32) {
         unsigned short out[8];
 #pragma unroll
@@ -145,8 +154,14 @@ tc_pack_rows_kernel(const float *__restrict__ src, int ld, int64_t rows, int64_t
             const int kk = j * 8 + e;
             unsigned short v = 0;
             if (prec) {
-                if (real && kk < d) v = f16_rn(-2.f * x[kk]);
-                else if (real && kk < d + 2) v = 0x3c00;
+                if (real && kk < d) {
+                    const float val = -2.f * x[kk] * sc;
+                    v = f16_rn(val);
+                    const float dl = val - f16_to_f(v);   // inf / NaN on overflow: the row then fails its certificate
+                    res = fmaf(dl, dl, res);
+                } else if (real && kk < d + 2) {
+                    v = 0x3c00;
+                }
             } else if (real && kk < 3 * d) {
                 const int seg = kk / d, c = kk - seg * d;
                 const float val = -2.f * x[c];
@@ -164,6 +179,24 @@ tc_pack_rows_kernel(const float *__restrict__ src, int ld, int64_t rows, int64_t
         w.w = out[6] | ((unsigned)out[7] << 16);
         *reinterpret_cast<uint4 *>(dst + (size_t)r * kp * 2 + (size_t)j * 16) = w;
     }
+    if (dq16 != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) res += __shfl_xor_sync(0xffffffffu, res, o);
+        if ((threadIdx.x & 31) == 0) dq16[r] = sqrtf(res) * 1.0000002f;
+    }
+}
+
+// scale16 = the power of two that brings the largest reference norm into (8, 16]
+__global__ void tc_scale_kernel(KnnHeader *hdr) {
+    const float rmax = sqrtf(hdr->rmax2);
+    float s = 1.f;
+    if (rmax > 0.f && isfinite(rmax)) {
+        int e;
+        frexpf(rmax, &e);            // rmax = m * 2^e, m in [0.5, 1)
+        s = ldexpf(1.f, 4 - e);      // rmax * s = m * 16 in [8, 16)
+    }
+    hdr->scale16 = s;
+    hdr->dr16 = 0.f;
 }
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
@@ -774,13 +807,13 @@ namespace {
 struct TcPlan {
     int kp, kc, qt, halves, stages, nbuf, nsplit, tiles_per_split, ntiles, ss;
     int64_t qtiles;
-    size_t smem, qpack_bytes, cand_bytes, thr_bytes;
+    size_t smem, qpack_bytes, cand_bytes, thr_bytes, dq_bytes;
     bool ok;
 };
 
-TcPlan tc_plan(int64_t N, int64_t M, int d, int k) {
+TcPlan tc_plan(int64_t N, int64_t M, int d, int k, int prec) {
     TcPlan p{};
-    p.kp = tc_kp(d);
+    p.kp = tc_kp(d, prec);
     const char *force_pad = getenv("SYM_TC_PAD");   // tuning / experiments only
     int kc = k + (force_pad ? atoi(force_pad) : TC_PAD);
     if (kc > M) kc = (int)M;
@@ -828,55 +861,61 @@ TcPlan tc_plan(int64_t N, int64_t M, int d, int k) {
     }
     p.tiles_per_split = (int)ceil_div(p.ntiles, nsplit);
     p.nsplit = (int)ceil_div(p.ntiles, p.tiles_per_split);
-    p.qpack_bytes = (size_t)p.qtiles * p.qt * TC_BM * p.kp * 2;  // row-major BF16x3 query rows
+    p.qpack_bytes = (size_t)p.qtiles * p.qt * TC_BM * p.kp * 2;  // row-major query operand rows
+    p.dq_bytes = prec ? (((size_t)p.qtiles * p.qt * TC_BM * sizeof(float) + 255) & ~(size_t)255) : 0;
     p.cand_bytes = ((size_t)N * p.nsplit * p.halves * kc * 8 + 255) & ~(size_t)255;
     p.thr_bytes = ((size_t)N * p.nsplit * p.halves * 4 + 255) & ~(size_t)255;
     return p;
 }
 }  // namespace
 
-size_t knn_tc_packed_bytes(int64_t M, int d) {
+size_t knn_tc_packed_bytes(int64_t M, int d, int prec) {
     if (d > 84) return 0;
-    return (size_t)(knn_mpad(M) / TC_BN) * tc_tile_bytes(tc_kp(d));
+    return (size_t)(knn_mpad(M) / TC_BN) * tc_tile_bytes(tc_kp(d, prec));
 }
 
-bool knn_tc_supported(int64_t N, int64_t M, int d, int k) {
+bool knn_tc_supported(int64_t N, int64_t M, int d, int k, int prec) {
     if (d > 84 || k > 120) return false;
-    return tc_plan(N, M, d, k).ok;
+    return tc_plan(N, M, d, k, prec).ok;
 }
 
-size_t knn_tc_workspace(int64_t N, int64_t M, int d, int k) {
-    if (!knn_tc_supported(N, M, d, k)) return 0;
-    TcPlan p = tc_plan(N, M, d, k);
-    return p.qpack_bytes + p.cand_bytes + p.thr_bytes + 1024;
+size_t knn_tc_workspace(int64_t N, int64_t M, int d, int k, int prec) {
+    if (!knn_tc_supported(N, M, d, k, prec)) return 0;
+    TcPlan p = tc_plan(N, M, d, k, prec);
+    return ((p.qpack_bytes + 255) & ~(size_t)255) + p.cand_bytes + p.thr_bytes + p.dq_bytes + 1024;
 }
 
 int knn_tc_fit(const float *Ref, int ldr, int64_t M, int d, const int32_t *order, KnnPacked pk, cudaStream_t st) {
     if (d > 84) return SYM_OK;
-    const int kp = tc_kp(d);
     const int64_t rows_pad = knn_mpad(M);
-    dim3 grid((unsigned)ceil_div(rows_pad, 256), (unsigned)(kp / 8));
-    tc_pack_kernel<<<grid, 256, 0, st>>>(Ref, ldr, M, rows_pad, d, kp, 0, order, pk.tc, tc_prec());
-    SYM_LAUNCH_CHECK("tc_pack_kernel(ref)");
+    tc_scale_kernel<<<1, 1, 0, st>>>(pk.hdr);   // after knn_fit_kernel (same stream): needs header.rmax2
+    SYM_LAUNCH_CHECK("tc_scale_kernel");
+    for (int prec = 0; prec < 2; ++prec) {
+        const int kp = tc_kp(d, prec);
+        dim3 grid((unsigned)ceil_div(rows_pad, 256), (unsigned)(kp / 8));
+        tc_pack_kernel<<<grid, 256, 0, st>>>(Ref, ldr, M, rows_pad, d, kp, 0, order, prec ? pk.tc16 : pk.tc, prec, pk.hdr);
+        SYM_LAUNCH_CHECK("tc_pack_kernel(ref)");
+    }
     return SYM_OK;
 }
 
 int knn_tc_scan(const float *Q, int ldq, int64_t N, const int32_t *q_perm, const int32_t *q_code,
-                const int32_t *cl_tile, KnnPacked pk, int64_t M, int d, int k, void *workspace,
+                const int32_t *cl_tile, KnnPacked pk, int64_t M, int d, int k, int prec, void *workspace,
                 size_t workspace_bytes, cudaStream_t st, const unsigned long long **cand, const float **thr,
-                int *ncand, int *nsplit, double *eps_rel) {
-    TcPlan p = tc_plan(N, M, d, k);
+                int *ncand, int *nsplit, double *eps_rel, const float **dq16) {
+    TcPlan p = tc_plan(N, M, d, k, prec);
     SYM_REQUIRE(p.ok, SYM_ERR_UNSUPPORTED_SHAPE, "tcgen05 scan: d=%d k=%d does not fit", d, k);
-    SYM_REQUIRE(workspace_bytes >= p.qpack_bytes + p.cand_bytes + p.thr_bytes, SYM_ERR_WORKSPACE_TOO_SMALL,
+    SYM_REQUIRE(workspace_bytes >= knn_tc_workspace(N, M, d, k, prec) - 1024, SYM_ERR_WORKSPACE_TOO_SMALL,
                 "tcgen05 scan: workspace too small");
     unsigned char *w = (unsigned char *)workspace;
     unsigned char *qpack = w; w += (p.qpack_bytes + 255) & ~(size_t)255;
     unsigned long long *cand_w = (unsigned long long *)w; w += p.cand_bytes;
-    float *thr_w = (float *)w;
+    float *thr_w = (float *)w; w += p.thr_bytes;
+    float *dq_w = prec ? (float *)w : nullptr;
     {
         const int64_t rows_pad = p.qtiles * p.qt * TC_BM;
         tc_pack_rows_kernel<<<(unsigned)ceil_div(rows_pad, 8), 256, 0, st>>>(Q, ldq, N, rows_pad, d, p.kp, q_perm, qpack,
-                                                                                 tc_prec());
+                                                                                 prec, pk.hdr, dq_w);
         SYM_LAUNCH_CHECK("tc_pack_rows_kernel(query)");
     }
     dim3 grid((unsigned)p.qtiles, (unsigned)p.nsplit);
@@ -884,10 +923,11 @@ int knn_tc_scan(const float *Q, int ldq, int64_t N, const int32_t *q_perm, const
     do {                                                                                                              \
         SYM_CUDA(cudaFuncSetAttribute(knn_scan_tc_kernel<QT, H>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
                                       (int)p.smem));                                                                  \
-        knn_scan_tc_kernel<QT, H><<<grid, 128 + 128 * QT * H, p.smem, st>>>(qpack, pk.tc, N, q_perm, q_code, cl_tile, \
+        knn_scan_tc_kernel<QT, H><<<grid, 128 + 128 * QT * H, p.smem, st>>>(qpack, prec ? pk.tc16 : pk.tc, N, q_perm,      \
+                                                                          q_code, cl_tile,                           \
                                                                           M, p.kp, p.kc, p.stages, p.nbuf,           \
                                                                           p.tiles_per_split, p.ntiles, p.ss,         \
-                                                                          tc_prec() ? TC_IDESC_F16 : TC_IDESC_BF16,  \
+                                                                          prec ? TC_IDESC_F16 : TC_IDESC_BF16,       \
                                                                           cand_w, thr_w);                            \
     } while (0)
     if (p.qt == 2 && p.halves == 2) SYM_TC_LAUNCH(2, 2);
@@ -901,9 +941,10 @@ int knn_tc_scan(const float *Q, int ldq, int64_t N, const int32_t *q_perm, const
     *ncand = p.nsplit * p.halves * p.kc;
     *nsplit = p.nsplit * p.halves;
     // BF16x3: dropped lo.lo / residual terms are <= ~3 * 2^-16 of |q_i r_i| each; FP32 accumulation on top
-    // single FP16: each operand is rounded once (2^-11 relative), so |error| <= 2 * 2^-10 (1 + 2^-11) sum|q_i r_i|
-    // <= 2^-9 ||q|| ||r||; the bound used by the re-rank is eps_rel * (2 ||q|| rmax + rmax^2)
-    *eps_rel = tc_prec() ? 1.0e-3 : 6.0e-5;
+    // single FP16: the operand rounding is bounded by the re-rank from the exact residuals (dq16, header.dr16);
+    // eps_rel then only covers the FP32 accumulation of the kp products and the two-piece ||r||^2
+    *eps_rel = prec ? 1.0e-5 : 6.0e-5;
+    *dq16 = dq_w;
     return SYM_OK;
 }
 
@@ -912,26 +953,27 @@ int knn_tc_scan(const float *Q, int ldq, int64_t N, const int32_t *q_perm, const
 // Test-only: scores of the first query tile against the first reference tile, through the same packing,
 // descriptors and MMA chain as the scan.  Q [<=128, d], Ref [<=128, d] -> out [128,128]; scratch >= 3 tiles.
 extern "C" int sym_debug_tc_scores(const float *Q, int32_t nq, const float *Ref, int32_t nr, int32_t d, float *out,
-                                   void *scratch, sym_stream_t stream, int32_t a_in_tmem) {
+                                   void *scratch, sym_stream_t stream, int32_t flags) {
+    const int a_in_tmem = flags & 1, prec = (flags >> 1) & 1;   // bit 0: query operand in tensor memory; bit 1: single FP16
     using namespace sym;
     SYM_REQUIRE(nq > 0 && nq <= 128 && nr > 0 && nr <= 128 && d > 0 && d <= 84, SYM_ERR_INVALID_ARGUMENT,
                 "sym_debug_tc_scores: bad sizes");
     cudaStream_t st = (cudaStream_t)stream;
-    const int kp = tc_kp(d);
+    const int kp = tc_kp(d, prec);
     unsigned char *qp = (unsigned char *)scratch, *rp = qp + tc_tile_bytes(kp);
     dim3 grid(1, (unsigned)(kp / 8));
-    tc_pack_kernel<<<grid, 256, 0, st>>>(Q, d, nq, 128, d, kp, 1, nullptr, qp, tc_prec());
+    tc_pack_kernel<<<grid, 256, 0, st>>>(Q, d, nq, 128, d, kp, 1, nullptr, qp, prec, nullptr);
     SYM_LAUNCH_CHECK("tc_pack_kernel");
-    tc_pack_kernel<<<grid, 256, 0, st>>>(Ref, d, nr, 128, d, kp, 0, nullptr, rp, tc_prec());
+    tc_pack_kernel<<<grid, 256, 0, st>>>(Ref, d, nr, 128, d, kp, 0, nullptr, rp, prec, nullptr);
     SYM_LAUNCH_CHECK("tc_pack_kernel");
     unsigned char *qrows = rp + tc_tile_bytes(kp);
     if (a_in_tmem) {
-        tc_pack_rows_kernel<<<16, 256, 0, st>>>(Q, d, nq, 128, d, kp, nullptr, qrows, tc_prec());
+        tc_pack_rows_kernel<<<16, 256, 0, st>>>(Q, d, nq, 128, d, kp, nullptr, qrows, prec, nullptr, nullptr);
         SYM_LAUNCH_CHECK("tc_pack_rows_kernel");
     }
     const size_t smem = 2 * tc_tile_bytes(kp) + 1024;
     SYM_CUDA(cudaFuncSetAttribute(tc_debug_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_debug_kernel<<<1, 128, smem, st>>>(qp, rp, kp, tc_prec() ? TC_IDESC_F16 : TC_IDESC_BF16, out,
+    tc_debug_kernel<<<1, 128, smem, st>>>(qp, rp, kp, prec ? TC_IDESC_F16 : TC_IDESC_BF16, out,
                                           a_in_tmem ? qrows : nullptr);
     SYM_LAUNCH_CHECK("tc_debug_kernel");
     return SYM_OK;

@@ -16,7 +16,8 @@ import torch
 from . import _lib
 
 CLIP = 10.0  # `symphonypy/_utils.py:253`: max_value, fixed by the reference API
-KNN_AUTO, KNN_FFMA, KNN_TCGEN05 = 0, 1, 2
+KNN_AUTO, KNN_FFMA, KNN_TCGEN05, KNN_TC16 = 0, 1, 2, 3
+KNN_TC = KNN_TCGEN05
 
 
 def _ptr(t):
@@ -216,6 +217,7 @@ class KnnIndex:
     centroids: torch.Tensor | None = None   # [C, d] f32, in chain order
     cl_tile: torch.Tensor | None = None     # [C] i32: first 128-row tile of the packed reference with rows of cluster c
     workspace: dict = field(default_factory=dict)
+    first_tier: dict = field(default_factory=dict)   # k -> scan method to start with (see knn_search_certified)
 
 
 LOCALITY_MIN_REF = 32768     # below this the whole reference is a few hundred tiles: no ordering
@@ -317,18 +319,45 @@ def knn_search(index: KnnIndex, Q: torch.Tensor, k: int, method: int = KNN_AUTO,
 
 
 def knn_search_certified(index: KnnIndex, Q: torch.Tensor, k: int, method: int = KNN_AUTO, events: list | None = None):
-    """`knn_search` plus the repair pass: rows whose over-selection margin could not be certified
-    (possible with the reduced-precision tensor-core scan, or with many exactly tied neighbours) are
-    re-run with the FP32 FFMA scan.  Returns (idx, dist2, n_repaired)."""
-    idx, dist2, unsafe = knn_search(index, Q, k, method, events=events)
-    n_bad = int(unsafe.sum().item())
+    """`knn_search` plus the repair passes.  Rows whose over-selection margin could not be certified (possible
+    with the reduced-precision tensor-core scans, or with many exactly tied neighbours) are re-run with the next
+    more accurate scan: single-FP16 tcgen05 -> BF16x3 tcgen05 -> FP32 FFMA.
+
+    With `method=KNN_AUTO` the first tier is the single-FP16 scan (a third of the MMAs) unless this index has
+    shown, for this k, that more than 8 % of the rows then need the BF16x3 scan anyway (dense neighbourhoods:
+    gaps between the k-th and (k+8)-th neighbour below the FP16 score error) — the index remembers and starts
+    with BF16x3 from then on.  Results do not depend on the tier.  Returns (idx, dist2, rows re-run)."""
+    lib = _lib.load()
+    N = Q.shape[0]
+
+    def supported(m: int, n: int) -> bool:
+        return bool(lib.sym_knn_method_supported(n, index.M, index.d, k, m))
+
+    adaptive = method == KNN_AUTO
+    if adaptive:
+        first = index.first_tier.get(k)
+        if first is None:
+            fp16_on = os.environ.get("SYM_KNN_FP16", "1") != "0"   # (switch for timing experiments)
+            first = KNN_TC16 if fp16_on and supported(KNN_TC16, N) else (KNN_TC if supported(KNN_TC, N) else KNN_FFMA)
+    else:
+        first = method
+    idx, dist2, unsafe = knn_search(index, Q, k, first, events=events)
+    n_first = n_bad = int(unsafe.sum().item())
     if n_bad and os.environ.get("SYM_KNN_NO_REPAIR") != "1":  # (the switch exists for kernel timing experiments only)
         rows = torch.nonzero(unsafe, as_tuple=False).flatten()
-        i2, d2, _ = knn_search(index, Q[rows].contiguous(), k, KNN_FFMA)
-        idx[rows] = i2
-        dist2[rows] = d2
-    return idx, dist2, n_bad
-
+        tier = first
+        while n_bad and tier != KNN_FFMA:
+            tier = KNN_TC if tier == KNN_TC16 and supported(KNN_TC, n_bad) else KNN_FFMA
+            i2, d2, u2 = knn_search(index, Q[rows].contiguous(), k, tier)
+            idx[rows] = i2
+            dist2[rows] = d2
+            if tier == KNN_FFMA:
+                break
+            rows = rows[torch.nonzero(u2, as_tuple=False).flatten()]
+            n_bad = int(rows.numel())
+    if adaptive and first == KNN_TC16 and N >= 4096 and n_first > 0.08 * N:
+        index.first_tier[k] = KNN_TC if supported(KNN_TC, N) else KNN_FFMA
+    return idx, dist2, n_first
 
 def vote(idx: torch.Tensor, ref_codes: torch.Tensor, want_conf: bool = True, dist2: torch.Tensor | None = None):
     """Majority vote with sklearn's tie rule (lowest class code); conf = winning fraction.

@@ -402,6 +402,74 @@ def test_knn_tcgen05_matches_sklearn(cuda_device, N, M, d, k):
     _check_knn(idx2.cpu().numpy(), dist22.cpu().numpy(), ref, q, k)
 
 
+def test_tc_score_tile_fp16(cuda_device, built_library):
+    """The single-FP16 score tile: error within the bound the re-rank uses, built from the exact rounding
+    residuals  ||Q'|| ||dR|| + ||dQ|| (||R'|| + ||dR||)  (+ accumulation), Q' = -2q."""
+    import ctypes
+
+    lib = ctypes.CDLL(built_library)
+    rng = np.random.default_rng(1)
+    for d, a_in_tmem in [(20, 1), (30, 0), (30, 1), (50, 1), (7, 1)]:
+        q = (rng.normal(size=(100, d)) * 0.7).astype(np.float32)
+        r = (rng.normal(size=(128, d)) * 0.7).astype(np.float32)
+        Q, R = torch.from_numpy(q).to(cuda_device), torch.from_numpy(r).to(cuda_device)
+        out = torch.zeros((128, 128), device=cuda_device)
+        scratch = torch.zeros(3 * 256 * 256 + 1024, dtype=torch.uint8, device=cuda_device)
+        rc = lib.sym_debug_tc_scores(ctypes.c_void_p(Q.data_ptr()), 100, ctypes.c_void_p(R.data_ptr()), 128, d,
+                                     ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(scratch.data_ptr()), None,
+                                     a_in_tmem | 2)
+        assert rc == 0
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()[:100]
+        q64, r64 = q.astype(np.float64), r.astype(np.float64)
+        want = (r64 ** 2).sum(1)[None, :] - 2.0 * q64 @ r64.T
+        Qp = -2.0 * q64
+        dQ = np.linalg.norm(Qp - Qp.astype(np.float16).astype(np.float64), axis=1)
+        dR = np.linalg.norm(r64 - r64.astype(np.float16).astype(np.float64), axis=1)
+        nQ, nR = np.linalg.norm(Qp, axis=1), np.linalg.norm(r64, axis=1)
+        bound = nQ[:, None] * dR[None, :] + dQ[:, None] * (nR + dR)[None, :] + 1e-5 * (nQ[:, None] * nR[None, :] + nR[None, :] ** 2)
+        err = np.abs(got - want)
+        assert (err <= bound).all(), (d, float((err / bound).max()))
+        assert err.max() > 1e-6          # it IS the reduced-precision path
+        assert (out.cpu().numpy()[100:] == 0).all()
+
+
+@pytest.mark.parametrize("N,M,d,k,scale", [(3000, 10000, 20, 10, 1.0), (500, 70000, 50, 30, 1.0), (20000, 50000, 30, 10, 1.0),
+                                           (4000, 30000, 30, 10, 3000.0), (4000, 30000, 30, 10, 1e-4)])
+def test_knn_fp16_tier_matches_sklearn(cuda_device, N, M, d, k, scale):
+    """Method 3 (single-FP16 operands): certified rows equal sklearn's brute force, whatever the scale of the
+    data (operands are rescaled by a power of two); the tiered wrapper repairs the rest."""
+    rng = np.random.default_rng(M + k)
+    centres = rng.normal(size=(8, d)) * 4
+    ref = ((centres[rng.integers(0, 8, M)] + rng.normal(size=(M, d))) * scale).astype(np.float32)
+    q = ((centres[rng.integers(0, 8, N)] + rng.normal(size=(N, d))) * scale).astype(np.float32)
+    q[:3] *= 1e4   # far outliers (FP16 overflow of the query operand when large enough): must fail the certificate, not the result
+    index = engine.knn_fit(torch.from_numpy(ref).to(cuda_device))
+    Q = torch.from_numpy(q).to(cuda_device)
+    idx, dist2, unsafe = engine.knn_search(index, Q, k, engine.KNN_TC16)
+    ok = (unsafe == 0).cpu().numpy()
+    assert ok.mean() > 0.5, ok.mean()
+    _check_knn(idx.cpu().numpy()[ok], dist2.cpu().numpy()[ok], ref, q[ok], k)
+    idx2, dist22, n_rep = engine.knn_search_certified(index, Q, k)          # auto: FP16 -> BF16x3 -> FP32
+    assert n_rep == int((~ok).sum())
+    _check_knn(idx2.cpu().numpy(), dist22.cpu().numpy(), ref, q, k)
+
+
+def test_knn_auto_falls_back_when_fp16_certificates_fail(cuda_device):
+    """Dense neighbourhoods (gaps far below the FP16 score error): most rows fail the FP16 certificate, the
+    results still equal sklearn's, and the index starts with BF16x3 from the second call on."""
+    rng = np.random.default_rng(5)
+    M, N, d, k = 40000, 6000, 50, 30
+    ref = (rng.normal(size=(M, d)) + 6.0).astype(np.float32)      # norms ~6x the spread: FP16 error > neighbour gaps
+    q = (rng.normal(size=(N, d)) + 6.0).astype(np.float32)
+    index = engine.knn_fit(torch.from_numpy(ref).to(cuda_device))
+    Q = torch.from_numpy(q).to(cuda_device)
+    idx, dist2, n_rep = engine.knn_search_certified(index, Q, k)
+    assert n_rep > 0.08 * N and index.first_tier[k] == engine.KNN_TC
+    _check_knn(idx.cpu().numpy(), dist2.cpu().numpy(), ref, q, k)
+    idx_b, dist2_b, _ = engine.knn_search_certified(index, Q, k)
+    assert torch.equal(idx, idx_b)
+
 def test_knn_locality_order_does_not_change_results(cuda_device):
     """Reference packed in cluster order + queries scanned in cluster order == plain order, and both == sklearn."""
     rng = np.random.default_rng(11)
