@@ -188,9 +188,12 @@ group_cov_kernel(const float *__restrict__ X, int ldx, int64_t N, int d, int G, 
     for (int c = tid; c < ch.n; c += GC_THREADS) ids[c] = perm ? perm[ch.pos + c] : (int32_t)(ch.pos + c);
     const int nent = d * d;
     const float *mu = mean + (int64_t)ch.level * d;
-    float acc[16];
+    // x - mean is exact in FP32 (both are floats within a factor of two for any cluster worth scoring); the
+    // products are summed in FP64: small clusters have ill-conditioned covariances whose inverse amplifies
+    // FP32 accumulation error beyond the 1e-4 parity bar (2 d^2 FP64 flop per cell is nothing here)
+    double acc[16];
 #pragma unroll
-    for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+    for (int e = 0; e < 16; ++e) acc[e] = 0.0;
     for (int s0 = 0; s0 < ch.n; s0 += 32) {
         __syncthreads();
         for (int i = tid; i < 32 * d; i += GC_THREADS) {
@@ -203,9 +206,9 @@ group_cov_kernel(const float *__restrict__ X, int ldx, int64_t N, int d, int G, 
             const int ent = tid + e * GC_THREADS;
             if (ent < nent) {
                 const int i = ent / d, j = ent - i * d;
-                float a = acc[e];
+                double a = acc[e];
 #pragma unroll 8
-                for (int c = 0; c < 32; ++c) a = fmaf(xs[c * (d + 1) + i], xs[c * (d + 1) + j], a);
+                for (int c = 0; c < 32; ++c) a = fma((double)xs[c * (d + 1) + i], (double)xs[c * (d + 1) + j], a);
                 acc[e] = a;
             }
         }
@@ -213,7 +216,7 @@ group_cov_kernel(const float *__restrict__ X, int ldx, int64_t N, int d, int G, 
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
         const int ent = tid + e * GC_THREADS;
-        if (ent < nent) atomicAdd(&cov[(int64_t)ch.level * nent + ent], (double)acc[e]);
+        if (ent < nent) atomicAdd(&cov[(int64_t)ch.level * nent + ent], acc[e]);
     }
 }
 

@@ -394,9 +394,14 @@ __device__ __noinline__ float tc_insert(unsigned long long *heap, int kc, float 
     while (g##G < thr) {                                                                              \
         int j = 7;                                                                                    \
         _Pragma("unroll") for (int e = 6; e >= 0; --e) j = __uint_as_float(v[(G) * 8 + e]) == g##G ? e : j; \
-        if (pend_id != 0xffffffffu) thr = tc_insert(heap, kc, pend_s, pend_id);                       \
-        pend_s = g##G;                                                                                \
-        pend_id = ref0 + (uint32_t)((G) * 8) + (uint32_t)j;                                           \
+        if (pend_id != 0xffffffffu) {                                                                 \
+            thr = tc_insert(heap, kc, pend_s, pend_id);                                               \
+            pend_id = 0xffffffffu;                                                                    \
+        }                                                                                             \
+        if (g##G < thr) {   /* still a hit against the threshold as it is NOW (the update lowered it) */ \
+            pend_s = g##G;                                                                            \
+            pend_id = ref0 + (uint32_t)((G) * 8) + (uint32_t)j;                                       \
+        }                                                                                             \
         _Pragma("unroll") for (int e = 0; e < 8; ++e) v[(G) * 8 + e] = j == e ? 0x7f800000u : v[(G) * 8 + e]; \
         g##G = tc_min8(v + (G) * 8);                                                                  \
     }
@@ -414,7 +419,10 @@ __device__ __forceinline__ float tc_min8(const uint32_t *v) {
 // A hit is parked in a one-entry pending slot (registers) and only goes into the heap when the lane's next hit
 // arrives or at the periodic flush, where all lanes that have something pending update their rows TOGETHER: in
 // the sparse phase of the scan (about one hit per warp and tile) this turns several serial ~400-cycle heap
-// updates into one.  The threshold of a lane with a pending hit is stale by that one entry (never too small).
+// updates into one.  The threshold of a lane with a pending hit is stale by that one entry (never too small);
+// a parked hit is always below the threshold in force when it was parked, and the threshold does not move until
+// it is inserted — tc_insert must never be given a score that is not below the current root, it would evict a
+// better candidate and void the certificate.
 struct TcProf {
     long long walked_cyc = 0, plain_cyc = 0;
     int walked = 0;
@@ -825,21 +833,27 @@ TcPlan tc_plan(int64_t N, int64_t M, int d, int k, int prec) {
     const char *force_qt = getenv("SYM_TC_QT");      // tuning / experiments only
     const char *force_nbuf = getenv("SYM_TC_NBUF");
     const char *force_h = getenv("SYM_TC_HALVES");
-    p.ss = getenv("SYM_TC_SS") && atoi(getenv("SYM_TC_SS")) ? 1 : 0;   // experiment: query operand in shared memory
-    // preference: 256 rows per CTA, then 128.  Two selection warps per quadrant (64 columns each, two heaps per
-    // row) are implemented but measured ~8% slower at config 2, so they are only used when asked for.
-    const int cfg[4][2] = {{2, 1}, {1, 1}, {2, 2}, {1, 2}};
-    for (int c = 0; c < 4; ++c) {
-        const int qt = cfg[c][0], h = cfg[c][1];
+    const char *force_ss = getenv("SYM_TC_SS");
+    // Preference: 256 rows per CTA, then 128; within that, the query operand in SHARED memory when there is room
+    // for it next to >= 3 reference stages: tensor memory then holds four accumulators, two per query tile, and the
+    // two query tiles stop sharing a rotation (measured 2-5 % faster than the tensor-memory operand with three
+    // shared accumulators; the SS form's slower MMA does not matter because selection is the bottleneck).
+    // Two selection warps per quadrant (64 columns each, two heaps per row) are implemented but measured ~8 %
+    // slower at config 2, so they are only used when asked for.
+    const int cfg[8][3] = {{2, 1, 1}, {2, 1, 0}, {1, 1, 1}, {1, 1, 0}, {2, 2, 1}, {2, 2, 0}, {1, 2, 1}, {1, 2, 0}};
+    for (int c = 0; c < 8; ++c) {
+        const int qt = cfg[c][0], h = cfg[c][1], ss = cfg[c][2];
         if (force_qt && atoi(force_qt) != qt) continue;
         if (force_h ? atoi(force_h) != h : h != 1) continue;
+        if (force_ss && (atoi(force_ss) != 0) != (ss != 0)) continue;
         fixed = (size_t)qt * h * tc_heap_stride(kc) * TC_BM * 8 + 256 /* barriers */ + 1024 /* alignment slack */ +
-                (p.ss ? (size_t)qt * tile + 1024 : 0);
+                (ss ? (size_t)qt * tile + 1024 : 0);
         stages = budget > fixed ? (int)((budget - fixed) / tile) : 0;
         if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
         p.qt = qt;
         p.halves = h;
-        p.nbuf = (512 - (p.ss ? 0 : qt * p.kp / 2)) / TC_BN;  // accumulators that fit beside the A operands in tensor memory
+        p.ss = ss;
+        p.nbuf = (512 - (ss ? 0 : qt * p.kp / 2)) / TC_BN;  // accumulators that fit beside the A operands in tensor memory
         if (p.nbuf > 4) p.nbuf = 4;
         if (force_nbuf && atoi(force_nbuf) >= 1 && atoi(force_nbuf) <= p.nbuf) p.nbuf = atoi(force_nbuf);
         if (stages >= 3 && p.nbuf >= 2) break;

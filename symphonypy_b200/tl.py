@@ -41,7 +41,7 @@ class settings:
 
     device = None                  # torch device; default: current CUDA device (LOCAL_RANK under torchrun)
     h2d_chunk_bytes = 256 << 20    # rows of X are streamed to the GPU in chunks of about this size
-    knn_method = engine.KNN_AUTO   # 0 auto, 1 FP32 FFMA scan, 2 tcgen05 scan
+    knn_method = engine.KNN_AUTO   # 0 auto (tiered), 1 FP32 FFMA scan, 2 tcgen05 BF16x3 scan, 3 tcgen05 single-FP16 scan
     keep_on_device = True          # remember device copies of the arrays written to obsm
     store_R = True                 # write obsm[f"{basis}_symphony_R"] (N x K) as the reference does
 

