@@ -390,20 +390,20 @@ __device__ __noinline__ float tc_insert(unsigned long long *heap, int kc, float 
 // Lanes whose group of 8 holds a hit: locate the group minimum with compare/select pairs (no data-dependent
 // branch per element: the 8 sequential branches of a plain walk cost more than the heap update), record it,
 // blank it and look again — one round in all but a few cases.
-#define TC_WALK8(G)                                                                                   \
-    while (g##G < thr) {                                                                              \
+#define TC_WALK8(G, GV)                                                                               \
+    while (GV < thr) {                                                                                \
         int j = 7;                                                                                    \
-        _Pragma("unroll") for (int e = 6; e >= 0; --e) j = __uint_as_float(v[(G) * 8 + e]) == g##G ? e : j; \
+        _Pragma("unroll") for (int e = 6; e >= 0; --e) j = __uint_as_float(v[(G) * 8 + e]) == GV ? e : j; \
         if (pend_id != 0xffffffffu) {                                                                 \
             thr = tc_insert(heap, kc, pend_s, pend_id);                                               \
             pend_id = 0xffffffffu;                                                                    \
         }                                                                                             \
-        if (g##G < thr) {   /* still a hit against the threshold as it is NOW (the update lowered it) */ \
-            pend_s = g##G;                                                                            \
+        if (GV < thr) {   /* still a hit against the threshold as it is NOW (the update lowered it) */ \
+            pend_s = GV;                                                                              \
             pend_id = ref0 + (uint32_t)((G) * 8) + (uint32_t)j;                                       \
         }                                                                                             \
         _Pragma("unroll") for (int e = 0; e < 8; ++e) v[(G) * 8 + e] = j == e ? 0x7f800000u : v[(G) * 8 + e]; \
-        g##G = tc_min8(v + (G) * 8);                                                                  \
+        GV = tc_min8(v + (G) * 8);                                                                    \
     }
 
 __device__ __forceinline__ float tc_min8(const uint32_t *v) {
@@ -423,38 +423,27 @@ __device__ __forceinline__ float tc_min8(const uint32_t *v) {
 // a parked hit is always below the threshold in force when it was parked, and the threshold does not move until
 // it is inserted — tc_insert must never be given a score that is not below the current root, it would evict a
 // better candidate and void the certificate.
-struct TcProf {
-    long long walked_cyc = 0, plain_cyc = 0;
-    int walked = 0;
+// The common case (no hit anywhere in the tile) is one straight-line block: the group minima of ALL chunks of
+// the tile (16 independent 3-input-min chains for 128 scores), one overall minimum, one compare.  Interleaving
+// the chains of the four chunks matters: with a branch after every chunk the warp waited out the dependent
+// latency of each chunk's tree separately (two selection warps per scheduler cannot hide it).
+struct TcMins {
+    float g0, g1, g2, g3;
 };
-__device__ __forceinline__ float tc_select32(uint32_t (&v)[32], float thr, uint32_t ref0, unsigned long long *heap,
-                                             int kc, float &pend_s, uint32_t &pend_id, TcProf &pf) {
-#ifdef TC_PROFILE
-    const long long pc0 = clock64();
-#endif
-    float g0 = tc_min8(v), g1 = tc_min8(v + 8), g2 = tc_min8(v + 16), g3 = tc_min8(v + 24);
-    const float m = fminf(fmin3(g0, g1, g2), g3);
-#ifndef TC_EXPERIMENT_NO_WALK
-#ifdef TC_PROFILE
-    const bool walked = __any_sync(0xffffffffu, m < thr);
-#endif
-    if (m < thr) {
-        TC_WALK8(0)
-        TC_WALK8(1)
-        TC_WALK8(2)
-        TC_WALK8(3)
+__device__ __forceinline__ TcMins tc_mins32(const uint32_t (&v)[32]) {
+    return TcMins{tc_min8(v), tc_min8(v + 8), tc_min8(v + 16), tc_min8(v + 24)};
+}
+__device__ __forceinline__ float tc_min4(const TcMins &m) { return fminf(fmin3(m.g0, m.g1, m.g2), m.g3); }
+
+// slow path for one 32-column chunk: some lane of the warp has a hit somewhere in the tile
+__device__ __forceinline__ float tc_walk32(uint32_t (&v)[32], TcMins m, float thr, uint32_t ref0,
+                                           unsigned long long *heap, int kc, float &pend_s, uint32_t &pend_id) {
+    if (tc_min4(m) < thr) {
+        TC_WALK8(0, m.g0)
+        TC_WALK8(1, m.g1)
+        TC_WALK8(2, m.g2)
+        TC_WALK8(3, m.g3)
     }
-#ifdef TC_PROFILE
-    __syncwarp();
-    {
-        const long long dt = clock64() - pc0;
-        if (walked) { pf.walked += 1; pf.walked_cyc += dt; }
-        else pf.plain_cyc += dt;
-    }
-#endif
-#else
-    if (m < -1e30f) thr = m;
-#endif
     return thr;
 }
 
@@ -542,6 +531,13 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
     __syncthreads();
     tc_fence_after();
 
+    // Register reallocation between the warp groups (the launch bound of 168 registers per thread is what 384
+    // threads can share evenly): the producer / issuer group needs few, the selection warps hold a whole
+    // accumulator row (128 scores) plus the group minima and spill without the extra room.
+    if (TC_H == 1) {
+        if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    }
     if (warp == 0) {
         // ===== producer: one bulk copy per reference tile =====
         if (lane == 0) {
@@ -634,7 +630,6 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
 #ifdef TC_PROFILE
         long long prof_0 = 0, prof_1 = 0, prof_2 = 0, prof_3 = 0, prof_5 = 0, prof_6 = 0;
 #endif
-        TcProf pf;
         for (int i = 0; i < ntiles; ++i) {
             TC_CLK(c0);
 #ifdef TC_SLEEPY_SELECT
@@ -675,16 +670,26 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
                 thr_before = thr;
                 pend_before = pend_id;
 #endif
-                thr = tc_select32(v0, thr, ref0, heap, kc, pend_s, pend_id, pf);
-                thr = tc_select32(v1, thr, ref0 + 32, heap, kc, pend_s, pend_id, pf);
-                thr = tc_select32(v2, thr, ref0 + 64, heap, kc, pend_s, pend_id, pf);
-                thr = tc_select32(v3, thr, ref0 + 96, heap, kc, pend_s, pend_id, pf);
+                const TcMins m0 = tc_mins32(v0), m1 = tc_mins32(v1), m2 = tc_mins32(v2), m3 = tc_mins32(v3);
+#ifndef TC_EXPERIMENT_NO_WALK
+                if (fminf(fmin3(tc_min4(m0), tc_min4(m1), tc_min4(m2)), tc_min4(m3)) < thr) {
+                    thr = tc_walk32(v0, m0, thr, ref0, heap, kc, pend_s, pend_id);
+                    thr = tc_walk32(v1, m1, thr, ref0 + 32, heap, kc, pend_s, pend_id);
+                    thr = tc_walk32(v2, m2, thr, ref0 + 64, heap, kc, pend_s, pend_id);
+                    thr = tc_walk32(v3, m3, thr, ref0 + 96, heap, kc, pend_s, pend_id);
+                }
+#else
+                if (fminf(fmin3(tc_min4(m0), tc_min4(m1), tc_min4(m2)), tc_min4(m3)) < -1e30f) thr = 0.f;
+#endif
             } else {
                 tc_wait_ld();
                 tc_fence_before();
                 if (lane == 0) mbar_arrive(&t_empty[buf]);
-                thr = tc_select32(v0, thr, ref0, heap, kc, pend_s, pend_id, pf);
-                thr = tc_select32(v1, thr, ref0 + 32, heap, kc, pend_s, pend_id, pf);
+                const TcMins m0 = tc_mins32(v0), m1 = tc_mins32(v1);
+                if (fminf(tc_min4(m0), tc_min4(m1)) < thr) {
+                    thr = tc_walk32(v0, m0, thr, ref0, heap, kc, pend_s, pend_id);
+                    thr = tc_walk32(v1, m1, thr, ref0 + 32, heap, kc, pend_s, pend_id);
+                }
             }
 #ifdef TC_PROFILE
             const long long c3 = clock64();
@@ -716,8 +721,6 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
             atomicAdd(&tc_prof[2], (unsigned long long)prof_2); atomicAdd(&tc_prof[3], (unsigned long long)prof_3);
             atomicAdd(&tc_prof[4], (unsigned long long)ntiles); atomicAdd(&tc_prof[5], (unsigned long long)prof_5);
             atomicAdd(&tc_prof[6], (unsigned long long)prof_6);
-            atomicAdd(&tc_prof[13], (unsigned long long)pf.walked); atomicAdd(&tc_prof[14], (unsigned long long)pf.walked_cyc);
-            atomicAdd(&tc_prof[15], (unsigned long long)pf.plain_cyc);
         }
 #endif
         // results: the row's candidates as (score, position) keys (unordered) and its final threshold
