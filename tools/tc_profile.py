@@ -26,6 +26,3 @@ print(f"  per warp-tile cycles: wait_full {v[0]/wt:.0f}  ld {v[1]/wt:.0f}  exami
 print(f"  warp-tiles with a walk {v[5]/wt:.3f}; lane hits per warp-tile {v[6]/wt:.3f}")
 it = max(v[12], 1)
 print(f"  issuer per tile cycles: wait ref tile {v[8]/it:.0f}  wait free acc {v[9]/it:.0f}  wait turn {v[10]/it:.0f}  issue {v[11]/it:.0f}")
-ch = 4 * wt
-print(f"  chunks: walked {v[13]/ch:.4f} of all, {v[14]/max(v[13],1):.0f} cycles each; not walked {v[15]/max(ch-v[13],1):.0f} cycles each")
-print(f"  warp-level heap updates per warp-tile {v[7]/wt:.3f}")
