@@ -8,7 +8,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base dem
     --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_list_$TAG.log 2>&1
 echo "launch list exit $?"
 $CMD > gpurun_out/plain2_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k "regex:.*knn_scan_tc.*" -s 3 -c 1 -f -o gpurun_out/prof_$TAG \
+ncu --set full --clock-control none --import-source on -k "regex:.*knn_scan_tc.*" -s 4 -c 1 -f -o gpurun_out/prof_$TAG \
     $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
 echo "full capture exit $?"
 tail -1 gpurun_out/plain_$TAG.log | cut -c1-300

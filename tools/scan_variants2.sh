@@ -1,17 +1,16 @@
 #!/bin/bash
-# kNN stage (config2, repairs on) for a few tuning variants of the selection path.
+# kNN stage (config2 / config3, repairs on) for tuning variants of the selection path (single-FP16 first tier).
 run() {
   echo "== $*"
-  env "$@" timeout 300 python bench.py --workload ${W:-config2} --steps 3 --warmup 2 --no-cpu --no-e2e 2>/dev/null | python -c "
-import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('knn ms', round(d['stage_ms']['knn'],2), 'repaired', d['roofline'].get('rows_repaired_per_step'))"
+  for W in config2 config3; do
+  env "$@" timeout 300 python bench.py --workload $W --steps 3 --warmup 3 --no-cpu --no-e2e 2>/dev/null | python -c "
+import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('  $W knn ms', round(d['stage_ms']['knn'],2), 'repaired', d['roofline'].get('rows_repaired_per_step'))"
+  done
 }
-run SYM_TC_SS=0
-run SYM_TC_SS=1
-run SYM_TC_SS=1 SYM_TC_PAD=6
-run SYM_TC_SS=1 SYM_TC_PAD=4
-SYM_NVCC_EXTRA="-DTC_FLUSH=8" python -m symphonypy_b200.build --force > /dev/null 2>&1
-run SYM_TC_SS=1 FLUSH=8
-SYM_NVCC_EXTRA="-DTC_FLUSH=2" python -m symphonypy_b200.build --force > /dev/null 2>&1
-run SYM_TC_SS=1 FLUSH=2
+run A=base
+run SYM_TC_PAD=6
 SYM_NVCC_EXTRA="-DTC_FLUSH=16" python -m symphonypy_b200.build --force > /dev/null 2>&1
-run SYM_TC_SS=1 FLUSH=16
+run FLUSH=16
+SYM_NVCC_EXTRA="-DTC_FLUSH=1048576" python -m symphonypy_b200.build --force > /dev/null 2>&1
+run FLUSH=never
+run FLUSH=never SYM_TC_PAD=6
