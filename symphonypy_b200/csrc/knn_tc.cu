@@ -447,6 +447,63 @@ __device__ __forceinline__ float tc_walk32(uint32_t (&v)[32], TcMins m, float th
     return thr;
 }
 
+// Slow path for a whole 128-column tile (TC_H == 1).  A bit mask of the groups that hold a hit is built without
+// branches; each hit group is then copied into eight common registers by a 16-way switch (the only code that is
+// specific to a group: a lane's hit can sit in any of 16 register groups and registers cannot be indexed), and
+// ONE copy of the locate / park / blank / re-examine loop serves every lane of the warp, whatever group its hit
+// is in.  (The first version had that loop once per group: lanes with hits in different groups ran them one
+// after the other, ~20 divergent regions per walked tile.)
+__device__ __forceinline__ float tc_walk128(const uint32_t (&v0)[32], const uint32_t (&v1)[32], const uint32_t (&v2)[32],
+                                            const uint32_t (&v3)[32], const TcMins &m0, const TcMins &m1,
+                                            const TcMins &m2, const TcMins &m3, float thr, uint32_t ref0,
+                                            unsigned long long *heap, int kc, float &pend_s, uint32_t &pend_id) {
+    unsigned mask = 0;
+#define TC_BIT(GV, B) mask |= (GV < thr) ? (1u << (B)) : 0u;
+    TC_BIT(m0.g0, 0) TC_BIT(m0.g1, 1) TC_BIT(m0.g2, 2) TC_BIT(m0.g3, 3)
+    TC_BIT(m1.g0, 4) TC_BIT(m1.g1, 5) TC_BIT(m1.g2, 6) TC_BIT(m1.g3, 7)
+    TC_BIT(m2.g0, 8) TC_BIT(m2.g1, 9) TC_BIT(m2.g2, 10) TC_BIT(m2.g3, 11)
+    TC_BIT(m3.g0, 12) TC_BIT(m3.g1, 13) TC_BIT(m3.g2, 14) TC_BIT(m3.g3, 15)
+#undef TC_BIT
+    while (mask) {
+        const int gi = __ffs(mask) - 1;
+        mask &= mask - 1;
+        float w[8];
+#define TC_CASE(I, V, O)                                                                     \
+    case I:                                                                                  \
+        _Pragma("unroll") for (int e = 0; e < 8; ++e) w[e] = __uint_as_float(V[(O) + e]);   \
+        break;
+        switch (gi) {
+            TC_CASE(0, v0, 0) TC_CASE(1, v0, 8) TC_CASE(2, v0, 16) TC_CASE(3, v0, 24)
+            TC_CASE(4, v1, 0) TC_CASE(5, v1, 8) TC_CASE(6, v1, 16) TC_CASE(7, v1, 24)
+            TC_CASE(8, v2, 0) TC_CASE(9, v2, 8) TC_CASE(10, v2, 16) TC_CASE(11, v2, 24)
+            TC_CASE(12, v3, 0) TC_CASE(13, v3, 8) TC_CASE(14, v3, 16)
+            default:
+                _Pragma("unroll") for (int e = 0; e < 8; ++e) w[e] = __uint_as_float(v3[24 + e]);
+                break;
+        }
+#undef TC_CASE
+        const uint32_t id0 = ref0 + (uint32_t)(gi * 8);
+        float g = fminf(fmin3(fmin3(w[0], w[1], w[2]), w[3], w[4]), fmin3(w[5], w[6], w[7]));
+        while (g < thr) {   // almost always one round
+            int j = 7;
+#pragma unroll
+            for (int e = 6; e >= 0; --e) j = w[e] == g ? e : j;
+            if (pend_id != 0xffffffffu) {
+                thr = tc_insert(heap, kc, pend_s, pend_id);
+                pend_id = 0xffffffffu;
+            }
+            if (g < thr) {   // still a hit against the threshold as it is NOW (the update lowered it)
+                pend_s = g;
+                pend_id = id0 + (uint32_t)j;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) w[e] = j == e ? INFINITY : w[e];
+            g = fminf(fmin3(fmin3(w[0], w[1], w[2]), w[3], w[4]), fmin3(w[5], w[6], w[7]));
+        }
+    }
+    return thr;
+}
+
 template <int TC_QT, int TC_H>
 __global__ void __launch_bounds__(128 + 128 * TC_QT * TC_H, 1)
 knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char *__restrict__ rpack, int64_t N,
@@ -672,12 +729,8 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
 #endif
                 const TcMins m0 = tc_mins32(v0), m1 = tc_mins32(v1), m2 = tc_mins32(v2), m3 = tc_mins32(v3);
 #ifndef TC_EXPERIMENT_NO_WALK
-                if (fminf(fmin3(tc_min4(m0), tc_min4(m1), tc_min4(m2)), tc_min4(m3)) < thr) {
-                    thr = tc_walk32(v0, m0, thr, ref0, heap, kc, pend_s, pend_id);
-                    thr = tc_walk32(v1, m1, thr, ref0 + 32, heap, kc, pend_s, pend_id);
-                    thr = tc_walk32(v2, m2, thr, ref0 + 64, heap, kc, pend_s, pend_id);
-                    thr = tc_walk32(v3, m3, thr, ref0 + 96, heap, kc, pend_s, pend_id);
-                }
+                if (fminf(fmin3(tc_min4(m0), tc_min4(m1), tc_min4(m2)), tc_min4(m3)) < thr)
+                    thr = tc_walk128(v0, v1, v2, v3, m0, m1, m2, m3, thr, ref0, heap, kc, pend_s, pend_id);
 #else
                 if (fminf(fmin3(tc_min4(m0), tc_min4(m1), tc_min4(m2)), tc_min4(m3)) < -1e30f) thr = 0.f;
 #endif
