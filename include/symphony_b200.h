@@ -58,6 +58,21 @@ int sym_project_dense(const float *X, int64_t N, int64_t ldx, const int32_t *gen
                       const float *mu, const float *inv_sd, const float *U, int32_t ldu, int32_t d,
                       float clip, float *Z, int32_t ldz, sym_stream_t stream);
 
+/* Tensor-core form of the same projection for a query whose genes are already in reference order
+ * (gene_col == NULL) and whose rows are 16-byte aligned (ldx % 4 == 0): tcgen05 MMAs with FP16x3 split operands
+ * (hi + lo fp16 pairs, FP32-class results), bound by streaming X rather than by FFMA.
+ *   sym_project_pack: packs u_scale * U [G, ldu] once into `packed` (sym_project_pack_bytes(G, d) bytes,
+ *   16-byte aligned): per 32 genes a hi and a lo fp16 tile in the UMMA K-major layout.  u_scale: a power of two
+ *   that brings max |U| into [512, 1024) (keeps the lo parts in the normal fp16 range).
+ *   sym_project_dense_tc: out_scale = 1 / u_scale is applied to the accumulator.  clip <= 60000 (fp16 range).
+ */
+size_t sym_project_pack_bytes(int32_t G, int32_t d);
+int sym_project_pack(const float *U, int32_t ldu, int32_t G, int32_t d, float u_scale, void *packed,
+                     sym_stream_t stream);
+int sym_project_dense_tc(const float *X, int64_t N, int64_t ldx, int32_t G, const float *mu, const float *inv_sd,
+                         const void *packed, int32_t d, float clip, float out_scale, float *Z, int32_t ldz,
+                         sym_stream_t stream);
+
 /* CSR query (scipy layout) — replaces _utils.py:240-243,284-285 (densify) + :298-308.
  *   Z[n,:] = z0 + sum_{nnz j of row n, gene g=col_gene[indices[j]] >= 0}
  *                   (clip((data[j]-mu[g])*inv_sd[g]) - clip(-mu[g]*inv_sd[g])) * U[g,:]

@@ -21,6 +21,10 @@ SIGNATURES = {
     "sym_compiled_arch": (c_int32, []),
     "sym_project_dense": (c_int32, [_P, c_int64, c_int64, _P, c_int32, _P, _P, _P, c_int32, c_int32, c_float, _P,
                                     c_int32, _P]),
+    "sym_project_pack_bytes": (c_size_t, [c_int32, c_int32]),
+    "sym_project_pack": (c_int32, [_P, c_int32, c_int32, c_int32, c_float, _P, _P]),
+    "sym_project_dense_tc": (c_int32, [_P, c_int64, c_int64, c_int32, _P, _P, _P, c_int32, c_float, c_float, _P, c_int32,
+                                      _P]),
     "sym_project_csr_bias": (c_int32, [_P, _P, _P, c_int32, c_int32, c_int32, c_float, _P, _P]),
     "sym_project_csr": (c_int32, [_P, _P, _P, c_int64, _P, _P, _P, _P, c_int32, c_int32, c_float, _P, _P, c_int32, _P]),
     "sym_assign": (c_int32, [_P, c_int32, c_int64, c_int32, _P, c_int32, _P, _P, _P]),

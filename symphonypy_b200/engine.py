@@ -7,6 +7,7 @@ torch stream of the tensor's device.
 """
 from __future__ import annotations
 
+import math
 import os
 from dataclasses import dataclass, field
 
@@ -18,6 +19,7 @@ from . import _lib
 CLIP = 10.0  # `symphonypy/_utils.py:253`: max_value, fixed by the reference API
 KNN_AUTO, KNN_FFMA, KNN_TCGEN05, KNN_TC16 = 0, 1, 2, 3
 KNN_TC = KNN_TCGEN05
+PROJECT_TC = os.environ.get("SYM_PROJECT_TC", "1") != "0"   # tensor-core projection when the layout allows
 
 
 def _ptr(t):
@@ -50,6 +52,8 @@ class Loadings:
     U: torch.Tensor        # [G, ldu] f32, zero padded, ldu % 4 == 0
     d: int
     z0: torch.Tensor | None = None  # CSR bias, filled lazily
+    upack: torch.Tensor | None = None  # loadings packed for the tensor-core projection, filled lazily
+    u_scale: float = 1.0               # power of two applied to U in `upack`
 
     @property
     def G(self) -> int:
@@ -83,6 +87,21 @@ def project_dense(X: torch.Tensor, ld: Loadings, gene_col: torch.Tensor | None =
     if gene_col is None:
         assert X.shape[1] >= ld.G
     Z = out if out is not None else torch.empty((N, ld.d), device=X.device, dtype=torch.float32)
+    # genes already in reference order and 16-byte aligned rows: tensor-core kernel (FP16x3, X-streaming bound);
+    # otherwise (column gather, odd strides) the FP32 FFMA kernel
+    if PROJECT_TC and gene_col is None and X.stride(0) % 4 == 0 and X.data_ptr() % 16 == 0 and N > 0:
+        if ld.upack is None:
+            umax = float(ld.U.abs().max().item())
+            # power of two bringing max |U| into [512, 1024): the fp16 lo parts stay normal, nothing overflows
+            ld.u_scale = float(2.0 ** (9 - math.floor(math.log2(umax)))) if umax > 0 and math.isfinite(umax) else 1.0
+            nbytes = int(lib.sym_project_pack_bytes(ld.G, ld.d))
+            ld.upack = torch.empty(nbytes, device=X.device, dtype=torch.uint8)
+            _lib.check(lib.sym_project_pack(ld.U.data_ptr(), ld.U.stride(0), ld.G, ld.d, ld.u_scale, ld.upack.data_ptr(),
+                                            _stream(X.device)), "sym_project_pack")
+        _lib.check(lib.sym_project_dense_tc(X.data_ptr(), N, X.stride(0), ld.G, ld.mu.data_ptr(), ld.inv_sd.data_ptr(),
+                                            ld.upack.data_ptr(), ld.d, CLIP, 1.0 / ld.u_scale, Z.data_ptr(), Z.stride(0),
+                                            _stream(X.device)), "sym_project_dense_tc")
+        return Z
     _lib.check(lib.sym_project_dense(X.data_ptr(), N, X.stride(0), _ptr(gene_col), ld.G, ld.mu.data_ptr(),
                                      ld.inv_sd.data_ptr(), ld.U.data_ptr(), ld.U.stride(0), ld.d, CLIP,
                                      Z.data_ptr(), Z.stride(0), _stream(X.device)), "sym_project_dense")

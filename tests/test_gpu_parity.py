@@ -81,8 +81,13 @@ def test_config1_against_oracle(cuda_device, variant):
 
 
 # ------------------------------------------------------------------------------ kernel level: project
-@pytest.mark.parametrize("N,G,d", [(1, 5, 3), (257, 2000, 20), (1000, 333, 30), (130, 96, 50), (64, 40, 100)])
-def test_project_dense_kernel(cuda_device, N, G, d):
+@pytest.mark.parametrize("tc", [False, True], ids=["ffma", "tcgen05"])
+@pytest.mark.parametrize("N,G,d", [(1, 5, 3), (257, 2000, 20), (1000, 333, 30), (130, 96, 50), (64, 40, 100),
+                                   (5000, 2000, 30), (300, 1028, 64)])
+def test_project_dense_kernel(cuda_device, monkeypatch, N, G, d, tc):
+    """Both projection kernels against float64: the FP32 FFMA kernel (2e-5 row-relative) and the tcgen05 BF16x3
+    kernel (FP16x3; taken when genes are in order and rows are 16-byte aligned), same bar."""
+    monkeypatch.setattr(engine, "PROJECT_TC", tc)
     rng = np.random.default_rng(N + G)
     X = (rng.gamma(2.0, 0.8, (N, G)) * (rng.random((N, G)) < 0.3)).astype(np.float32)
     X[0, 0] = 500.0  # exercises the clip
@@ -95,8 +100,11 @@ def test_project_dense_kernel(cuda_device, N, G, d):
     t[:, ok] = np.clip((X[:, ok].astype(np.float64) - mu[ok]) / sd[ok], -10, 10)
     want = t @ U
     ld = engine.make_loadings(mu, sd, U, present, cuda_device)
+    n0 = engine._lib.launch_count()
     Z = engine.project_dense(torch.from_numpy(X).to(cuda_device), ld)
     assert row_rel_err(Z.cpu().numpy(), want) < 2e-5
+    if tc and G % 4 == 0:
+        assert ld.upack is not None   # the tensor-core kernel ran
     # gather path: same matrix with shuffled columns plus an index
     perm = rng.permutation(G)
     Xs = np.ascontiguousarray(X[:, perm])
