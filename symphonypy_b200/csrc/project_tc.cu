@@ -29,6 +29,9 @@ namespace sym {
 constexpr int PT_BM = 128;          // cells per CTA (UMMA M)
 constexpr int PT_GK = 32;           // genes per stage
 constexpr int PT_STAGES = 3;
+#ifndef PT_AHEAD
+#define PT_AHEAD 1                  // chunks of X prefetched into registers per producer thread
+#endif
 constexpr int PT_PRODUCERS = 256;   // producer threads
 constexpr int PT_THREADS = PT_PRODUCERS + 32;
 constexpr uint32_t PT_A_TILE = PT_BM * PT_GK * 2;   // one 16-bit operand tile of the cells: 8 KB
@@ -36,6 +39,20 @@ constexpr uint32_t PT_A_TILE = PT_BM * PT_GK * 2;   // one 16-bit operand tile o
 __host__ __device__ inline int pt_dpad(int d) { return d <= 32 ? 32 : d <= 64 ? 64 : 128; }
 __host__ __device__ inline size_t pt_b_tile(int dpad) { return (size_t)dpad * PT_GK * 2; }   // one 16-bit tile of U
 
+// Streaming loads of 8 consecutive floats (one thread's share of a chunk).  One 256-bit load when the row pitch
+// allows (32-byte aligned): with two 128-bit loads every 32-byte sector is requested twice, by different
+// instructions, and without L1 allocation both requests go to L2 — the kernel was then bound by L2 -> SM sector
+// traffic at twice the bytes of X.  The 128-bit fallback therefore allocates in L1.
+__device__ __forceinline__ void pt_ldg8(const float *p, bool wide, float4 &a, float4 &b) {
+    if (wide) {
+        asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                     : "l"(p));
+    } else {
+        a = __ldg(reinterpret_cast<const float4 *>(p));
+        b = __ldg(reinterpret_cast<const float4 *>(p + 4));
+    }
+}
 // two floats -> packed fp16 pair (.x = a in the low half), and back
 __device__ __forceinline__ uint32_t pt_pack(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
@@ -115,12 +132,34 @@ project_tc_kernel(const float *__restrict__ X, int64_t N, int64_t ldx, int G, co
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < 8) {
-        // ===== producers: item j = (cell j*64 + tid/4, k-unit tid%4): 8 consecutive genes of one cell =====
-        const int ku = tid & 3;
-        const int rl[2] = {tid >> 2, 64 + (tid >> 2)};
-        float4 nx[2][2];   // the next chunk, in flight
-        auto load = [&](int c) {
+        // ===== producers: item j = (cell j*64 + 8*warp + lane%8, k-unit lane/8): 8 consecutive genes of one cell =====
+        // lane = ku * 8 + (row % 8): the 8 lanes that a 128-bit shared-memory store handles together write the
+        // same k-unit of 8 consecutive cells = 128 contiguous bytes (with ku fastest they hit the same banks four
+        // at a time: 16 wavefronts per store instead of 4, and the shared-memory pipe became the bottleneck)
+        const int ku = lane >> 3;
+        const int rl[2] = {warp * 8 + (lane & 7), 64 + warp * 8 + (lane & 7)};
+        const bool wide = (ldx % 8) == 0 && (reinterpret_cast<uintptr_t>(X) & 31) == 0;
+        float4 nxbuf[PT_AHEAD][2][2];   // the next PT_AHEAD chunks, in flight
+        float4 msbuf[PT_AHEAD][4];      // their per-gene offsets and scales (mu x2, inv_sd x2): loaded ahead as well,
+                                        // an L2-latency load right before its use was the top stall of this kernel
+        auto load = [&](int c, float4 (&nx)[2][2], float4 (&ms)[4]) {
             const int g = c * PT_GK + ku * 8;
+            if (g + 8 <= G) {   // g is a multiple of 8: 32-byte aligned
+                ms[0] = __ldg(reinterpret_cast<const float4 *>(mu + g));
+                ms[1] = __ldg(reinterpret_cast<const float4 *>(mu + g + 4));
+                ms[2] = __ldg(reinterpret_cast<const float4 *>(inv_sd + g));
+                ms[3] = __ldg(reinterpret_cast<const float4 *>(inv_sd + g + 4));
+            } else {
+                float t[16];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const bool ok = g + e < G;
+                    t[e] = ok ? __ldg(mu + g + e) : 0.f;
+                    t[8 + e] = ok ? __ldg(inv_sd + g + e) : 0.f;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) ms[q] = make_float4(t[4 * q], t[4 * q + 1], t[4 * q + 2], t[4 * q + 3]);
+            }
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const int64_t row = row0 + rl[j];
@@ -128,8 +167,7 @@ project_tc_kernel(const float *__restrict__ X, int64_t N, int64_t ldx, int G, co
                 if (row < N) {
                     const float *p = X + row * ldx + g;
                     if (g + 8 <= G) {
-                        a = ldg_stream(reinterpret_cast<const float4 *>(p));
-                        b = ldg_stream(reinterpret_cast<const float4 *>(p + 4));
+                        pt_ldg8(p, wide, a, b);
                     } else {
                         float t[8];
 #pragma unroll
@@ -142,8 +180,10 @@ project_tc_kernel(const float *__restrict__ X, int64_t N, int64_t ldx, int G, co
                 nx[j][1] = b;
             }
         };
-        load(0);
-        for (int c = 0; c < nchunks; ++c) {
+#pragma unroll
+        for (int a = 0; a < PT_AHEAD; ++a)
+            if (a < nchunks) load(a, nxbuf[a], msbuf[a]);
+        auto step = [&](int c, float4 (&nx)[2][2], float4 (&ms)[4]) {
             const int s = c % PT_STAGES;
             const uint32_t ph = (uint32_t)((c / PT_STAGES) & 1);
             float x[2][8];
@@ -152,23 +192,9 @@ project_tc_kernel(const float *__restrict__ X, int64_t N, int64_t ldx, int G, co
                 x[j][0] = nx[j][0].x; x[j][1] = nx[j][0].y; x[j][2] = nx[j][0].z; x[j][3] = nx[j][0].w;
                 x[j][4] = nx[j][1].x; x[j][5] = nx[j][1].y; x[j][6] = nx[j][1].z; x[j][7] = nx[j][1].w;
             }
-            if (c + 1 < nchunks) load(c + 1);
-            // per-gene scale and offset of this thread's 8 genes
-            const int g = c * PT_GK + ku * 8;
-            float m[8], is[8];
-            if (g + 8 <= G) {   // g is a multiple of 8: 32-byte aligned
-                const float4 m0 = __ldg(reinterpret_cast<const float4 *>(mu + g)), m1 = __ldg(reinterpret_cast<const float4 *>(mu + g + 4));
-                const float4 s0 = __ldg(reinterpret_cast<const float4 *>(inv_sd + g)), s1 = __ldg(reinterpret_cast<const float4 *>(inv_sd + g + 4));
-                m[0] = m0.x; m[1] = m0.y; m[2] = m0.z; m[3] = m0.w; m[4] = m1.x; m[5] = m1.y; m[6] = m1.z; m[7] = m1.w;
-                is[0] = s0.x; is[1] = s0.y; is[2] = s0.z; is[3] = s0.w; is[4] = s1.x; is[5] = s1.y; is[6] = s1.z; is[7] = s1.w;
-            } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const bool ok = g + e < G;
-                    m[e] = ok ? __ldg(mu + g + e) : 0.f;
-                    is[e] = ok ? __ldg(inv_sd + g + e) : 0.f;
-                }
-            }
+            const float m[8] = {ms[0].x, ms[0].y, ms[0].z, ms[0].w, ms[1].x, ms[1].y, ms[1].z, ms[1].w};
+            const float is[8] = {ms[2].x, ms[2].y, ms[2].z, ms[2].w, ms[3].x, ms[3].y, ms[3].z, ms[3].w};
+            if (c + PT_AHEAD < nchunks) load(c + PT_AHEAD, nx, ms);
             mbar_wait(&empty[s], ph ^ 1);   // the MMAs that read this stage last time are done
             unsigned char *stage = psm + (size_t)s * STAGE;
             if (tid == 0) {   // this chunk's loadings: [hi | lo] in one bulk copy
@@ -196,6 +222,11 @@ project_tc_kernel(const float *__restrict__ X, int64_t N, int64_t ldx, int G, co
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> tensor core reads
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_full[s]);
+        };
+        for (int c0 = 0; c0 < nchunks; c0 += PT_AHEAD) {
+#pragma unroll
+            for (int a = 0; a < PT_AHEAD; ++a)
+                if (c0 + a < nchunks) step(c0 + a, nxbuf[a], msbuf[a]);
         }
         // ===== epilogue: accumulator rows -> Z =====
         if (warp < 4) {
