@@ -118,15 +118,48 @@ moe_stats_kernel(const float *__restrict__ Z, int ldz, const float *__restrict__
     extern __shared__ __align__(16) float smem[];
     const int KP = (K + 7) & ~7;           // R row stride in smem
     const int DP = ((d + 1) + 3) & ~3;     // [Z|1] row stride
-    float *Rs = smem;                      // [ST_SUB][KP]
-    float *Zs = Rs + ST_SUB * KP;          // [ST_SUB][DP]
-    int32_t *ids = reinterpret_cast<int32_t *>(Zs + ST_SUB * DP);  // [MOE_CH] cell ids of the chunk
+    // two stages of [ST_SUB][KP] R rows and [ST_SUB][DP] [Z|1] rows, filled by cp.async straight from global
+    // memory (no register round trip: the load -> STS dependency of a synchronous fill was 58 % of this kernel's
+    // stalls), the next stage in flight while the current one is multiplied
+    const int stage_floats = ST_SUB * KP + ST_SUB * DP;
+    int32_t *ids = reinterpret_cast<int32_t *>(smem + 2 * stage_floats);  // [MOE_CH] cell ids of the chunk
     const int tid = threadIdx.x;
     for (int i = tid; i < ch.n; i += ST_THREADS) ids[i] = perm ? perm[ch.pos + i] : (int32_t)(ch.pos + i);
     __syncthreads();
 
     const int col = 1 + var_offset.off[v] + ch.level;  // design column of this level
     const int tk = tid / 16, tc = tid % 16;         // 16 x 16 threads -> 128 clusters x 64 columns
+    const bool r16 = (K % 4) == 0 && (reinterpret_cast<uintptr_t>(R) & 15) == 0;          // 16-byte copies of R rows
+    const bool z8 = (d % 2) == 0 && (ldz % 2) == 0 && (reinterpret_cast<uintptr_t>(Z) & 7) == 0;   // 8-byte copies of Z rows
+    const int kv = KP / 4, zv = z8 ? d / 2 : d;
+    auto fill = [&](int stage, int s0) {
+        float *Rs = smem + stage * stage_floats, *Zs = Rs + ST_SUB * KP;
+        const int ns = ch.n - s0 < ST_SUB ? ch.n - s0 : ST_SUB;
+        if (r16) {
+            for (int i = tid; i < ST_SUB * kv; i += ST_THREADS) {
+                const int c = i / kv, k = (i - c * kv) * 4;
+                const bool ok = c < ns && k < K;
+                cp_async16_zfill(Rs + c * KP + k, ok ? R + (int64_t)ids[s0 + c] * K + k : R, ok);
+            }
+        } else {
+            for (int i = tid; i < ST_SUB * KP; i += ST_THREADS) {
+                const int c = i / KP, k = i - c * KP;
+                const bool ok = c < ns && k < K;
+                cp_async4_zfill(Rs + i, ok ? R + (int64_t)ids[s0 + c] * K + k : R, ok);
+            }
+        }
+        for (int i = tid; i < ST_SUB * zv; i += ST_THREADS) {
+            const int c = i / zv, j = i - c * zv;
+            const bool ok = c < ns;
+            if (z8) cp_async8_zfill(Zs + c * DP + 2 * j, ok ? Z + (int64_t)ids[s0 + c] * ldz + 2 * j : Z, ok);
+            else cp_async4_zfill(Zs + c * DP + j, ok ? Z + (int64_t)ids[s0 + c] * ldz + j : Z, ok);
+        }
+        for (int i = tid; i < ST_SUB * (DP - d); i += ST_THREADS) {   // the ones column and the padding
+            const int c = i / (DP - d), j = d + (i - c * (DP - d));
+            Zs[c * DP + j] = (j == d && c < ns) ? 1.f : 0.f;
+        }
+        cp_async_commit();
+    };
     for (int k0 = 0; k0 < K; k0 += 128) {
         for (int c0 = 0; c0 < d + 1; c0 += 64) {
             float acc[8][4];
@@ -134,20 +167,18 @@ moe_stats_kernel(const float *__restrict__ Z, int ldz, const float *__restrict__
             for (int i = 0; i < 8; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-            for (int s0 = 0; s0 < ch.n; s0 += ST_SUB) {
-                const int ns = ch.n - s0 < ST_SUB ? ch.n - s0 : ST_SUB;
-                __syncthreads();
-                for (int i = tid; i < ST_SUB * KP; i += ST_THREADS) {
-                    const int c = i / KP, k = i % KP;
-                    Rs[i] = (c < ns && k < K) ? R[(int64_t)ids[s0 + c] * K + k] : 0.f;
-                }
-                for (int i = tid; i < ST_SUB * DP; i += ST_THREADS) {
-                    const int c = i / DP, j = i % DP;
-                    float val = 0.f;
-                    if (c < ns) val = j < d ? Z[(int64_t)ids[s0 + c] * ldz + j] : (j == d ? 1.f : 0.f);
-                    Zs[i] = val;
+            __syncthreads();   // everyone is done with both stages of the previous pass
+            fill(0, 0);
+            int stage = 0;
+            for (int s0 = 0; s0 < ch.n; s0 += ST_SUB, stage ^= 1) {
+                if (s0 + ST_SUB < ch.n) {
+                    fill(stage ^ 1, s0 + ST_SUB);
+                    cp_async_wait<1>();
+                } else {
+                    cp_async_wait<0>();
                 }
                 __syncthreads();
+                const float *Rs = smem + stage * stage_floats, *Zs = Rs + ST_SUB * KP;
                 const int kb = k0 + tk * 8, cb = c0 + tc * 4;
                 if (kb < KP && cb < DP) {
 #pragma unroll 4
@@ -165,6 +196,7 @@ moe_stats_kernel(const float *__restrict__ Z, int ldz, const float *__restrict__
                         }
                     }
                 }
+                __syncthreads();   // before the stage just read is refilled (two fills from now)
             }
             const int kb = k0 + tk * 8, cb = c0 + tc * 4;
 #pragma unroll
@@ -401,7 +433,7 @@ extern "C" int sym_moe_stats(const float *Z, int32_t ldz, const float *R, int64_
                 "sym_moe_stats: a variable with several levels needs sym_batch_order output");
     if (N == 0) return SYM_OK;
     const int KP = (K + 7) & ~7, DP = ((d + 1) + 3) & ~3;
-    const size_t smem = (size_t)(ST_SUB * KP + ST_SUB * DP) * sizeof(float) + MOE_CH * sizeof(int32_t);
+    const size_t smem = 2 * (size_t)(ST_SUB * KP + ST_SUB * DP) * sizeof(float) + MOE_CH * sizeof(int32_t);
     SYM_REQUIRE(smem <= 200 * 1024, SYM_ERR_UNSUPPORTED_SHAPE, "sym_moe_stats: K=%d too large", K);
     SYM_CUDA(cudaFuncSetAttribute(moe_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SYM_REQUIRE(V <= MOE_MAX_VARS, SYM_ERR_UNSUPPORTED_SHAPE, "sym_moe_stats: more than %d batch variables", MOE_MAX_VARS);
