@@ -336,8 +336,9 @@ moe_apply_kernel(const float *__restrict__ Zin, int ldzin, const float *__restri
     const int DP = (d + 3) & ~3;
     const int KP = (K + 3) & ~3;
     float *Ws = smem;                 // [KP][DP]   W[:, col, :]
-    float *Rs = Ws + (size_t)KP * DP; // [64][AP_KS + 4]
-    int32_t *ids = reinterpret_cast<int32_t *>(Rs + 64 * (AP_KS + 4));
+    float *Rs0 = Ws + (size_t)KP * DP; // 2 stages of [64][AP_KS + 4], filled by cp.async
+    constexpr int RS = 64 * (AP_KS + 4);
+    int32_t *ids = reinterpret_cast<int32_t *>(Rs0 + 2 * RS);
     const int tid = threadIdx.x;
     const int col = 1 + var_offset + ch.level;
     for (int i = tid; i < ch.n; i += AP_THREADS) ids[i] = perm ? perm[ch.pos + i] : (int32_t)(ch.pos + i);
@@ -347,6 +348,24 @@ moe_apply_kernel(const float *__restrict__ Zin, int ldzin, const float *__restri
     }
     __syncthreads();
     const int tr = tid / 16, tc = tid % 16;  // rows tr + 16*i (i<4), outputs tc*4..+3
+    const bool r16 = (K % 4) == 0 && (reinterpret_cast<uintptr_t>(R) & 15) == 0;
+    auto fill = [&](int stage, int r0, int k0) {   // R[rows r0..r0+63, clusters k0..k0+31] -> stage
+        float *Rs = Rs0 + stage * RS;
+        if (r16) {
+            for (int i = tid; i < 64 * (AP_KS / 4); i += AP_THREADS) {
+                const int r = i / (AP_KS / 4), k = (i % (AP_KS / 4)) * 4;
+                const bool ok = r0 + r < ch.n && k0 + k < K;
+                cp_async16_zfill(Rs + r * (AP_KS + 4) + k, ok ? R + (int64_t)ids[r0 + r] * K + k0 + k : R, ok);
+            }
+        } else {
+            for (int i = tid; i < 64 * AP_KS; i += AP_THREADS) {
+                const int r = i / AP_KS, k = i % AP_KS;
+                const bool ok = r0 + r < ch.n && k0 + k < K;
+                cp_async4_zfill(Rs + r * (AP_KS + 4) + k, ok ? R + (int64_t)ids[r0 + r] * K + k0 + k : R, ok);
+            }
+        }
+        cp_async_commit();
+    };
     for (int r0 = 0; r0 < ch.n; r0 += 64) {
         for (int c0 = 0; c0 < d; c0 += 64) {
             float acc[4][4];
@@ -354,14 +373,18 @@ moe_apply_kernel(const float *__restrict__ Zin, int ldzin, const float *__restri
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-            for (int k0 = 0; k0 < K; k0 += AP_KS) {
-                __syncthreads();
-                for (int i = tid; i < 64 * AP_KS; i += AP_THREADS) {
-                    const int r = i / AP_KS, k = i % AP_KS;
-                    Rs[r * (AP_KS + 4) + k] =
-                        (r0 + r < ch.n && k0 + k < K) ? R[(int64_t)ids[r0 + r] * K + k0 + k] : 0.f;
+            __syncthreads();   // both stages free
+            fill(0, r0, 0);
+            int stage = 0;
+            for (int k0 = 0; k0 < K; k0 += AP_KS, stage ^= 1) {
+                if (k0 + AP_KS < K) {
+                    fill(stage ^ 1, r0, k0 + AP_KS);
+                    cp_async_wait<1>();
+                } else {
+                    cp_async_wait<0>();
                 }
                 __syncthreads();
+                const float *Rs = Rs0 + stage * RS;
                 const int cb = c0 + tc * 4;
                 if (cb < DP) {
 #pragma unroll 8
@@ -378,6 +401,7 @@ moe_apply_kernel(const float *__restrict__ Zin, int ldzin, const float *__restri
                         }
                     }
                 }
+                __syncthreads();   // before the stage just read is refilled
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -476,7 +500,7 @@ extern "C" int sym_moe_apply(const float *Zin, int32_t ldzin, const float *R, in
                 "sym_moe_apply: a variable with several levels needs sym_batch_order output");
     if (N == 0) return SYM_OK;
     const int DP = (d + 3) & ~3, KP = (K + 3) & ~3;
-    const size_t smem = ((size_t)KP * DP + 64 * (AP_KS + 4)) * sizeof(float) + MOE_CH * sizeof(int32_t);
+    const size_t smem = ((size_t)KP * DP + 2 * 64 * (AP_KS + 4)) * sizeof(float) + MOE_CH * sizeof(int32_t);
     SYM_REQUIRE(smem <= 200 * 1024, SYM_ERR_UNSUPPORTED_SHAPE, "sym_moe_apply: K=%d d=%d too large", K, d);
     SYM_CUDA(cudaFuncSetAttribute(moe_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t grid = ceil_div(N, MOE_CH) + (perm ? n_levels_v : 0);
