@@ -24,6 +24,13 @@ import tempfile
 import time
 import warnings
 
+# torchrun exports OMP_NUM_THREADS=1 to its workers unless the user set it; rank 0 also times the CPU baseline /
+# reference arm, which is to run on all host cores.  OpenBLAS and libgomp size their pools from the environment
+# when they are loaded, so the variable has to go before numpy is imported.
+if os.environ.get("TORCHELASTIC_RUN_ID") and os.environ.get("OMP_NUM_THREADS") == "1" and \
+        os.environ.get("RANK", "0") == "0":
+    del os.environ["OMP_NUM_THREADS"]
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -149,7 +156,10 @@ def cpu_baseline(w, n_map: int, n_knn: int, seed: int = 0, ref_host=None):
     X, codes, _ = synth.make_query(model, n_map, w["levels"], seed + 100)
     query, ref = synth.to_anndata(model, Zref, comp, C, Nr, X, codes, w["K"], seed=seed)
     key = None if w["levels"] == [1] else [f"batch{v}" for v in range(len(w["levels"]))]
-    with warnings.catch_warnings():
+    # all the host threads this process may use: torchrun exports OMP_NUM_THREADS=1 to its workers, which would
+    # otherwise pin OpenBLAS and sklearn's OpenMP loops to one core
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    with warnings.catch_warnings(), threadpoolctl.threadpool_limits(limits=ncpu):
         warnings.simplefilter("ignore")
         t0 = time.perf_counter()
         so.map_embedding(query, ref, key=key)
@@ -158,9 +168,9 @@ def cpu_baseline(w, n_map: int, n_knn: int, seed: int = 0, ref_host=None):
         t0 = time.perf_counter()
         so.transfer_labels_knn(sub, ref, "cell_type", n_neighbors=w["k"])
         t_knn = time.perf_counter() - t0
+        info = threadpoolctl.threadpool_info()
     n_knn = min(n_knn, n_map)
     per_cell = t_map / n_map + t_knn / n_knn
-    info = threadpoolctl.threadpool_info()
     threads = max([i.get("num_threads", 1) for i in info] + [1])
     return {"value": 1.0 / per_cell, "unit": "cells/s", "cores": int(min(threads, os.cpu_count() or 1)), "kind": "port",
             "sample": f"oracle port (numpy/OpenBLAS + sklearn {__import__('sklearn').__version__} KNeighborsClassifier): "
