@@ -211,6 +211,32 @@ def run_reference(args, w):
 
 
 # ------------------------------------------------------------------------------------------ ours
+def bind_to_gpu_numa_node(local_rank: int):
+    """Multi-rank runs: pin this process (and so its pinned host buffers, which are placed on the allocating
+    thread's node) to the NUMA node its GPU hangs off, so that eight ranks streaming 8 GB each do not all pull
+    through one socket.  Returns (node, previous affinity) or (None, None); never fails the run."""
+    try:
+        import torch
+
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return None, None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        prev = os.sched_getaffinity(0)
+        cpus &= prev
+        if not cpus:
+            return None, None
+        os.sched_setaffinity(0, cpus)
+        return node, prev
+    except Exception:
+        return None, None
+
+
 def main():
     args = parse()
     w = WORKLOADS[args.workload]
@@ -229,6 +255,7 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU path)"
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    numa_node, full_affinity = bind_to_gpu_numa_node(local) if world > 1 else (None, None)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     tl.settings.device = dev
@@ -424,6 +451,8 @@ def main():
 
     cpu = None
     if rank == 0 and not args.no_cpu:
+        if full_affinity is not None:   # the CPU baseline runs on all host cores, not on this GPU's NUMA node only
+            os.sched_setaffinity(0, full_affinity)
         cpu = cpu_baseline(w, args.cpu_n_map, args.cpu_n_knn, ref_host=(Zref, comp, C, Nr))
 
     if rank == 0:
@@ -434,7 +463,7 @@ def main():
             "config": {"workload": w["desc"], "name": args.workload, "cells_per_gpu": N, "ref_cells": M, "genes": G,
                        "pcs": d, "clusters": K, "k": k, "batch_levels": levels,
                        "l2": "inputs larger than L2 (X is %.1f GB per step)" % (N * G * 4 / 1e9),
-                       "knn_method": args.knn_method},
+                       "knn_method": args.knn_method, "numa_node": numa_node},
             "stage_ms": stage_ms, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks,
         }
