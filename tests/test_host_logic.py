@@ -140,3 +140,21 @@ def test_anndata_lite_gene_indexing():
     sub = a[:, pd.Index(["d", "b"])]
     np.testing.assert_array_equal(sub.X, X[:, [3, 1]])
     assert list(sub.var_names) == ["d", "b"] and len(a) == 3
+
+
+def test_decode_labels_matches_plain_numpy_take():
+    """The Arrow dictionary decode used for string labels builds the same column (values and dtype) as assigning
+    sklearn's object array of predictions, and non-string classes take the numpy path."""
+    import pandas as pd
+
+    rng = np.random.default_rng(0)
+    classes = np.array(["B cell", "T cell", "ü-type", ""], dtype=object)
+    lab = rng.integers(0, len(classes), 1000).astype(np.int32)
+    idx = pd.RangeIndex(1000).astype(str)
+    obs = pd.DataFrame(index=idx)
+    obs["fast"] = tl._decode_labels(classes, lab, idx)
+    obs["plain"] = classes[lab]
+    assert obs["fast"].dtype == obs["plain"].dtype
+    assert obs["fast"].equals(obs["plain"])
+    ints = tl._decode_labels(np.array([3, 7, 11]), lab % 3, idx)
+    assert isinstance(ints, np.ndarray) and ints.dtype.kind == "i" and (ints == np.array([3, 7, 11])[lab % 3]).all()
