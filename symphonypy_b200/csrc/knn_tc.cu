@@ -1,27 +1,31 @@
-// tcgen05 candidate scan for the brute-force kNN (method 2)      — symphonypy/tl.py:425-433
+// tcgen05 candidate scan for the brute-force kNN (methods 2 and 3)  — symphonypy/tl.py:425-433
 //
-// The distance GEMM  S[q,r] = ||r||^2 - 2 q.r  runs on the 5th-generation tensor cores with BF16x3
-// split operands (FP32-class accuracy: each float is hi + lo bf16, and hi.hi + hi.lo + lo.hi are
-// summed in the FP32 accumulator), concatenated along K so that ONE chain of tcgen05.mma
-// instructions per tile yields the finished score, ||r||^2 included:
+// The distance GEMM  S[q,r] = ||r||^2 - 2 q.r  runs on the 5th-generation tensor cores, with the norm carried as
+// extra K columns so that ONE chain of tcgen05.mma instructions per tile yields the finished score.  Two operand
+// precisions, both packed once per reference by sym_knn_fit:
 //
+//   method 3, single FP16 (first tier)        K' = d + 2
 //     K' index      query operand (A, M=128 rows)      reference operand (B, N=128 rows)
+//     [0,d)         fp16(-2 s q)                       fp16(s r)         s = power of two, max ||s r|| in (8, 16]
+//     d, d+1        1                                  the two fp16 pieces of ||s r||^2
+//   method 2, BF16x3 (second tier)             K' = 3d + 3   (each float is hi + lo bf16; hi.hi + hi.lo + lo.hi)
 //     [0,d)         hi(-2q)                            hi(r)
 //     [d,2d)        hi(-2q)                            lo(r)
 //     [2d,3d)       lo(-2q)                            hi(r)
 //     3d..3d+2      1                                  the three bf16 pieces of ||r||^2 (exact)
 //
-// Both operands are packed ahead of time (reference once in sym_knn_fit, queries per call) in the
-// canonical K-major no-swizzle UMMA layout, so a tile is one contiguous block moved by a single
-// cp.async.bulk into shared memory, and the accumulator never leaves the SM: four 128x128 FP32
-// accumulators rotate through the 512 TMEM columns.
+// Reference tiles are stored in the canonical K-major no-swizzle UMMA layout, so a tile is one contiguous block
+// moved by a single cp.async.bulk into shared memory; the accumulators (2-4 x 128x128 FP32) never leave tensor
+// memory until the selection warps read them.
 //
-// Warp roles (192 threads):  warp 0 = bulk-copy producer, warp 1 = TMEM owner + MMA issuer,
-// warps 2-5 = selection: thread <-> query row <-> TMEM lane.  A selection thread pulls 32 scores
-// with one tcgen05.ld, folds them with 3-input min (16 FMNMX3) against its row's kc-th best,
-// and only on a hit walks the 32 values and updates the row's top-kc list in shared memory.
-// The scan over-selects (kc = k + 8); the float64 re-rank in knn.cu certifies the margin with the
-// scores recorded here and flags rows that need the FP32 scan.
+// Warp roles (384 threads for two query tiles):  warp 0 = bulk-copy producer; warps 1-2 = MMA issuers, one per
+// query tile (warp 1 owns the TMEM allocation); warps 4-11 = selection, thread <-> query row <-> TMEM lane.  A
+// selection thread pulls the 128 scores of its row with four tcgen05.ld, hands the accumulator back, folds the
+// scores with 3-input min against its row's kc-th best (one straight-line block), and only on a hit locates the
+// candidates and updates the row's 4-ary heap in shared memory.
+// The scan over-selects (kc = k + 8); the float64 re-rank in knn.cu certifies the margin with the scores recorded
+// here (error bound per row: measured FP16 rounding residuals, or 6e-5 relative for BF16x3) and flags the rows
+// that have to be re-run with the next tier.
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
