@@ -226,15 +226,17 @@ __device__ unsigned long long tc_prof[16];
 //   warp 0       : producer (cp.async.bulk of one packed tile per stage)
 //   warps 1..QT  : MMA issuers, one per query tile (warp 1 also owns the TMEM allocation)
 //   warps 4..    : selection; warp w serves query tile (w-4)/4, TMEM lane quadrant w%4, thread <-> query row
-// TMEM: accumulator (query tile q, buffer b) lives at columns (q*TC_ACC + b)*128.
+// TMEM: the accumulators occupy the last nbuf*128 columns; in front of them the query operands when they live in
+// tensor memory (TS form).  With the query operand in shared memory (SS form) there are four accumulators, two
+// per query tile; otherwise 2-3, rotated through both query tiles in global issue order.
 //
-// Selection, per 32-column chunk: tcgen05.ld (issued one chunk ahead), four independent 3-input-min
-// chains over groups of 8, one compare against the row's kc-th best.  Only groups in which some lane
-// of the warp has a hit are walked, and a hit calls the (single, out-of-line) list update.
+// Selection per tile: four tcgen05.ld (128 scores per row), the accumulator handed back, 16 independent
+// 3-input-min chains over groups of 8, one compare against the row's kc-th best; only on a hit are the groups
+// examined and the (single, out-of-line) heap update called.
 
-// The row's kc best candidates form a binary MAX-HEAP of 64-bit keys (order-preserving score bits | position)
-// in shared memory; the root is the kc-th best = the row's threshold.  A hit replaces the root and sifts down:
-// ~log2(kc) levels of two 8-byte loads, a compare and one 8-byte store, instead of a pass over the list.
+// The row's kc best candidates form a 4-ary MAX-HEAP of 64-bit keys (score bits | position) in shared memory;
+// the root is the kc-th best = the row's threshold.  A hit replaces the root and sifts down: ~log4(kc) levels of
+// four independent 8-byte loads, three compares and one 8-byte store, instead of a pass over the list.
 // Every lane works on ITS OWN row (lanes run in lock-step when several rows hit at once); the row stride `ks`
 // is odd, so equal heap levels of the 32 rows of a warp fall into different banks.  Returns the new threshold.
 // (A warp-cooperative variant — one row at a time, REDUX for the maximum — was measured 2x slower end to end:
