@@ -58,6 +58,11 @@ __device__ __forceinline__ unsigned short bf16_rn(float x) {
 __device__ __forceinline__ float bf16_to_f(unsigned short h) { return __uint_as_float((unsigned)h << 16); }
 __device__ __forceinline__ unsigned short f16_rn(float x) { return __half_as_ushort(__float2half_rn(x)); }
 __device__ __forceinline__ float f16_to_f(unsigned short h) { return __half2float(__ushort_as_half(h)); }
+// |v - fp16(v)| as the error bound of the re-rank counts it.  Values below the smallest normal fp16 are charged in
+// full: the bound then holds whether or not the tensor core honours fp16 subnormal inputs (nothing here depends on it).
+__device__ __forceinline__ float tc_f16_residual(float v, unsigned short h) {
+    return fabsf(v) < 6.103515625e-5f ? v : v - f16_to_f(h);
+}
 
 // One thread = one row x one k-unit (8 consecutive K' indices, 16 bytes).
 // Element (r, kk) of a tile lives at  (kk/8)*2048 + (r/8)*128 + (r%8)*16 + (kk%8)*2  bytes.
@@ -82,7 +87,8 @@ tc_pack_kernel(const float *__restrict__ src, int ld, int64_t rows, int64_t rows
     if (prec && hdr && real && !is_query && j == 0) {   // exact rounding residual of this row, max over rows -> header
         float res = 0.f;
         for (int c = 0; c < d; ++c) {
-            const float v = x[c] * sc, dl = v - f16_to_f(f16_rn(v));
+            const float v = x[c] * sc;
+            const float dl = tc_f16_residual(v, f16_rn(v));
             res = fmaf(dl, dl, res);
         }
         atomicMax(reinterpret_cast<int *>(&hdr->dr16), __float_as_int(sqrtf(res) * 1.0000002f));
@@ -162,7 +168,7 @@ tc_pack_rows_kernel(const float *__restrict__ src, int ld, int64_t rows, int64_t
                 if (real && kk < d) {
                     const float val = -2.f * x[kk] * sc;
                     v = f16_rn(val);
-                    const float dl = val - f16_to_f(v);   // inf / NaN on overflow: the row then fails its certificate
+                    const float dl = tc_f16_residual(val, v);   // inf / NaN on overflow: the row then fails its certificate
                     res = fmaf(dl, dl, res);
                 } else if (real && kk < d + 2) {
                     v = 0x3c00;

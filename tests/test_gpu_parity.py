@@ -433,7 +433,7 @@ def test_tc_score_tile_fp16(cuda_device, built_library):
         want = (r64 ** 2).sum(1)[None, :] - 2.0 * q64 @ r64.T
         Qp = -2.0 * q64
         dQ = np.linalg.norm(Qp - Qp.astype(np.float16).astype(np.float64), axis=1)
-        dR = np.linalg.norm(r64 - r64.astype(np.float16).astype(np.float64), axis=1)
+        dR = np.linalg.norm(r64 - r64.astype(np.float16).astype(np.float64), axis=1)   # (no subnormal-range values here)
         nQ, nR = np.linalg.norm(Qp, axis=1), np.linalg.norm(r64, axis=1)
         bound = nQ[:, None] * dR[None, :] + dQ[:, None] * (nR + dR)[None, :] + 1e-5 * (nQ[:, None] * nR[None, :] + nR[None, :] ** 2)
         err = np.abs(got - want)
