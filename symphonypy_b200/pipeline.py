@@ -11,14 +11,16 @@ import torch
 from . import _dist, engine
 
 
-def soft_assign_and_correct(Z, Y, inv_sigma, codes, n_levels, lam, Nr, C, mark=None):
+def soft_assign_and_correct(Z, Y, inv_sigma, codes, n_levels, lam, Nr, C, mark=None, R=None):
     """Z [N,d] f32 (device) -> (R [N,K], Zcorr [N,d]).   `symphonypy/tl.py:358-397`.
 
     codes [V,N] int32 level codes, n_levels per variable, lam [B+1] f64 ridge diagonal,
     Nr [K] / C [K,d] f64 reference priors (device).  Raises LinAlgError when a ridge system is singular.
+    `R`: soft assignments already computed by the caller (streamed per chunk behind the projection), else None.
     """
     mark = mark or (lambda name: None)
-    R = engine.assign(Z, Y, inv_sigma)
+    if R is None:
+        R = engine.assign(Z, Y, inv_sigma)
     mark("assign")
     orders = [engine.batch_order(codes[v], n_levels[v]) for v in range(len(n_levels))]
     gram, cross = engine.moe_stats(Z, R, codes, n_levels, orders)

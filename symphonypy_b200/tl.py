@@ -104,8 +104,9 @@ def _pinned_stage(nbytes: int, slot: int) -> torch.Tensor:
     return buf
 
 
-def _project_host_dense(Xh: torch.Tensor, ld: engine.Loadings, gene_col, Z: torch.Tensor) -> None:
-    """Stream a host matrix through the GPU: H2D of chunk i+1 overlaps the projection of chunk i."""
+def _project_host_dense(Xh: torch.Tensor, ld: engine.Loadings, gene_col, Z: torch.Tensor, after_chunk=None) -> None:
+    """Stream a host matrix through the GPU: H2D of chunk i+1 overlaps the projection of chunk i.
+    `after_chunk(Z, s, e)` runs on the compute stream right after rows [s, e) have been projected."""
     dev = Z.device
     N, C = Xh.shape
     if N == 0:
@@ -139,11 +140,14 @@ def _project_host_dense(Xh: torch.Tensor, ld: engine.Loadings, gene_col, Z: torc
         if xb.dtype != torch.float32:
             xb = xb.float()
         engine.project_dense(xb, ld, gene_col, out=Z[s:e])
+        if after_chunk is not None:
+            after_chunk(Z, s, e)
         free[b].record(compute)
 
 
-def _project(adata_query, adata_ref, loadings_key, use_genes_column, dev) -> torch.Tensor:
-    """`_map_query_to_ref` (`_utils.py:248-308`): returns Z [N, d] on the device."""
+def _project(adata_query, adata_ref, loadings_key, use_genes_column, dev, after_chunk=None) -> torch.Tensor:
+    """`_map_query_to_ref` (`_utils.py:248-308`): returns Z [N, d] on the device.  `after_chunk(Z, s, e)` is called
+    on the compute stream whenever rows [s, e) of Z are final (once per H2D chunk for a host matrix)."""
     assert "mean" in adata_ref.var, "Gene expression means are expected to be saved in adata_ref.var"
     assert "std" in adata_ref.var, "Gene expression stds are expected to be saved in adata_ref.var"
     if use_genes_column is None:
@@ -188,6 +192,8 @@ def _project(adata_query, adata_ref, loadings_key, use_genes_column, dev) -> tor
         indices = torch.from_numpy(np.ascontiguousarray(Xc.indices)).to(dev, non_blocking=True).int()
         indptr = torch.from_numpy(np.ascontiguousarray(Xc.indptr)).to(dev, non_blocking=True).long()
         engine.project_csr(data, indices, indptr, N, torch.from_numpy(col_gene).to(dev), ld, out=Z)
+        if after_chunk is not None and N > 0:
+            after_chunk(Z, 0, N)
         return Z
 
     gene_col = None if identity else torch.from_numpy(q_idx.astype(np.int32)).to(dev)
@@ -195,6 +201,8 @@ def _project(adata_query, adata_ref, loadings_key, use_genes_column, dev) -> tor
         if X.is_cuda:
             xd = X if (X.dtype == torch.float32 and X.stride(1) == 1) else X.float().contiguous()
             engine.project_dense(xd, ld, gene_col, out=Z)
+            if after_chunk is not None and N > 0:
+                after_chunk(Z, 0, N)
             return Z
         Xh = X if X.is_contiguous() else X.contiguous()
     else:
@@ -207,7 +215,7 @@ def _project(adata_query, adata_ref, loadings_key, use_genes_column, dev) -> tor
                 Xh = torch.from_numpy(Xn)
         else:
             Xh = torch.from_numpy(Xn)
-    _project_host_dense(Xh, ld, gene_col, Z)
+    _project_host_dense(Xh, ld, gene_col, Z, after_chunk)
     return Z
 
 
@@ -260,6 +268,20 @@ def _to_host_async(t: torch.Tensor) -> np.ndarray:
     arr = host.numpy()
     weakref.finalize(arr, _POOL.give, buf)
     return arr
+
+
+def _pinned_result(shape, dtype=torch.float32):
+    """(pinned host tensor, numpy view of it) for a result that is filled by asynchronous D2H copies; the buffer
+    returns to the pool when the numpy array is garbage collected.  (None, empty array) for empty results."""
+    n = int(np.prod(shape))
+    if n == 0:
+        return None, np.empty(tuple(shape), dtype=np.float32 if dtype == torch.float32 else np.int32)
+    nbytes = n * torch.empty((), dtype=dtype).element_size()
+    buf = _POOL.take(nbytes)
+    host = buf[:nbytes].view(dtype).view(tuple(shape))
+    arr = host.numpy()
+    weakref.finalize(arr, _POOL.give, buf)
+    return host, arr
 
 
 def _to_host(t: torch.Tensor) -> np.ndarray:
@@ -348,16 +370,34 @@ def map_embedding(
     ref_basis_loadings = harmony_ref["ref_basis_loadings"]  # `tl.py:347` overrides the keyword
 
     with torch.cuda.device(dev):
-        # 1. project
-        Z = _project(adata_query, adata_ref, ref_basis_loadings, use_genes_column, dev)
-        N, d = Z.shape
-
-        # 2. soft assignment against the reference centroids
+        # soft-assignment operands first: the assignment of a chunk of cells runs right behind its projection
         Kc = int(harmony_ref["K"])
         Cn = np.asarray(harmony_ref["C"], dtype=np.float64)
         Y = Cn / np.linalg.norm(Cn, ord=2, axis=1, keepdims=True)  # `tl.py:361-362`
         inv_sig = _inv_sigma(sigma, Kc, dev)
         Yd = torch.from_numpy(np.ascontiguousarray(Y, dtype=np.float32)).to(dev)
+        N = int(adata_query.X.shape[0])
+        R = torch.empty((N, Kc), device=dev, dtype=torch.float32)
+        z_host, z_h = _pinned_result((N, Cn.shape[1]))
+        r_host, r_h = _pinned_result((N, Kc)) if settings.store_R else (None, None)
+        d2h = torch.cuda.Stream(dev)
+
+        def after_chunk(Zd, s, e):
+            # 2. soft assignment of rows [s, e) against the reference centroids (per cell: needs nothing global),
+            # then Z and R of these rows go back to the host while the next chunk of X is still coming in
+            # (PCIe is full duplex: ~0.5 GB of results hidden behind the 8 GB of input at the BASELINE shape)
+            engine.assign(Zd[s:e], Yd, inv_sig, out=R[s:e])
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            d2h.wait_event(ev)
+            with torch.cuda.stream(d2h):
+                z_host[s:e].copy_(Zd[s:e], non_blocking=True)
+                if r_host is not None:
+                    r_host[s:e].copy_(R[s:e], non_blocking=True)
+
+        # 1. project
+        Z = _project(adata_query, adata_ref, ref_basis_loadings, use_genes_column, dev, after_chunk)
+        d = Z.shape[1]
         assert Yd.shape == (Kc, d), "harmony C must be [K, n_components]"
 
         # 3. mixture-of-experts correction
@@ -368,13 +408,13 @@ def map_embedding(
         Nr = torch.from_numpy(np.ascontiguousarray(harmony_ref["Nr"], dtype=np.float64)).to(dev)
         Cd = torch.from_numpy(np.ascontiguousarray(Cn)).to(dev)
         R, Zc, info = pipeline.soft_assign_and_correct(Z, Yd, inv_sig, codes, n_levels, torch.from_numpy(lam).to(dev),
-                                                       Nr, Cd)
+                                                       Nr, Cd, R=R)
         pipeline.check_solve(info)
 
         # 4. results back into the AnnData, as the reference does (`tl.py:394-397`, `_utils.py:306`)
-        z_h, zc_h = _to_host_async(Z), _to_host_async(Zc)
-        r_h = _to_host_async(R) if settings.store_R else None
+        zc_h = _to_host_async(Zc)
         torch.cuda.current_stream(dev).synchronize()
+        d2h.synchronize()
         adata_query.obsm[transferred_primary_basis] = z_h
         adata_query.obsm[transferred_adjusted_basis] = zc_h
         _remember(z_h, Z)
@@ -382,7 +422,6 @@ def map_embedding(
         if r_h is not None:
             adata_query.obsm[f"{transferred_adjusted_basis}_symphony_R"] = r_h
             _remember(r_h, R)
-
 
 # ----------------------------------------------------------------------------- per-cell confidence
 def per_cell_confidence(
