@@ -158,3 +158,62 @@ def test_decode_labels_matches_plain_numpy_take():
     assert obs["fast"].equals(obs["plain"])
     ints = tl._decode_labels(np.array([3, 7, 11]), lab % 3, idx)
     assert isinstance(ints, np.ndarray) and ints.dtype.kind == "i" and (ints == np.array([3, 7, 11])[lab % 3]).all()
+
+
+def test_knn_tier_logic_with_a_fake_scan(monkeypatch):
+    """`engine.knn_search_certified` on CPU tensors with the scan replaced by a stub: uncertified rows go
+    FP16 -> BF16x3 -> FP32, only the flagged rows are re-run, and an index that fails the FP16 certificate too
+    often starts with BF16x3 from then on."""
+    import torch
+
+    from symphonypy_b200 import engine
+
+    class FakeLib:
+        def sym_knn_method_supported(self, n, M, d, k, m):
+            return 1
+
+    monkeypatch.setattr(engine._lib, "load", lambda: FakeLib())
+    calls = []
+
+    def fake_search(index, Q, k, method=engine.KNN_AUTO, want_unsafe=True, events=None):
+        n = Q.shape[0]
+        calls.append((method, n))
+        tag = Q[:, 0].long()                      # row identity travels in column 0
+        idx = (tag[:, None] * 10 + method).int().repeat(1, k)
+        dist2 = torch.zeros((n, k))
+        # FP16 fails the rows whose tag is a multiple of `index.fail16`, BF16x3 those that are multiples of 50
+        if method == engine.KNN_TC16:
+            unsafe = (tag % index.fail16 == 0).to(torch.uint8)
+        elif method == engine.KNN_TC:
+            unsafe = (tag % 50 == 0).to(torch.uint8)
+        else:
+            unsafe = torch.zeros(n, dtype=torch.uint8)
+        return idx, dist2, unsafe
+
+    monkeypatch.setattr(engine, "knn_search", fake_search)
+    N, k = 5000, 3
+    Q = torch.arange(N, dtype=torch.float32)[:, None].repeat(1, 4)
+    index = engine.KnnIndex(ref=torch.zeros((10, 4)), packed=torch.zeros(1, dtype=torch.uint8), M=10, d=4)
+
+    index.fail16 = 25                             # 4 % of the rows fail the FP16 certificate: FP16 stays first
+    idx, dist2, n_rep = engine.knn_search_certified(index, Q, k)
+    assert calls == [(engine.KNN_TC16, N), (engine.KNN_TC, 200), (engine.KNN_FFMA, 100)]
+    assert n_rep == 200 and k not in index.first_tier
+    tier = idx[:, 0] % 10
+    rows = torch.arange(N)
+    assert (tier[rows % 25 != 0] == engine.KNN_TC16).all()
+    assert (tier[(rows % 25 == 0) & (rows % 50 != 0)] == engine.KNN_TC).all()
+    assert (tier[rows % 50 == 0] == engine.KNN_FFMA).all()
+    assert (idx[:, 0] // 10 == rows).all()        # every row got its own result back
+
+    calls.clear()
+    index.fail16 = 5                              # 20 % fail: the index remembers and starts with BF16x3 next time
+    engine.knn_search_certified(index, Q, k)
+    assert calls[0] == (engine.KNN_TC16, N) and index.first_tier[k] == engine.KNN_TC
+    calls.clear()
+    engine.knn_search_certified(index, Q, k)
+    assert calls == [(engine.KNN_TC, N), (engine.KNN_FFMA, 100)]
+
+    calls.clear()                                 # an explicit method is never adapted
+    engine.knn_search_certified(index, Q, k, engine.KNN_TC16)
+    assert calls[0] == (engine.KNN_TC16, N)
