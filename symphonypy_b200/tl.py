@@ -460,6 +460,23 @@ def per_cell_confidence(
 
 
 # ----------------------------------------------------------------------------- per-cluster confidence
+def _cluster_maha_dists(size, mean, scatter, centroids, centroids_norm, u, lamb) -> np.ndarray:
+    """`_cluster_maha_dist` (`symphonypy/_utils.py:436-463`) for all clusters at once, from their sizes [G],
+    centroids [G, d] and centred scatter matrices sum (x-mean)(x-mean)^T [G, d, d]: Mahalanobis distance to the
+    reference centroid with the largest cosine, NaN for clusters with fewer than u*d cells."""
+    G, d = mean.shape
+    dist = np.full(G, np.nan)
+    for g in range(G):
+        if size[g] < u * d:
+            logger.info("cluster contains too few cells to estimate confidence: ', query_cluster_labels_unique[c])")
+            continue
+        cov = scatter[g] / (size[g] - 1) + np.diag([lamb] * d)
+        closest = centroids[np.argmax(centroids_norm @ mean[g])]
+        dif = closest - mean[g]
+        dist[g] = float((dif @ np.linalg.inv(cov) @ dif) ** 0.5)
+    return dist
+
+
 def per_cluster_confidence(
     adata_query,
     adata_ref,
@@ -505,15 +522,7 @@ def per_cluster_confidence(
         mean_h = mean[:G].cpu().numpy()
         scatter_h = scatter[:G].cpu().numpy()
 
-    dist = np.full(G, np.nan)
-    for g in range(G):
-        if size_h[g] < u * d:
-            logger.info("cluster contains too few cells to estimate confidence: ', query_cluster_labels_unique[c])")
-            continue
-        cov = scatter_h[g] / (size_h[g] - 1) + np.diag([lamb] * d)
-        closest = centroids[np.argmax(centroids_norm @ mean_h[g])]
-        dif = closest - mean_h[g]
-        dist[g] = float((dif @ np.linalg.inv(cov) @ dif) ** 0.5)
+    dist = _cluster_maha_dists(size_h, mean_h, scatter_h, centroids, centroids_norm, u, lamb)
 
     if uns is not None:
         adata_query.uns[uns] = {"key": cluster_key, "dist": dist, "cluster_labels": labels.to_numpy()}

@@ -217,3 +217,24 @@ def test_knn_tier_logic_with_a_fake_scan(monkeypatch):
     calls.clear()                                 # an explicit method is never adapted
     engine.knn_search_certified(index, Q, k, engine.KNN_TC16)
     assert calls[0] == (engine.KNN_TC16, N)
+
+
+def test_cluster_maha_dists_matches_oracle():
+    """Host half of `per_cluster_confidence`: from exact per-cluster moments it reproduces the oracle's
+    (= the reference's) distances, NaN for clusters below u*d cells included."""
+    from oracle import symphony_oracle as so
+
+    rng = np.random.default_rng(3)
+    d, K = 6, 9
+    cent = rng.normal(size=(K, d)) * 5
+    cent_norm = cent / np.linalg.norm(cent, axis=1, keepdims=True)
+    groups = [rng.normal(size=(n, d)) @ rng.normal(size=(d, d)) + rng.normal(size=d) * 3 for n in (40, 13, 5, 200)]
+    size = np.array([g.shape[0] for g in groups])
+    mean = np.stack([g.mean(0) for g in groups])
+    scatter = np.stack([(g - g.mean(0)).T @ (g - g.mean(0)) for g in groups])
+    for u, lamb in ((2, 0.0), (1, 0.3)):
+        got = tl._cluster_maha_dists(size, mean, scatter, cent, cent_norm, u, lamb)
+        want = [so.cluster_maha_dist(g, cent, cent_norm, u, lamb) for g in groups]
+        want = np.array([np.nan if w is None else w for w in want])
+        np.testing.assert_allclose(got, want, rtol=1e-10, equal_nan=True)
+        assert np.isnan(got).sum() == (size < u * d).sum()
