@@ -238,3 +238,39 @@ def test_cluster_maha_dists_matches_oracle():
         want = np.array([np.nan if w is None else w for w in want])
         np.testing.assert_allclose(got, want, rtol=1e-10, equal_nan=True)
         assert np.isnan(got).sum() == (size < u * d).sum()
+
+
+def test_public_header_is_plain_c(tmp_path):
+    """`include/symphony_b200.h` is the drop-in boundary: it has to compile as C99 and as C++ with nothing but
+    the standard headers (no torch, no CUDA types), and a C program has to link against the built library."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "symphony_b200.h"\n'
+                   'int main(void) { return sym_version() > 0 && sym_compiled_arch() == 100 ? 0 : 1; }\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-fsyntax-only", str(src)],
+                   check=True)
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-I", inc, "-fsyntax-only", "-x", "c++", str(src)],
+                   check=True)
+
+
+def test_c_program_links_and_calls_the_library(tmp_path, built_library):
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "link.c"
+    src.write_text('#include <stdio.h>\n#include "symphony_b200.h"\n'
+                   'int main(void) { printf("%d %d\\n", sym_version(), sym_compiled_arch()); '
+                   'return sym_knn_method_supported(1000, 5000, 30, 10, 3) == 1 ? 0 : 2; }\n')
+    exe = tmp_path / "link"
+    libdir = os.path.dirname(built_library)
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", libdir,
+                    "-lsymphony_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert int(out[0]) > 0 and int(out[1]) == 100   # host-only entry points: no GPU needed
