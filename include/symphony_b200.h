@@ -216,6 +216,15 @@ int sym_group_cov(const float *X, int32_t ldx, int64_t N, int32_t d, int32_t G, 
                   const int64_t *seg, const int32_t *chunk_start, const float *mean, double *cov,
                   sym_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * (7) test hook (no reference counterpart): the FP32 scores S[q,r] = ||r||^2 - 2 q.r of ONE 128 x 128 tile as the
+ *     tcgen05 scan computes them — same packing, descriptors and MMA chain — so that tests/test_gpu_parity.py can
+ *     compare the tensor-core arithmetic with float64.  Q [nq<=128, d], Ref [nr<=128, d] -> out [128,128];
+ *     scratch >= 3 packed tiles.  flags bit 0: query operand in tensor memory; bit 1: single-FP16 operands.
+ */
+int sym_debug_tc_scores(const float *Q, int32_t nq, const float *Ref, int32_t nr, int32_t d, float *out, void *scratch,
+                        sym_stream_t stream, int32_t flags);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,13 @@ def allreduce_stats(gram: torch.Tensor, cross: torch.Tensor) -> None:
     cross.copy_(flat[:, B1 * B1:].reshape(cross.shape))
 
 
+def broadcast(t: torch.Tensor, src: int = 0) -> torch.Tensor:
+    """`t` as rank `src` holds it, on every rank (in place; no-op outside a process group)."""
+    if active():
+        dist.broadcast(t, src=src)
+    return t
+
+
 def union_levels(local_levels: list[list[str]]) -> list[list[str]]:
     """Sorted union, per batch variable, of the level names seen on every rank."""
     if not active():

@@ -10,7 +10,8 @@ import os
 from ctypes import c_char_p, c_float, c_int32, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_C", "libsymphony_b200.so")
+# SYM_B200_LIB: experiments only (an instrumented / tuning build made by `python -m symphonypy_b200.build --variant`)
+LIB_PATH = os.environ.get("SYM_B200_LIB") or os.path.join(_HERE, "_C", "libsymphony_b200.so")
 
 # symbol -> (restype, argtypes); mirrors include/symphony_b200.h line by line
 _P = c_void_p
@@ -48,6 +49,7 @@ SIGNATURES = {
     "sym_cell_confidence": (c_int32, [_P, c_int32, c_int64, c_int32, _P, c_int32, _P, _P, _P, _P]),
     "sym_group_sums": (c_int32, [_P, c_int32, c_int64, c_int32, c_int32, _P, _P, _P, _P, _P]),
     "sym_group_cov": (c_int32, [_P, c_int32, c_int64, c_int32, c_int32, _P, _P, _P, _P, _P, _P]),
+    "sym_debug_tc_scores": (c_int32, [_P, c_int32, _P, c_int32, c_int32, _P, _P, _P, c_int32]),
 }
 
 _lib = None

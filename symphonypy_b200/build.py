@@ -34,18 +34,24 @@ def _digest() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, variant: str = "", extra: list[str] | None = None) -> str:
+    """Builds the product library; with `variant` (experiments only: instrumented or tuning builds that
+    `SYM_B200_LIB` points `_lib.load()` at) a second library `libsymphony_b200_<variant>.so` with `extra` nvcc flags."""
     os.makedirs(OUT_DIR, exist_ok=True)
-    stamp = os.path.join(OUT_DIR, "build.stamp")
-    dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
-        return LIB
+    lib = LIB if not variant else LIB.replace(".so", f"_{variant}.so")
+    flags = FLAGS + list(extra or [])
+    stamp = os.path.join(OUT_DIR, f"build{'_' + variant if variant else ''}.stamp")
+    dig = _digest() + hashlib.sha256(" ".join(flags).encode()).hexdigest()
+    if not force and os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read() == dig:
+        return lib
+    obj_dir = OUT_DIR if not variant else os.path.join(OUT_DIR, variant)
+    os.makedirs(obj_dir, exist_ok=True)
 
     def compile_one(src):
-        obj = os.path.join(OUT_DIR, src.replace(".cu", ".o"))
-        cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
+        cmd = [NVCC, *flags, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
-        with open(os.path.join(OUT_DIR, src + ".ptxas.log"), "w") as f:
+        with open(os.path.join(obj_dir, src + ".ptxas.log"), "w") as f:
             f.write(r.stderr)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{r.stderr[-4000:]}")
@@ -55,13 +61,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    r = subprocess.run([NVCC, "-shared", "-o", LIB, *objs, "-lcudart"], capture_output=True, text=True)
+    r = subprocess.run([NVCC, "-shared", "-o", lib, *objs, "-lcudart"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stderr[-4000:]}")
     with open(stamp, "w") as f:
         f.write(dig)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    # python -m symphonypy_b200.build [--force] [-v] [--variant NAME -DFLAG ...]
+    argv = sys.argv[1:]
+    var = argv[argv.index("--variant") + 1] if "--variant" in argv else ""
+    print(build(force="--force" in argv, verbose="-v" in argv, variant=var, extra=[a for a in argv if a.startswith("-D")]))

@@ -285,30 +285,41 @@ knn_scan_ffma_kernel(const float *__restrict__ Q, int ldq, int64_t N, const int3
 }
 
 // ------------------------------------------------------------------------------------------ rerank
-// One warp per query row.  Exact float64 distances of the candidates, top-k by (dist, index).
+// One warp per query row.  The scan hands over `ncand` candidates per row; a candidate is a GROUP of `gsz`
+// consecutive positions of the packed reference, keyed by the smallest scan score in the group (gsz = 8 for the
+// tcgen05 scans, which select groups; gsz = 1 for the FP32 scan).  Every member gets its exact float64 distance
+// (sklearn's formula); members whose exact score lies below the row's threshold (plus the error margin) are
+// ranked by (distance, index); the certificate is checked.
+//   gsz = 8: the 8 members of a group sit next to each other in refT[c][pos .. pos+7] — eight lanes read one
+//            32-byte sector per dimension;  gsz = 1: the member's row Ref[order[pos]] is read.
 constexpr int RR_THREADS = 256;
-constexpr int RR_MAXC = 512;  // candidates per row the shared scratch can hold
+constexpr int RR_MAXC = 512;   // candidates per row the scan may hand over, and members per row that can be ranked
+constexpr int RR_DMAX = 128;
+constexpr size_t RR_SMEM = (size_t)(RR_THREADS / 32) * (RR_MAXC * (sizeof(double) + sizeof(int32_t)) + RR_DMAX * sizeof(float));
 
 __global__ void __launch_bounds__(RR_THREADS)
-knn_rerank_kernel(const float *__restrict__ Q, int ldq, int64_t N, const float *__restrict__ Ref, int ldr, int64_t M,
-                  int d, int k, const unsigned long long *__restrict__ cand, const float *__restrict__ thr, int ncand, int nsplit,
-                  double eps_rel, const KnnHeader *__restrict__ hdr, const int32_t *__restrict__ order,
+knn_rerank_kernel(const float *__restrict__ Q, int ldq, int64_t N, const float *__restrict__ Ref, int ldr,
+                  const float *__restrict__ refT, int64_t Mpad, int64_t M, int d, int k,
+                  const unsigned long long *__restrict__ cand, const float *__restrict__ thr, int ncand, int nsplit,
+                  int gsz, double eps_rel, const KnnHeader *__restrict__ hdr, const int32_t *__restrict__ order,
                   const int32_t *__restrict__ q_perm, const float *__restrict__ dq16, int32_t *__restrict__ idx_out,
                   float *__restrict__ dist_out, uint8_t *__restrict__ unsafe) {
-    __shared__ double sd[RR_THREADS / 32][RR_MAXC];
-    __shared__ int32_t si[RR_THREADS / 32][RR_MAXC];
+    extern __shared__ __align__(16) unsigned char rr_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *wd = reinterpret_cast<double *>(rr_smem) + (size_t)warp * RR_MAXC;
+    int32_t *wi = reinterpret_cast<int32_t *>(rr_smem + (size_t)(RR_THREADS / 32) * RR_MAXC * sizeof(double)) + (size_t)warp * RR_MAXC;
+    float *wq = reinterpret_cast<float *>(rr_smem + (size_t)(RR_THREADS / 32) * RR_MAXC * (sizeof(double) + sizeof(int32_t))) + (size_t)warp * RR_DMAX;
     const int64_t row = (int64_t)blockIdx.x * (RR_THREADS / 32) + warp;  // row of the scan (locality order)
     if (row >= N) return;
     const int64_t n = q_perm ? q_perm[row] : row;                        // the query it stands for
     const float *q = Q + n * ldq;
+    for (int c = lane; c < d; c += 32) wq[c] = q[c];
+    __syncwarp();
     double qn = 0.0;
     for (int c = 0; c < d; ++c) {
-        const double v = (double)q[c];
+        const double v = (double)wq[c];
         qn = fma(v, v, qn);
     }
-    double *wd = sd[warp];
-    int32_t *wi = si[warp];
     const double rmax2 = (double)hdr->rmax2;
     double eps = eps_rel * (2.0 * sqrt(qn) * sqrt(rmax2) + rmax2);
     double unscale = 1.0;   // scan scores and thresholds are in units of scale16^2 when the operands were single FP16
@@ -321,66 +332,95 @@ knn_rerank_kernel(const float *__restrict__ Q, int ldq, int64_t N, const float *
         unscale = 1.0 / (s * s);
         eps += (qs * dr + dq * (rs + dr)) * unscale;
     }
-    int bad = 0;  // a recorded scan score further than eps from the exact score voids the certificate
-    int nvalid = 0;
-    for (int e = lane; e < k; e += 32) {  // slots that no candidate claims (fewer than k valid candidates) stay empty
+    double tmin = INFINITY;   // the row's threshold: every reference outside the candidates has scan score >= tmin
+    for (int s = 0; s < nsplit; ++s) tmin = fmin(tmin, (double)thr[row * nsplit + s]);
+    tmin *= unscale;
+    for (int e = lane; e < k; e += 32) {  // slots that no member claims (fewer than k ranked members) stay empty
         idx_out[n * k + e] = -1;
         dist_out[n * k + e] = INFINITY;
     }
-    __syncwarp();
-    for (int e = lane; e < ncand; e += 32) {
-        const unsigned long long key = cand[row * ncand + e];
-        const uint32_t pos = (uint32_t)(key & 0xffffffffull);   // position in the packed reference
-        double dist = INFINITY;
-        const bool valid = key != ~0ull && (int64_t)pos < M;
-        const uint32_t id = valid ? (uint32_t)order[pos] : 0u;  // original reference row
+    int bad = 0;      // a recorded scan score further than eps from the exact score voids the certificate
+    int nsurv = 0;    // members kept for ranking (warp-uniform)
+    const int total = ncand * gsz;
+    const int gshift = gsz == 8 ? 3 : 0;
+    for (int base = 0; base < total; base += 32) {
+        const int e = base + lane;
+        const bool in_range = e < total;
+        const unsigned long long key = in_range ? cand[row * ncand + (e >> gshift)] : ~0ull;
+        const bool gvalid = key != ~0ull;
+        const int64_t pos = (int64_t)(uint32_t)(key & 0xffffffffull) + (e & (gsz - 1));   // position in the packed reference
+        const bool valid = gvalid && pos < M;
+        double s_exact = INFINITY;
+        int32_t id = 0x7fffffff;
         if (valid) {
-            const float *r = Ref + (int64_t)id * ldr;
+            id = order[pos];   // original reference row
             double rn = 0.0, dot = 0.0;
-            for (int c = 0; c < d; ++c) {
-                const double rv = (double)r[c];
-                rn = fma(rv, rv, rn);
-                dot = fma((double)q[c], rv, dot);
+            if (gsz == 8) {
+                const float *r = refT + pos;
+                for (int c = 0; c < d; ++c) {
+                    const double rv = (double)r[(int64_t)c * Mpad];
+                    rn = fma(rv, rv, rn);
+                    dot = fma((double)wq[c], rv, dot);
+                }
+            } else {
+                const float *r = Ref + (int64_t)id * ldr;
+                for (int c = 0; c < d; ++c) {
+                    const double rv = (double)r[c];
+                    rn = fma(rv, rv, rn);
+                    dot = fma((double)wq[c], rv, dot);
+                }
             }
-            const double s_exact = rn - 2.0 * dot;
-            bad |= !(fabs((double)knn_key_score(key) * unscale - s_exact) <= eps);
-            dist = fmax(qn + s_exact, 0.0);  // sklearn: ||x||^2 - 2 x.y + ||y||^2, clamped at 0
+            s_exact = rn - 2.0 * dot;
         }
-        nvalid += valid;
-        wd[e] = dist;
-        wi[e] = valid ? (int32_t)id : 0x7fffffff;
+        // the recorded score is the minimum over the group: compare it with the exact minimum over the members
+        double gmin = s_exact;
+        if (gsz == 8) {
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) gmin = fmin(gmin, __shfl_xor_sync(0xffffffffu, gmin, o));
+        }
+        if (gvalid && (e & (gsz - 1)) == 0 && gmin != INFINITY)
+            bad |= !(fabs((double)knn_key_score(key) * unscale - gmin) <= eps);
+        // members that can still be among the k nearest IF the row certifies: exact score below the threshold
+        // (with the error margin, so that exact ties at the threshold stay in).  The FP32 scan's candidates are
+        // single references and all of them are ranked (it is the last tier: its answer stands).
+        const bool keep = valid && (gsz == 1 || s_exact <= tmin + 2.0 * eps);
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        const int off = nsurv + __popc(m & ((1u << lane) - 1u));
+        if (keep && off < RR_MAXC) {
+            wd[off] = fmax(qn + s_exact, 0.0);  // sklearn: ||x||^2 - 2 x.y + ||y||^2, clamped at 0
+            wi[off] = id;
+        }
+        nsurv += __popc(m);
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if (nsurv > RR_MAXC) {   // cannot rank them all: rank what fits, flag the row
+        nsurv = RR_MAXC;
+        bad = 1;
     }
     __syncwarp();
     double kth = 0.0;
-    for (int e = lane; e < ncand; e += 32) {
+    for (int e = lane; e < nsurv; e += 32) {
         const double de = wd[e];
         const int32_t ie = wi[e];
         int rank = 0;
-        for (int f = 0; f < ncand; ++f) {
+        for (int f = 0; f < nsurv; ++f) {
             const double df = wd[f];
             rank += (df < de) || (df == de && wi[f] < ie);
         }
-        if (rank < k && ie != 0x7fffffff) {
+        if (rank < k) {
             idx_out[n * k + rank] = ie;
             dist_out[n * k + rank] = (float)de;
         }
         if (rank == k - 1) kth = de;
     }
     if (unsafe != nullptr) {
-        // certificate: every reference row NOT among the candidates has scan score >= thr (its
-        // split's kc-th best).  With |scan score - exact| <= eps it cannot beat the exact k-th
-        // neighbour if  kth_exact - ||q||^2 + 2 eps < thr.
+        // certificate: every reference row NOT among the candidates has scan score >= tmin (its split's kc-th
+        // best group minimum).  With |scan score - exact| <= eps it cannot beat the exact k-th neighbour if
+        // kth_exact - ||q||^2 + 2 eps < tmin.
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) kth = fmax(kth, __shfl_xor_sync(0xffffffffu, kth, o));
-        bad = __any_sync(0xffffffffu, bad);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
-        bad |= nvalid < k;
-        if (lane == 0) {
-            double tmin = INFINITY;
-            for (int s = 0; s < nsplit; ++s) tmin = fmin(tmin, (double)thr[row * nsplit + s]);
-            unsafe[n] = (!bad && kth - qn + 2.0 * eps < tmin * unscale) ? 0 : 1;
-        }
+        bad |= nsurv < k;
+        if (lane == 0) unsafe[n] = (!bad && kth - qn + 2.0 * eps < tmin) ? 0 : 1;
     }
 }
 
@@ -599,7 +639,7 @@ extern "C" int sym_knn(const float *Q, int32_t ldq, int64_t N, const float *Ref,
     KnnPacked pk = knn_packed_layout(const_cast<void *>(packed), M, d);
     if (method == 0) method = knn_tc_supported(N, M, d, k, 0) ? 2 : 1;
 
-    int ncand = 0, nsplit = 1;
+    int ncand = 0, nsplit = 1, group = 1;   // group: reference positions per candidate (8 for the tcgen05 scans)
     double eps_rel = 0.0;
     const unsigned long long *cand = nullptr;
     const float *thr = nullptr;
@@ -609,7 +649,7 @@ extern "C" int sym_knn(const float *Q, int32_t ldq, int64_t N, const float *Ref,
         SYM_REQUIRE(knn_tc_supported(N, M, d, k, prec), SYM_ERR_UNSUPPORTED_SHAPE,
                     "sym_knn: tcgen05 scan does not support this shape");
         int rc = knn_tc_scan(Q, ldq, N, q_perm, q_code, cl_tile, pk, M, d, k, prec, workspace, workspace_bytes, st, &cand,
-                             &thr, &ncand, &nsplit, &eps_rel, &dq16);
+                             &thr, &ncand, &nsplit, &group, &eps_rel, &dq16);
         if (rc != SYM_OK) return rc;
     } else {
         ScanPlan p;
@@ -629,9 +669,10 @@ extern "C" int sym_knn(const float *Q, int32_t ldq, int64_t N, const float *Ref,
         eps_rel = (double)(d + 4) * 5.97e-8;
     }
     SYM_REQUIRE(ncand <= RR_MAXC, SYM_ERR_UNSUPPORTED_SHAPE, "sym_knn: internal: %d candidates per row", ncand);
-    knn_rerank_kernel<<<(unsigned)ceil_div(N, RR_THREADS / 32), RR_THREADS, 0, st>>>(
-        Q, ldq, N, Ref, ldr, M, d, k, cand, thr, ncand, nsplit, eps_rel, pk.hdr, pk.order, q_perm, dq16, idx, dist2,
-        unsafe);
+    SYM_CUDA(cudaFuncSetAttribute(knn_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RR_SMEM));
+    knn_rerank_kernel<<<(unsigned)ceil_div(N, RR_THREADS / 32), RR_THREADS, RR_SMEM, st>>>(
+        Q, ldq, N, Ref, ldr, pk.refT, pk.Mpad, M, d, k, cand, thr, ncand, nsplit, group, eps_rel, pk.hdr, pk.order, q_perm,
+        dq16, idx, dist2, unsafe);
     SYM_LAUNCH_CHECK("knn_rerank_kernel");
     return SYM_OK;
 }

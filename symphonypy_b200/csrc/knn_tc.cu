@@ -40,9 +40,6 @@ constexpr int TC_BN = 128;        // reference rows per tile (UMMA N)
 // TMEM accumulator buffers per query tile: 4 / QT  (QT * ACC * 128 = 512 columns)
 constexpr int TC_MAX_STAGES = 6;
 constexpr int TC_PAD = 8;         // over-selection: kc = k + TC_PAD
-#ifndef TC_FLUSH
-#define TC_FLUSH 4               // tiles between flushes of the pending hits (power of two)
-#endif
 
 // operand precision: 0 = BF16x3 (three split products, K' = 3d+3), 1 = single FP16 (K' = d+2)
 __host__ __device__ inline int tc_kp(int d, int prec) { return prec ? (d + 2 + 15) / 16 * 16 : (3 * d + 3 + 15) / 16 * 16; }
@@ -250,7 +247,7 @@ __device__ unsigned long long tc_prof[16];
 // accumulator was slower too: the selection warps have no such slack once updates are frequent.)
 __host__ __device__ inline int tc_heap_stride(int kc) { return 1 + 4 * ((kc - 1 + 3) / 4); }   // odd, >= kc
 
-__device__ __noinline__ float tc_insert(unsigned long long *heap, int kc, float s, uint32_t id) {
+__device__ __forceinline__ float tc_insert(unsigned long long *heap, int kc, float s, uint32_t id) {
     // entries are (raw float score bits << 32 | position); only the scores are compared (one FSETP per level) —
     // equal scores may settle in either order, the float64 re-rank orders the survivors by (distance, index).
     // 4-ary: node i has children 4i+1..4i+4, so kc = 18 is two levels below the root instead of four; the four
@@ -258,6 +255,7 @@ __device__ __noinline__ float tc_insert(unsigned long long *heap, int kc, float 
     const unsigned long long key = ((unsigned long long)__float_as_uint(s) << 32) | id;
     int i = 0;
     float root = s;   // score at the root after the update (no read-back of what was just stored)
+#pragma unroll 1
     while (true) {
         const int c = 4 * i + 1;
         if (c >= kc) break;
@@ -278,25 +276,6 @@ __device__ __noinline__ float tc_insert(unsigned long long *heap, int kc, float 
     return root;
 }
 
-// Lanes whose group of 8 holds a hit: locate the group minimum with compare/select pairs (no data-dependent
-// branch per element: the 8 sequential branches of a plain walk cost more than the heap update), record it,
-// blank it and look again — one round in all but a few cases.
-#define TC_WALK8(G, GV)                                                                               \
-    while (GV < thr) {                                                                                \
-        int j = 7;                                                                                    \
-        _Pragma("unroll") for (int e = 6; e >= 0; --e) j = __uint_as_float(v[(G) * 8 + e]) == GV ? e : j; \
-        if (pend_id != 0xffffffffu) {                                                                 \
-            thr = tc_insert(heap, kc, pend_s, pend_id);                                               \
-            pend_id = 0xffffffffu;                                                                    \
-        }                                                                                             \
-        if (GV < thr) {   /* still a hit against the threshold as it is NOW (the update lowered it) */ \
-            pend_s = GV;                                                                              \
-            pend_id = ref0 + (uint32_t)((G) * 8) + (uint32_t)j;                                       \
-        }                                                                                             \
-        _Pragma("unroll") for (int e = 0; e < 8; ++e) v[(G) * 8 + e] = j == e ? 0x7f800000u : v[(G) * 8 + e]; \
-        GV = tc_min8(v + (G) * 8);                                                                    \
-    }
-
 __device__ __forceinline__ float tc_min8(const uint32_t *v) {
     float m = fmin3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
     m = fmin3(m, __uint_as_float(v[3]), __uint_as_float(v[4]));
@@ -304,20 +283,10 @@ __device__ __forceinline__ float tc_min8(const uint32_t *v) {
     return fminf(m, __uint_as_float(v[7]));
 }
 
-// one 32-column chunk of the warp's 32 rows against the rows' thresholds
 // (Padding needs no bounds check: padded reference rows carry ||r||^2 = +inf and padded query rows are all-zero
-// operands, so their scores are +inf / NaN and never pass `sv < thr`.)
-// A hit is parked in a one-entry pending slot (registers) and only goes into the heap when the lane's next hit
-// arrives or at the periodic flush, where all lanes that have something pending update their rows TOGETHER: in
-// the sparse phase of the scan (about one hit per warp and tile) this turns several serial ~400-cycle heap
-// updates into one.  The threshold of a lane with a pending hit is stale by that one entry (never too small);
-// a parked hit is always below the threshold in force when it was parked, and the threshold does not move until
-// it is inserted — tc_insert must never be given a score that is not below the current root, it would evict a
-// better candidate and void the certificate.
+// operands, so their scores are +inf / NaN and never pass `s < thr`.)
 // The common case (no hit anywhere in the tile) is one straight-line block: the group minima of ALL chunks of
-// the tile (16 independent 3-input-min chains for 128 scores), one overall minimum, one compare.  Interleaving
-// the chains of the four chunks matters: with a branch after every chunk the warp waited out the dependent
-// latency of each chunk's tree separately (two selection warps per scheduler cannot hide it).
+// the tile (16 independent 3-input-min chains for 128 scores), one overall minimum, one compare, one vote.
 struct TcMins {
     float g0, g1, g2, g3;
 };
@@ -326,91 +295,91 @@ __device__ __forceinline__ TcMins tc_mins32(const uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ float tc_min4(const TcMins &m) { return fminf(fmin3(m.g0, m.g1, m.g2), m.g3); }
 
-// slow path for one 32-column chunk: some lane of the warp has a hit somewhere in the tile
-__device__ __forceinline__ float tc_walk32(uint32_t (&v)[32], TcMins m, float thr, uint32_t ref0,
-                                           unsigned long long *heap, int kc, float &pend_s, uint32_t &pend_id) {
-    if (tc_min4(m) < thr) {
-        TC_WALK8(0, m.g0)
-        TC_WALK8(1, m.g1)
-        TC_WALK8(2, m.g2)
-        TC_WALK8(3, m.g3)
+// ---- what is selected: GROUPS of 8 consecutive reference positions, keyed by the group's minimum score ----
+// The fast path already has the minimum of every group of 8 scores (the leaves of its min tree).  Selecting groups
+// instead of single references means the slow path never has to look INSIDE a group (registers cannot be indexed:
+// round 1 walked the 8 scores of a hit group through a 16-way switch, ~250 instructions and 4.5 KB of code per
+// event): a hit is (group minimum, first position of the group), read off the 16 minima by a select tree.  The
+// float64 re-rank expands each of a row's kc candidate groups into its 8 members and ranks those whose exact score
+// is below the row's threshold.  The certificate is unchanged: a reference outside the candidate groups has
+// score >= its group's minimum >= the row's final threshold.
+//
+// ---- hits are queued, not inserted where they are found ----
+// Round 1 updated the row's heap right away (a ~400-cycle update with 1-2 of 32 lanes active, on the critical
+// path of a warp that three other warps wait for).  Now a hit is appended to the lane's own small queue in shared
+// memory (one 8-byte store) and the queues of all 32 rows of the warp are drained TOGETHER every `flush` tiles (or
+// when a lane's queue is full): the same heap updates with most lanes active at once.  The threshold of a row is
+// stale by what sits in its queue (never too small): rejected scores are >= the threshold in force at that time
+// >= the final threshold, which is all the certificate needs.  A queued score is re-checked against the root when
+// it is drained — tc_insert must never be given a score that is not below the current root, it would evict a
+// better candidate and void the certificate.
+//
+// ---- code size ----
+// Measured (profiles/r2a_*): rarely executed code ran at 10-20 cycles per instruction — the kernel is ~32 KB of
+// SASS, the selection warps share a ~6 KB L0 instruction cache with the issuer, and every visit to the slow path
+// re-fetched it.  The slow path is therefore written for FEW BYTES, not few executed instructions: loops are kept
+// rolled (`#pragma unroll 1`), the drain is one out-of-line function, nothing is specialised per group.
+#ifndef TC_QCAP
+#define TC_QCAP 8                 // queue entries per row
+#endif
+constexpr int TC_GROUP = 8;       // reference positions per candidate group
+
+__device__ __noinline__ float tc_drain(unsigned long long *heap, int kc, const unsigned long long *queue, int qn,
+                                       float thr) {
+#pragma unroll 1
+    for (int j = 0; j < qn; ++j) {
+        const unsigned long long e = queue[j];
+        const float s = __uint_as_float((uint32_t)(e >> 32));
+        if (s < thr) thr = tc_insert(heap, kc, s, (uint32_t)e);
     }
     return thr;
 }
 
-// Slow path for a whole 128-column tile (TC_H == 1).  A bit mask of the groups that hold a hit is built without
-// branches; each hit group is then copied into eight common registers by a 16-way switch (the only code that is
-// specific to a group: a lane's hit can sit in any of 16 register groups and registers cannot be indexed), and
-// ONE copy of the locate / park / blank / re-examine loop serves every lane of the warp, whatever group its hit
-// is in.  (The first version had that loop once per group: lanes with hits in different groups ran them one
-// after the other, ~20 divergent regions per walked tile.)
-__device__ __forceinline__ float tc_walk128(const uint32_t (&v0)[32], const uint32_t (&v1)[32], const uint32_t (&v2)[32],
-                                            const uint32_t (&v3)[32], const TcMins &m0, const TcMins &m1,
-                                            const TcMins &m2, const TcMins &m3, float thr, uint32_t ref0,
-                                            unsigned long long *heap, int kc, float &pend_s, uint32_t &pend_id) {
-    unsigned mask = 0;
-#define TC_BIT(GV, B) mask |= (GV < thr) ? (1u << (B)) : 0u;
+// Slow path of a tile for ONE lane whose row has a group minimum below its threshold (typically one lane of the
+// warp, one group): mask of the hit groups, then per hit a 15-select tree over the 16 minima and one queue append.
+__device__ __forceinline__ void tc_hits(const TcMins &m0, const TcMins &m1, const TcMins &m2, const TcMins &m3,
+                                        float &thr, uint32_t ref0, unsigned long long *heap, int kc,
+                                        unsigned long long *queue, int &qn) {
+    unsigned hm = 0;
+#define TC_BIT(GV, B) hm |= (GV < thr) ? (1u << (B)) : 0u;
     TC_BIT(m0.g0, 0) TC_BIT(m0.g1, 1) TC_BIT(m0.g2, 2) TC_BIT(m0.g3, 3)
     TC_BIT(m1.g0, 4) TC_BIT(m1.g1, 5) TC_BIT(m1.g2, 6) TC_BIT(m1.g3, 7)
     TC_BIT(m2.g0, 8) TC_BIT(m2.g1, 9) TC_BIT(m2.g2, 10) TC_BIT(m2.g3, 11)
     TC_BIT(m3.g0, 12) TC_BIT(m3.g1, 13) TC_BIT(m3.g2, 14) TC_BIT(m3.g3, 15)
 #undef TC_BIT
-    while (mask) {
-        const int gi = __ffs(mask) - 1;
-        mask &= mask - 1;
-        float w[8];
-#define TC_CASE(I, V, O)                                                                     \
-    case I:                                                                                  \
-        _Pragma("unroll") for (int e = 0; e < 8; ++e) w[e] = __uint_as_float(V[(O) + e]);   \
-        break;
-        switch (gi) {
-            TC_CASE(0, v0, 0) TC_CASE(1, v0, 8) TC_CASE(2, v0, 16) TC_CASE(3, v0, 24)
-            TC_CASE(4, v1, 0) TC_CASE(5, v1, 8) TC_CASE(6, v1, 16) TC_CASE(7, v1, 24)
-            TC_CASE(8, v2, 0) TC_CASE(9, v2, 8) TC_CASE(10, v2, 16) TC_CASE(11, v2, 24)
-            TC_CASE(12, v3, 0) TC_CASE(13, v3, 8) TC_CASE(14, v3, 16)
-            default:
-                _Pragma("unroll") for (int e = 0; e < 8; ++e) w[e] = __uint_as_float(v3[24 + e]);
-                break;
+#pragma unroll 1
+    while (hm) {
+        const int gi = __ffs(hm) - 1;
+        hm &= hm - 1;
+        const bool b0 = gi & 1, b1 = gi & 2, b2 = gi & 4, b3 = gi & 8;
+        const float s0 = b0 ? m0.g1 : m0.g0, s1 = b0 ? m0.g3 : m0.g2, s2 = b0 ? m1.g1 : m1.g0, s3 = b0 ? m1.g3 : m1.g2;
+        const float s4 = b0 ? m2.g1 : m2.g0, s5 = b0 ? m2.g3 : m2.g2, s6 = b0 ? m3.g1 : m3.g0, s7 = b0 ? m3.g3 : m3.g2;
+        const float t0 = b1 ? s1 : s0, t1 = b1 ? s3 : s2, t2 = b1 ? s5 : s4, t3 = b1 ? s7 : s6;
+        const float u0 = b2 ? t1 : t0, u1 = b2 ? t3 : t2;
+        const float gm = b3 ? u1 : u0;
+        if (qn == TC_QCAP) {   // (the mask may now hold groups that are no longer hits: harmless, re-checked at the drain)
+            thr = tc_drain(heap, kc, queue, qn, thr);
+            qn = 0;
         }
-#undef TC_CASE
-        const uint32_t id0 = ref0 + (uint32_t)(gi * 8);
-        float g = fminf(fmin3(fmin3(w[0], w[1], w[2]), w[3], w[4]), fmin3(w[5], w[6], w[7]));
-        while (g < thr) {   // almost always one round
-            int j = 7;
-#pragma unroll
-            for (int e = 6; e >= 0; --e) j = w[e] == g ? e : j;
-            if (pend_id != 0xffffffffu) {
-                thr = tc_insert(heap, kc, pend_s, pend_id);
-                pend_id = 0xffffffffu;
-            }
-            if (g < thr) {   // still a hit against the threshold as it is NOW (the update lowered it)
-                pend_s = g;
-                pend_id = id0 + (uint32_t)j;
-            }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) w[e] = j == e ? INFINITY : w[e];
-            g = fminf(fmin3(fmin3(w[0], w[1], w[2]), w[3], w[4]), fmin3(w[5], w[6], w[7]));
-        }
+        queue[qn++] = ((unsigned long long)__float_as_uint(gm) << 32) | (ref0 + (uint32_t)(gi * TC_GROUP));
     }
-    return thr;
 }
 
-template <int TC_QT, int TC_H>
-__global__ void __launch_bounds__(128 + 128 * TC_QT * TC_H, 1)
+template <int TC_QT>
+__global__ void __launch_bounds__(128 + 128 * TC_QT, 1)
 knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char *__restrict__ rpack, int64_t N,
                    const int32_t *__restrict__ q_perm, const int32_t *__restrict__ q_code,
                    const int32_t *__restrict__ cl_tile, int64_t M, int kp, int kc, int stages, int nbuf,
-                   int tiles_per_split, int ntiles_all, int ss_mode, uint32_t idesc,
+                   int tiles_per_split, int ntiles_all, int ss_mode, uint32_t idesc, int flush_mask,
                    unsigned long long *__restrict__ cand_out, float *__restrict__ thr_out) {
     extern __shared__ __align__(1024) unsigned char smraw[];
     const uint32_t tile_bytes = (uint32_t)tc_tile_bytes(kp);
     const int ks = tc_heap_stride(kc);  // odd row stride: the 32 rows of a warp hit 32 different banks
     unsigned char *r_s = smraw;                                        // [stages][tile_bytes]
-    // TC_H = 1: one selection warp per (query tile, TMEM lane quadrant) examines all 128 columns of a tile;
-    // TC_H = 2: two warps share a quadrant, 64 columns each, each with its own heap per row (the re-rank merges
-    // the two candidate lists) — twice the selection throughput for twice the list memory.
-    unsigned long long *heap_s = (unsigned long long *)(r_s + (size_t)stages * tile_bytes);  // [TC_QT*TC_H][TC_BM][ks]
-    uint64_t *bars = (uint64_t *)(heap_s + (size_t)TC_QT * TC_H * ks * TC_BM);
+    // one selection warp per (query tile, TMEM lane quadrant) examines all 128 columns of a tile
+    unsigned long long *heap_s = (unsigned long long *)(r_s + (size_t)stages * tile_bytes);  // [TC_QT][TC_BM][ks]
+    unsigned long long *queue_s = heap_s + (size_t)TC_QT * ks * TC_BM;                       // [TC_QT][TC_BM][TC_QCAP]
+    uint64_t *bars = (uint64_t *)(queue_s + (size_t)TC_QT * TC_BM * TC_QCAP);
     uint64_t *r_full = bars;                      // [TC_MAX_STAGES]
     uint64_t *r_empty = r_full + TC_MAX_STAGES;   // [TC_MAX_STAGES]
     uint64_t *t_full = r_empty + TC_MAX_STAGES;   // [4]  accumulator buffers, used in rotation by all query tiles
@@ -440,7 +409,7 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < TC_MAX_STAGES; ++i) { mbar_init(&r_full[i], 1); mbar_init(&r_empty[i], TC_QT); }
-        for (int i = 0; i < 4; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4 * TC_H); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
         *turn = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -451,7 +420,7 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (warp >= 4) {  // selection threads initialise their row's heap (all slots empty = the largest key)
-        const int list = (warp - 4) >> 2, row = (warp & 3) * 32 + lane;
+        const int list = (warp - 4) >> 2, row = (warp & 3) * 32 + lane;   // list = query tile
         for (int e = 0; e < ks; ++e)
             heap_s[((size_t)list * TC_BM + row) * ks + e] = ((e < kc ? 0x7f800000ull : 0xff800000ull) << 32) | 0xffffffffull;
     }
@@ -459,9 +428,9 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if (warp >= 4 && ((warp - 4) >> 2) % TC_H == 0) {
+    if (warp >= 4) {
         // park this thread's query row (BF16x3, kp values) in tensor memory: it is the A operand of every MMA
-        const int qt = ((warp - 4) >> 2) / TC_H, quad = warp & 3;
+        const int qt = (warp - 4) >> 2, quad = warp & 3;
         const int64_t n = ((int64_t)blockIdx.x * TC_QT + qt) * TC_BM + quad * 32 + lane;
         const uint4 *src = reinterpret_cast<const uint4 *>(qrows + (size_t)n * kp * 2);
         const uint32_t dst = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)qt * a_cols;
@@ -482,10 +451,8 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
     // Register reallocation between the warp groups (the launch bound of 168 registers per thread is what 384
     // threads can share evenly): the producer / issuer group needs few, the selection warps hold a whole
     // accumulator row (128 scores) plus the group minima and spill without the extra room.
-    if (TC_H == 1) {
-        if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
-        else asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
-    }
+    if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     if (warp == 0) {
         // ===== producer: one bulk copy per reference tile =====
         if (lane == 0) {
@@ -564,19 +531,17 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
         // spare warp(s): nothing to do until the final barrier
     } else {
         // ===== selection =====
-        const int list = (warp - 4) >> 2, quad = warp & 3;
-        const int qt = list / TC_H, half = list % TC_H;
-        constexpr int COLS = TC_BN / TC_H;   // columns of every tile this warp examines
+        const int qt = (warp - 4) >> 2, quad = warp & 3;
         const int row = quad * 32 + lane;
-        unsigned long long *heap = heap_s + ((size_t)list * TC_BM + row) * ks;   // this thread's row
+        unsigned long long *heap = heap_s + ((size_t)qt * TC_BM + row) * ks;         // this thread's row
+        unsigned long long *queue = queue_s + ((size_t)qt * TC_BM + row) * TC_QCAP;  // its queue of hits not yet inserted
         float thr = INFINITY;
-        float pend_s = 0.f;
-        uint32_t pend_id = 0xffffffffu;   // no pending hit
-        const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + acc0 + (uint32_t)(half * COLS);
+        int qn = 0;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + acc0;
         int buf = qt % nbuf, use = qt / nbuf;   // chain (i, qt) = sequence number i*QT + qt
         int t_cur = t_home;
 #ifdef TC_PROFILE
-        long long prof_0 = 0, prof_1 = 0, prof_2 = 0, prof_3 = 0, prof_5 = 0, prof_6 = 0;
+        long long prof_0 = 0, prof_1 = 0, prof_2 = 0, prof_3 = 0, prof_5 = 0, prof_6 = 0, prof_7 = 0, prof_13 = 0, prof_14 = 0;
 #endif
         for (int i = 0; i < ntiles; ++i) {
             TC_CLK(c0);
@@ -586,7 +551,7 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
             mbar_wait(&t_full[buf], use & 1);
 #endif
             tc_fence_after();
-            const uint32_t ref0 = (uint32_t)(t_cur * TC_BN + half * COLS);
+            const uint32_t ref0 = (uint32_t)(t_cur * TC_BN);
             if (++t_cur == t_end) t_cur = t_beg;
             const uint32_t acc = lane_base + (uint32_t)(buf * TC_BN);
 #ifdef TC_EXPERIMENT_NO_SELECT
@@ -594,90 +559,90 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
             if (lane == 0) mbar_arrive(&t_empty[buf]);
             __syncwarp();
 #else
-            // pull this warp's share of the accumulator row into registers and hand the TMEM buffer straight
-            // back: the next chain can then run while this tile is examined (the buffer is held for one load latency)
-            uint32_t v0[32], v1[32];
+            // pull the accumulator row into registers and hand the TMEM buffer straight back: the next chain can
+            // then run while this tile is examined (the buffer is held for one load latency).  (Splitting the load
+            // in two with a wait in between, to fold the first half while the second is in flight, was slower:
+            // 211 vs 131 cycles — the scoreboard already lets the min chains start as each LDTM lands.)
+            uint32_t v0[32], v1[32], v2[32], v3[32];
             TC_CLK(c1);
-#ifdef TC_PROFILE
-            long long c2 = 0;
-            float thr_before = 0.f;
-            uint32_t pend_before = 0;
-#endif
             tc_ld32(acc, v0);
             tc_ld32(acc + 32, v1);
-            if (TC_H == 1) {
-                uint32_t v2[32], v3[32];
-                tc_ld32(acc + 64, v2);
-                tc_ld32(acc + 96, v3);
-                tc_wait_ld();
-                tc_fence_before();
-                if (lane == 0) mbar_arrive(&t_empty[buf]);
-#ifdef TC_PROFILE
-                c2 = clock64();
-                prof_0 += c1 - c0; prof_1 += c2 - c1;
-                thr_before = thr;
-                pend_before = pend_id;
-#endif
-                const TcMins m0 = tc_mins32(v0), m1 = tc_mins32(v1), m2 = tc_mins32(v2), m3 = tc_mins32(v3);
+            tc_ld32(acc + 64, v2);
+            tc_ld32(acc + 96, v3);
+            tc_wait_ld();
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(&t_empty[buf]);
+            TC_CLK(c2);
+            const TcMins m0 = tc_mins32(v0), m1 = tc_mins32(v1), m2 = tc_mins32(v2), m3 = tc_mins32(v3);
+            const float mall = fminf(fmin3(tc_min4(m0), tc_min4(m1), tc_min4(m2)), tc_min4(m3));
 #ifndef TC_EXPERIMENT_NO_WALK
-                if (fminf(fmin3(tc_min4(m0), tc_min4(m1), tc_min4(m2)), tc_min4(m3)) < thr)
-                    thr = tc_walk128(v0, v1, v2, v3, m0, m1, m2, m3, thr, ref0, heap, kc, pend_s, pend_id);
-#else
-                if (fminf(fmin3(tc_min4(m0), tc_min4(m1), tc_min4(m2)), tc_min4(m3)) < -1e30f) thr = 0.f;
-#endif
-            } else {
-                tc_wait_ld();
-                tc_fence_before();
-                if (lane == 0) mbar_arrive(&t_empty[buf]);
-                const TcMins m0 = tc_mins32(v0), m1 = tc_mins32(v1);
-                if (fminf(tc_min4(m0), tc_min4(m1)) < thr) {
-                    thr = tc_walk32(v0, m0, thr, ref0, heap, kc, pend_s, pend_id);
-                    thr = tc_walk32(v1, m1, thr, ref0 + 32, heap, kc, pend_s, pend_id);
-                }
-            }
+            const bool any_hit = __any_sync(0xffffffffu, mall < thr);
 #ifdef TC_PROFILE
-            const long long c3 = clock64();
-            if (TC_H == 1) {
-                prof_2 += c3 - c2;
-                const bool touched = (pend_id != pend_before) || (thr != thr_before);
-                prof_5 += __any_sync(0xffffffffu, touched) ? 1 : 0;
-                prof_6 += __popc(__ballot_sync(0xffffffffu, touched));
-            }
+            const long long c2a = clock64();
+            prof_7 += c2a - c2;
 #endif
-            if ((i & (TC_FLUSH - 1)) == TC_FLUSH - 1 && pend_id != 0xffffffffu) {   // periodic flush, lanes in lock-step
-                thr = tc_insert(heap, kc, pend_s, pend_id);
-                pend_id = 0xffffffffu;
+            if (any_hit) {
+#ifdef TC_PROFILE
+                const int qn0 = qn;
+                const float thr0 = thr;
+#endif
+                if (mall < thr) {
+#ifdef TC_PROFILE
+                    const long long h0 = clock64();
+#endif
+                    tc_hits(m0, m1, m2, m3, thr, ref0, heap, kc, queue, qn);
+#ifdef TC_PROFILE
+                    prof_13 += clock64() - h0;
+                    prof_14 += 1;
+#endif
+                }
+                __syncwarp();
+#ifdef TC_PROFILE
+                prof_5 += 1;
+                prof_6 += __popc(__ballot_sync(0xffffffffu, qn != qn0 || thr != thr0));
+#endif
+            }
+#else
+            if (mall < -1e30f) thr = 0.f;
+#endif
+            TC_CLK(c3);
+            if ((i & flush_mask) == flush_mask && __any_sync(0xffffffffu, qn != 0)) {   // periodic drain, lanes in lock-step
+                thr = tc_drain(heap, kc, queue, qn, thr);
+                qn = 0;
             }
             __syncwarp();
 #ifdef TC_PROFILE
-            prof_3 += clock64() - c3;
+            prof_0 += c1 - c0; prof_1 += c2 - c1; prof_2 += c3 - c2; prof_3 += clock64() - c3;
 #endif
 #endif
             // advance the rotation by TC_QT chains
             buf += TC_QT;
             while (buf >= nbuf) { buf -= nbuf; ++use; }
         }
-        if (pend_id != 0xffffffffu) thr = tc_insert(heap, kc, pend_s, pend_id);
+        if (qn != 0) thr = tc_drain(heap, kc, queue, qn, thr);
         __syncwarp();
 #ifdef TC_PROFILE
         if (lane == 0) {
             atomicAdd(&tc_prof[0], (unsigned long long)prof_0); atomicAdd(&tc_prof[1], (unsigned long long)prof_1);
             atomicAdd(&tc_prof[2], (unsigned long long)prof_2); atomicAdd(&tc_prof[3], (unsigned long long)prof_3);
             atomicAdd(&tc_prof[4], (unsigned long long)ntiles); atomicAdd(&tc_prof[5], (unsigned long long)prof_5);
-            atomicAdd(&tc_prof[6], (unsigned long long)prof_6);
+            atomicAdd(&tc_prof[6], (unsigned long long)prof_6); atomicAdd(&tc_prof[7], (unsigned long long)prof_7);
+        }
+        if (prof_14) {   // per hit lane: cycles inside tc_hits, number of visits
+            atomicAdd(&tc_prof[13], (unsigned long long)prof_13); atomicAdd(&tc_prof[14], (unsigned long long)prof_14);
         }
 #endif
         // results: the row's candidates as (score, position) keys (unordered) and its final threshold
         const int64_t n = ((int64_t)blockIdx.x * TC_QT + qt) * TC_BM + row;
         if (n < N) {
-            const int64_t slot = (n * nsplit + split) * TC_H + half;
+            const int64_t slot = n * nsplit + split;
             for (int e = 0; e < kc; ++e) {
                 const unsigned long long h = heap[e];
                 const uint32_t pos = (uint32_t)h;
                 cand_out[slot * kc + e] = pos == 0xffffffffu ? ~0ull : knn_make_key(__uint_as_float((uint32_t)(h >> 32)), pos);
             }
             const int64_t split_refs = min(M, (int64_t)t_end * TC_BN) - (int64_t)t_beg * TC_BN;
-            thr_out[slot] = split_refs <= kc ? INFINITY : thr;  // nothing was left out of such a split
+            thr_out[slot] = ceil_div(split_refs, TC_GROUP) <= kc ? INFINITY : thr;  // every group of such a split was handed over
         }
     }
     tc_fence_before();
@@ -760,7 +725,7 @@ tc_debug_kernel(const unsigned char *__restrict__ qpack, const unsigned char *__
 // ------------------------------------------------------------------------------------------ host side
 namespace {
 struct TcPlan {
-    int kp, kc, qt, halves, stages, nbuf, nsplit, tiles_per_split, ntiles, ss;
+    int kp, kc, qt, stages, nbuf, nsplit, tiles_per_split, ntiles, ss, flush_mask;
     int64_t qtiles;
     size_t smem, qpack_bytes, cand_bytes, thr_bytes, dq_bytes;
     bool ok;
@@ -779,32 +744,33 @@ TcPlan tc_plan(int64_t N, int64_t M, int d, int k, int prec) {
     int stages = 0;
     const char *force_qt = getenv("SYM_TC_QT");      // tuning / experiments only
     const char *force_nbuf = getenv("SYM_TC_NBUF");
-    const char *force_h = getenv("SYM_TC_HALVES");
     const char *force_ss = getenv("SYM_TC_SS");
     // Preference: 256 rows per CTA, then 128; within that, the query operand in SHARED memory when there is room
     // for it next to >= 3 reference stages: tensor memory then holds four accumulators, two per query tile, and the
     // two query tiles stop sharing a rotation (measured 2-5 % faster than the tensor-memory operand with three
     // shared accumulators; the SS form's slower MMA does not matter because selection is the bottleneck).
-    // Two selection warps per quadrant (64 columns each, two heaps per row) are implemented but measured ~8 %
-    // slower at config 2, so they are only used when asked for.
-    const int cfg[8][3] = {{2, 1, 1}, {2, 1, 0}, {1, 1, 1}, {1, 1, 0}, {2, 2, 1}, {2, 2, 0}, {1, 2, 1}, {1, 2, 0}};
-    for (int c = 0; c < 8; ++c) {
-        const int qt = cfg[c][0], h = cfg[c][1], ss = cfg[c][2];
+    const int cfg[4][2] = {{2, 1}, {2, 0}, {1, 1}, {1, 0}};
+    for (int c = 0; c < 4; ++c) {
+        const int qt = cfg[c][0], ss = cfg[c][1];
         if (force_qt && atoi(force_qt) != qt) continue;
-        if (force_h ? atoi(force_h) != h : h != 1) continue;
         if (force_ss && (atoi(force_ss) != 0) != (ss != 0)) continue;
-        fixed = (size_t)qt * h * tc_heap_stride(kc) * TC_BM * 8 + 256 /* barriers */ + 1024 /* alignment slack */ +
+        fixed = (size_t)qt * (tc_heap_stride(kc) + TC_QCAP) * TC_BM * 8 + 256 /* barriers */ + 1024 /* alignment slack */ +
                 (ss ? (size_t)qt * tile + 1024 : 0);
         stages = budget > fixed ? (int)((budget - fixed) / tile) : 0;
         if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
         p.qt = qt;
-        p.halves = h;
         p.ss = ss;
         p.nbuf = (512 - (ss ? 0 : qt * p.kp / 2)) / TC_BN;  // accumulators that fit beside the A operands in tensor memory
         if (p.nbuf > 4) p.nbuf = 4;
         if (force_nbuf && atoi(force_nbuf) >= 1 && atoi(force_nbuf) <= p.nbuf) p.nbuf = atoi(force_nbuf);
         if (stages >= 3 && p.nbuf >= 2) break;
     }
+    // tiles between two lock-step drains of the rows' hit queues (power of two)
+    const char *force_flush = getenv("SYM_TC_FLUSH");
+    int flush = force_flush ? atoi(force_flush) : 32;
+    if (flush < 1) flush = 1;
+    while (flush & (flush - 1)) flush &= flush - 1;
+    p.flush_mask = flush - 1;
     p.stages = stages;
     p.ok = stages >= 2 && p.nbuf >= 1 && p.kp <= 256 && d <= 84;
     p.smem = fixed + (size_t)(stages > 0 ? stages : 0) * tile;
@@ -815,7 +781,7 @@ TcPlan tc_plan(int64_t N, int64_t M, int d, int k, int prec) {
     if (p.qtiles < kNumSMs) {
         nsplit = (int)ceil_div(kNumSMs, p.qtiles);
         const int by_work = p.ntiles / 16 > 0 ? p.ntiles / 16 : 1;
-        const int by_rerank = 512 / (kc * p.halves) > 0 ? 512 / (kc * p.halves) : 1;
+        const int by_rerank = 512 / kc > 0 ? 512 / kc : 1;
         nsplit = nsplit < by_work ? nsplit : by_work;
         nsplit = nsplit < by_rerank ? nsplit : by_rerank;
         if (nsplit < 1) nsplit = 1;
@@ -824,8 +790,8 @@ TcPlan tc_plan(int64_t N, int64_t M, int d, int k, int prec) {
     p.nsplit = (int)ceil_div(p.ntiles, p.tiles_per_split);
     p.qpack_bytes = (size_t)p.qtiles * p.qt * TC_BM * p.kp * 2;  // row-major query operand rows
     p.dq_bytes = prec ? (((size_t)p.qtiles * p.qt * TC_BM * sizeof(float) + 255) & ~(size_t)255) : 0;
-    p.cand_bytes = ((size_t)N * p.nsplit * p.halves * kc * 8 + 255) & ~(size_t)255;
-    p.thr_bytes = ((size_t)N * p.nsplit * p.halves * 4 + 255) & ~(size_t)255;
+    p.cand_bytes = ((size_t)N * p.nsplit * kc * 8 + 255) & ~(size_t)255;
+    p.thr_bytes = ((size_t)N * p.nsplit * 4 + 255) & ~(size_t)255;
     return p;
 }
 }  // namespace
@@ -863,7 +829,7 @@ int knn_tc_fit(const float *Ref, int ldr, int64_t M, int d, const int32_t *order
 int knn_tc_scan(const float *Q, int ldq, int64_t N, const int32_t *q_perm, const int32_t *q_code,
                 const int32_t *cl_tile, KnnPacked pk, int64_t M, int d, int k, int prec, void *workspace,
                 size_t workspace_bytes, cudaStream_t st, const unsigned long long **cand, const float **thr,
-                int *ncand, int *nsplit, double *eps_rel, const float **dq16) {
+                int *ncand, int *nsplit, int *group, double *eps_rel, const float **dq16) {
     TcPlan p = tc_plan(N, M, d, k, prec);
     SYM_REQUIRE(p.ok, SYM_ERR_UNSUPPORTED_SHAPE, "tcgen05 scan: d=%d k=%d does not fit", d, k);
     SYM_REQUIRE(workspace_bytes >= knn_tc_workspace(N, M, d, k, prec) - 1024, SYM_ERR_WORKSPACE_TOO_SMALL,
@@ -880,27 +846,25 @@ int knn_tc_scan(const float *Q, int ldq, int64_t N, const int32_t *q_perm, const
         SYM_LAUNCH_CHECK("tc_pack_rows_kernel(query)");
     }
     dim3 grid((unsigned)p.qtiles, (unsigned)p.nsplit);
-#define SYM_TC_LAUNCH(QT, H)                                                                                          \
+#define SYM_TC_LAUNCH(QT)                                                                                             \
     do {                                                                                                              \
-        SYM_CUDA(cudaFuncSetAttribute(knn_scan_tc_kernel<QT, H>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+        SYM_CUDA(cudaFuncSetAttribute(knn_scan_tc_kernel<QT>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
                                       (int)p.smem));                                                                  \
-        knn_scan_tc_kernel<QT, H><<<grid, 128 + 128 * QT * H, p.smem, st>>>(qpack, prec ? pk.tc16 : pk.tc, N, q_perm,      \
-                                                                          q_code, cl_tile,                           \
-                                                                          M, p.kp, p.kc, p.stages, p.nbuf,           \
-                                                                          p.tiles_per_split, p.ntiles, p.ss,         \
-                                                                          prec ? TC_IDESC_F16 : TC_IDESC_BF16,       \
-                                                                          cand_w, thr_w);                            \
+        knn_scan_tc_kernel<QT><<<grid, 128 + 128 * QT, p.smem, st>>>(qpack, prec ? pk.tc16 : pk.tc, N, q_perm, q_code,   \
+                                                                     cl_tile, M, p.kp, p.kc, p.stages, p.nbuf,        \
+                                                                     p.tiles_per_split, p.ntiles, p.ss,               \
+                                                                     prec ? TC_IDESC_F16 : TC_IDESC_BF16,             \
+                                                                     p.flush_mask, cand_w, thr_w);                    \
     } while (0)
-    if (p.qt == 2 && p.halves == 2) SYM_TC_LAUNCH(2, 2);
-    else if (p.qt == 2) SYM_TC_LAUNCH(2, 1);
-    else if (p.halves == 2) SYM_TC_LAUNCH(1, 2);
-    else SYM_TC_LAUNCH(1, 1);
+    if (p.qt == 2) SYM_TC_LAUNCH(2);
+    else SYM_TC_LAUNCH(1);
 #undef SYM_TC_LAUNCH
     SYM_LAUNCH_CHECK("knn_scan_tc_kernel");
     *cand = cand_w;
     *thr = thr_w;
-    *ncand = p.nsplit * p.halves * p.kc;
-    *nsplit = p.nsplit * p.halves;
+    *ncand = p.nsplit * p.kc;
+    *nsplit = p.nsplit;
+    *group = TC_GROUP;   // a candidate is a group of 8 consecutive packed positions, keyed by its minimum score
     // BF16x3: dropped lo.lo / residual terms are <= ~3 * 2^-16 of |q_i r_i| each; FP32 accumulation on top
     // single FP16: the operand rounding is bounded by the re-rank from the exact residuals (dq16, header.dr16);
     // eps_rel then only covers the FP32 accumulation of the kp products and the two-piece ||r||^2

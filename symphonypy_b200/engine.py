@@ -35,11 +35,20 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 
 
 def require_cuda(device=None) -> torch.device:
+    """The device to run on: `device` if given, else the current CUDA device — under `torchrun` (a process group is
+    initialised and LOCAL_RANK is set) the device of this rank, unless the caller already chose one with
+    `torch.cuda.set_device`."""
     if not torch.cuda.is_available():
         raise _lib.SymphonyLibraryError(
             "symphonypy_b200 needs a CUDA device (B200, sm_100a); there is no CPU path.")
-    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
-    return dev
+    if device is not None:
+        return torch.device(device)
+    cur = torch.cuda.current_device()
+    local = os.environ.get("LOCAL_RANK")
+    if (cur == 0 and local is not None and torch.distributed.is_available() and torch.distributed.is_initialized()
+            and int(local) < torch.cuda.device_count()):
+        cur = int(local)
+    return torch.device("cuda", cur)
 
 
 # ------------------------------------------------------------------------------------- project

@@ -22,16 +22,19 @@ from __future__ import annotations
 
 import logging
 import numbers
+import os
 import warnings
 import weakref
+import zlib
 from collections import OrderedDict
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 import pandas as pd
 import torch
 from scipy.sparse import issparse
 
-from . import _design, engine, pipeline
+from . import _design, _dist, engine, pipeline
 
 logger = logging.getLogger("symphonypy")
 
@@ -42,13 +45,65 @@ class settings:
     device = None                  # torch device; default: current CUDA device (LOCAL_RANK under torchrun)
     h2d_chunk_bytes = 256 << 20    # rows of X are streamed to the GPU in chunks of about this size
     knn_method = engine.KNN_AUTO   # 0 auto (tiered), 1 FP32 FFMA scan, 2 tcgen05 BF16x3 scan, 3 tcgen05 single-FP16 scan
-    keep_on_device = True          # remember device copies of the arrays written to obsm
+    # Remember device copies of the arrays this module wrote to obsm (saves their re-upload in transfer_labels_kNN /
+    # per_cell_confidence).  Off by default: a remembered copy is found by the identity of the numpy array, so an
+    # IN-PLACE edit of that obsm array between two calls would go unnoticed.  Re-uploading from the pinned result
+    # buffer costs ~2 ms per 100 MB.
+    keep_on_device = False
     store_R = True                 # write obsm[f"{basis}_symphony_R"] (N x K) as the reference does
+    pinned_pool_bytes = 2 << 30    # page-locked result buffers kept for reuse after their arrays are collected
 
 
 # ----------------------------------------------------------------------------- device caches
-_DEV_CACHE: "OrderedDict[int, tuple]" = OrderedDict()   # id(ndarray) -> (weakref, cuda tensor)
+# Reference-side device objects (loadings, packed kNN index) are cached across calls: building them costs more than
+# mapping a query.  Every cache key carries a DIGEST OF THE FULL CONTENT of the host arrays the object was built
+# from (mean, std, gene mask, loadings; the reference embedding), so the normal scanpy idiom of editing
+# `adata_ref` in place (re-scaling, re-running PCA, replacing rows) is noticed and the object rebuilt.  Hashing
+# runs at memory speed on a few threads (120 MB of float64 embedding: ~4 ms) — far below a rebuild.
+# Label columns are NOT cached: they are re-encoded on every call (3-20 ms for 500k labels).
+_DEV_CACHE: "OrderedDict[int, tuple]" = OrderedDict()   # id(ndarray) -> (weakref, cuda tensor); settings.keep_on_device
 _REF_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
+
+try:
+    import xxhash as _xxhash
+except ImportError:  # pragma: no cover - the image has it; zlib is the stand-in
+    _xxhash = None
+_HASH_CHUNK = 16 << 20
+_HASH_POOL: list = []
+
+
+def _hash_bytes(mv) -> int:
+    if _xxhash is not None:
+        return _xxhash.xxh3_64_intdigest(mv)
+    return (zlib.crc32(mv) << 32) | zlib.adler32(mv)
+
+
+def content_digest(*arrays) -> str:
+    """64-bit digests of the full contents (plus dtype and shape) of host arrays, as one string."""
+    out = []
+    for a in arrays:
+        if a is None:
+            out.append("-")
+            continue
+        if isinstance(a, torch.Tensor):
+            out.append(f"t{a.data_ptr():x}:{tuple(a.shape)}:{a._version}")   # device tensors: identity + version counter
+            continue
+        a = np.asarray(a)
+        if a.dtype == object:
+            a = np.asarray(pd.util.hash_pandas_object(pd.Series(a), index=False))
+        if not a.flags.c_contiguous:
+            a = np.ascontiguousarray(a)
+        mv = memoryview(a).cast("B") if a.size else memoryview(b"")
+        n = len(mv)
+        if n <= _HASH_CHUNK:
+            h = _hash_bytes(mv)
+        else:
+            if not _HASH_POOL:
+                _HASH_POOL.append(ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)))
+            parts = list(_HASH_POOL[0].map(lambda o: _hash_bytes(mv[o:o + _HASH_CHUNK]), range(0, n, _HASH_CHUNK)))
+            h = _hash_bytes(np.asarray(parts, dtype=np.uint64).tobytes())
+        out.append(f"{a.dtype.str}{a.shape}{h:x}")
+    return "|".join(out)
 
 
 def _remember(arr: np.ndarray, t: torch.Tensor) -> None:
@@ -61,35 +116,41 @@ def _remember(arr: np.ndarray, t: torch.Tensor) -> None:
 
 
 def _device_copy(arr, dev) -> torch.Tensor:
-    """Device float32 copy of an obsm entry (cache hit when this module wrote it)."""
+    """Device float32 copy of an obsm entry (cache hit only with `settings.keep_on_device`)."""
     if isinstance(arr, torch.Tensor):
         return arr.to(dev, torch.float32)
-    hit = _DEV_CACHE.get(id(arr))
-    if hit is not None and hit[0]() is arr and hit[1].device == dev:
-        return hit[1]
+    if settings.keep_on_device:
+        hit = _DEV_CACHE.get(id(arr))
+        if hit is not None and hit[0]() is arr and hit[1].device == dev:
+            return hit[1]
     a = np.ascontiguousarray(np.asarray(arr))
+    if not a.flags.writeable:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return torch.from_numpy(a).to(dev).float()
     return torch.from_numpy(a).to(dev).float()
 
 
-def _cached(key, owner, build):
+def _cached(key, build):
+    """`build()` once per key.  Keys hold content digests, so there is nothing to invalidate; old entries fall out
+    of the 8-entry LRU (or `clear_caches()`)."""
     hit = _REF_CACHE.get(key)
-    if hit is not None and hit[0]() is owner:
+    if hit is not None:
         _REF_CACHE.move_to_end(key)
-        return hit[1]
+        return hit
     val = build()
-    try:
-        ref = weakref.ref(owner)
-    except TypeError:
-        return val
-    _REF_CACHE[key] = (ref, val)
+    _REF_CACHE[key] = val
     while len(_REF_CACHE) > 8:
         _REF_CACHE.popitem(last=False)
     return val
 
 
 def clear_caches() -> None:
+    """Forget every cached device object, staging buffer and pooled page-locked result buffer."""
     _DEV_CACHE.clear()
     _REF_CACHE.clear()
+    _PIN_BUFS.clear()
+    _POOL.clear()
 
 
 # ----------------------------------------------------------------------------- project
@@ -166,14 +227,16 @@ def _project(adata_query, adata_ref, loadings_key, use_genes_column, dev, after_
             "%i out of %i genes from the reference are missing in the query dataset or have zero std in the reference, "
             "their expressions in the query will be set to zero", int((~present).sum()), genes.shape[0])
 
+    means_all = np.asarray(adata_ref.var["mean"])
+    pcs = np.asarray(adata_ref.varm[loadings_key])
+
     def build():
-        means = np.array(adata_ref.var["mean"]) if hv is None else np.array(adata_ref.var["mean"])[hv]
-        pcs = np.asarray(adata_ref.varm[loadings_key])
+        means = np.array(means_all) if hv is None else np.array(means_all)[hv]
         U = pcs if hv is None else pcs[np.asarray(adata_ref.var_names.isin(genes))]  # `_utils.py:307`
         return engine.make_loadings(means, stds, U, present, dev)
 
-    ld = _cached(("loadings", id(adata_ref), loadings_key, use_genes_column, str(dev), present.tobytes()),
-                 adata_ref, build)
+    # key = full content of everything the device operands are built from (in-place edits of adata_ref are noticed)
+    ld = _cached(("loadings", str(dev), content_digest(means_all, stds, hv, present, pcs)), build)
     G = ld.G
     X = adata_query.X
     N = X.shape[0]
@@ -234,22 +297,36 @@ def _inv_sigma(sigma, K: int, dev) -> torch.Tensor:
 class _PinnedPool:
     """Page-locked host buffers for results.  A device->host copy into pageable memory runs at a few GB/s;
     into pinned memory it runs at PCIe speed and asynchronously.  The numpy arrays handed to the user are
-    views of pool buffers; a buffer goes back to the pool when its array is garbage collected."""
+    views of pool buffers; a buffer goes back to the pool when its array is garbage collected.
+
+    Buffers are sized to the request rounded up to 2 MiB (not to a power of two: an N x K result of 10M cells
+    must not pin twice its size), and the pool keeps at most `settings.pinned_pool_bytes` of FREE buffers —
+    what does not fit is released to the OS instead of staying page-locked."""
+
+    GRAIN = 2 << 20
 
     def __init__(self):
         self.free: dict[int, list] = {}
+        self.free_bytes = 0
 
     def take(self, nbytes: int) -> torch.Tensor:
-        size = 1 << max(12, int(nbytes - 1).bit_length())  # power-of-two size classes
+        size = max(self.GRAIN, (int(nbytes) + self.GRAIN - 1) // self.GRAIN * self.GRAIN)
         bucket = self.free.get(size)
         if bucket:
+            self.free_bytes -= size
             return bucket.pop()
         return torch.empty(size, dtype=torch.uint8).pin_memory()
 
     def give(self, buf: torch.Tensor) -> None:
-        bucket = self.free.setdefault(buf.numel(), [])
-        if len(bucket) < 4:
-            bucket.append(buf)
+        size = buf.numel()
+        if self.free_bytes + size > settings.pinned_pool_bytes:
+            return   # dropped: the page-locked memory is freed with the tensor
+        self.free.setdefault(size, []).append(buf)
+        self.free_bytes += size
+
+    def clear(self) -> None:
+        self.free.clear()
+        self.free_bytes = 0
 
 
 _POOL = _PinnedPool()
@@ -307,7 +384,13 @@ def _run_soft_kmeans(adata_ref, ref_basis: str = "X_pca", K: int | None = None, 
     dev = engine.require_cuda(settings.device)
     with torch.cuda.device(dev):
         Z = _device_copy(adata_ref.obsm[ref_basis], dev)
-        C, _ = engine.kmeans(Z, K, n_init=10, max_iter=25, seed=random_state)
+        # Under torch.distributed every rank holds the same reference but would draw its own random centres: the
+        # all-reduced MoE statistics would then mix unrelated clusterings.  Rank 0 clusters, everyone gets its centres.
+        if _dist.rank() == 0:
+            C, _ = engine.kmeans(Z, K, n_init=10, max_iter=25, seed=random_state)
+        else:
+            C = torch.empty((K, Z.shape[1]), device=dev, dtype=torch.float64)
+        C = _dist.broadcast(C.contiguous(), src=0)
         Y = C / C.norm(dim=1, keepdim=True)
         R = engine.assign(Z, Y.float().contiguous(), _inv_sigma(sigma, K, dev))     # [N, K]
         Rt = R.double().T.contiguous()                                             # stored [K, N], as Harmony's R
@@ -496,6 +579,9 @@ def per_cluster_confidence(
     (`engine.group_moments`); the reference slices the AnnData once per cluster.  The G small d x d systems are
     finished on the host with `np.linalg.inv`, so a singular covariance raises `LinAlgError` as the reference does.
 
+    Under `torch.distributed` the moments are those of THIS rank's shard (no reduction across ranks): call it
+    on the whole query.
+
     Quirk: the reference's per-cell broadcast (`tl.py:179`, `dists[x[0]]`) relies on positional `Series[0]`, which
     raises `KeyError` under pandas >= 3; the intended result (every cell gets its cluster's score) is written."""
     assert "harmony" in adata_ref.uns, \
@@ -506,7 +592,9 @@ def per_cluster_confidence(
     centroids = C_ / Nr[..., np.newaxis]
     centroids_norm = centroids / np.linalg.norm(centroids, ord=2, axis=1, keepdims=True)
 
-    grouped = adata_query.obs.groupby(cluster_key)
+    # observed=True: with categorical keys pandas < 3 would otherwise list the full cartesian product in size().index
+    # while ngroup() numbers the observed groups only
+    grouped = adata_query.obs.groupby(cluster_key, observed=True, sort=True)
     labels = grouped.size().index
     codes_h = grouped.ngroup().to_numpy()
     G = len(labels)
@@ -574,26 +662,33 @@ def _label_columns(adata_ref, ref_labels):
     return [y], False
 
 
-def _encode_labels(adata_ref, col: pd.Series, dev):
-    """sklearn's `classes_` (sorted unique labels) and the integer code of every reference cell, on the
-    device.  Cached per reference: encoding 500k strings costs more than the whole GPU search.  The cache key
-    carries a fingerprint of the column (length + hash of ~1k evenly spaced values) so edits are noticed."""
-    n = len(col)
-    probe = col.iloc[:: max(1, n // 1024)]
-    fp = (n, int(pd.util.hash_pandas_object(probe, index=False).sum()))
-
-    def build():
-        values = np.asarray(col)
-        try:
-            inv, classes = pd.factorize(values, sort=True)
+def _encode_labels(col: pd.Series, dev):
+    """sklearn's `classes_` (sorted unique labels) and the integer code of every reference cell, on the device.
+    Re-done on every call (no cache: an edited label column must never transfer old labels); the dtype-specific
+    paths keep that cheap — categorical columns (what AnnData stores) are remapped from their codes in ~3 ms for
+    500k cells, Arrow-backed strings factorize in ~8 ms, object columns in ~20 ms."""
+    inv = classes = None
+    try:
+        if isinstance(col.dtype, pd.CategoricalDtype):
+            codes = col.cat.codes.to_numpy()
+            if (codes < 0).any():
+                raise ValueError("missing labels")
+            present = np.unique(codes)
+            cats = np.asarray(col.cat.categories)[present]
+            order = np.argsort(cats, kind="stable")          # sklearn: np.unique(y) order
+            lut = np.zeros(len(col.cat.categories), dtype=np.int32)
+            lut[present[order]] = np.arange(len(order), dtype=np.int32)
+            inv, classes = lut[codes], cats[order]
+        else:
+            inv, classes = pd.factorize(col, sort=True)
             classes = np.asarray(classes)
+            if classes.dtype.kind in "OUT" or isinstance(col.dtype, pd.StringDtype):
+                classes = classes.astype(object)
             if (inv < 0).any():
                 raise ValueError("missing labels")
-        except (TypeError, ValueError):
-            classes, inv = np.unique(values, return_inverse=True)
-        return classes, torch.from_numpy(inv.astype(np.int32)).to(dev)
-
-    return _cached(("labels", id(adata_ref), col.name, fp, str(dev)), adata_ref, build)
+    except (TypeError, ValueError):
+        classes, inv = np.unique(np.asarray(col), return_inverse=True)
+    return classes, torch.from_numpy(np.ascontiguousarray(inv, dtype=np.int32)).to(dev)
 
 
 def _decode_labels(classes: np.ndarray, lab: np.ndarray, index: pd.Index):
@@ -647,15 +742,16 @@ def transfer_labels_kNN(
         query_labels = ref_labels
 
     with torch.cuda.device(dev):
-        index = _cached(("knn", id(ref_emb), str(dev)), ref_emb if not isinstance(ref_emb, torch.Tensor) else adata_ref,
-                        lambda: engine.knn_fit(_device_copy(ref_emb, dev)))
+        # the packed index is found again by the CONTENT of the reference embedding (a replaced or edited obsm array
+        # gets a new index)
+        index = _cached(("knn", str(dev), content_digest(ref_emb)), lambda: engine.knn_fit(_device_copy(ref_emb, dev)))
         Q = _device_copy(adata_query.obsm[query_basis], dev)
         idx, dist2, n_repaired = engine.knn_search_certified(index, Q, k, settings.knn_method)
         if n_repaired:
             logger.debug("kNN: %d query rows re-run with the FP32 scan", n_repaired)
         preds, confs = [], []
         for col in label_cols:
-            classes, codes = _encode_labels(adata_ref, col, dev)  # sklearn: classes_ = sorted unique labels
+            classes, codes = _encode_labels(col, dev)  # sklearn: classes_ = sorted unique labels
             lab, conf = engine.vote(idx, codes, want_conf=confidence_key is not None,
                                     dist2=dist2 if params["weights"] == "distance" else None)
             preds.append((classes, _to_host(lab)))

@@ -767,3 +767,70 @@ def test_distance_weighted_vote_matches_sklearn(cuda_device):
     proba = knn.predict_proba(emb.astype(np.float64)).max(axis=1)
     assert (np.asarray(query.obs["cell_type"]) == want).mean() >= 0.999
     np.testing.assert_allclose(np.asarray(query.obs["p"]), proba, rtol=2e-4, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------ caches follow in-place edits of adata_ref
+def test_in_place_edits_of_the_reference_are_noticed(cuda_device):
+    """Reference-side device objects are cached by CONTENT: relabelling, replacing embedding rows or re-scaling the
+    gene statistics of `adata_ref` in place between two calls must give the results of the edited reference."""
+    quiet()
+    query, ref = synth.small_case(N=900, M=3000, G=256, d=20, K=30, L=6, levels=(1,), seed=5)
+    tl.clear_caches()
+
+    def run(q):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            tl.map_embedding(q, ref, key=None)
+            tl.transfer_labels_kNN(q, ref, "cell_type", n_neighbors=5)
+
+    def oracle(q):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            so.map_embedding(q, ref, key=None)
+            so.transfer_labels_knn(q, ref, "cell_type", n_neighbors=5)
+
+    q0 = copy.deepcopy(query)
+    run(q0)
+    first = np.asarray(q0.obs["cell_type"], dtype=str)
+
+    # 1. a FEW labels edited in place (the round-1 fingerprint sampled ~1k of them): cells of one type renamed
+    col = ref.obs["cell_type"]
+    victim = first[0]
+    ref.obs["cell_type"] = np.where(np.asarray(col, dtype=str) == victim, "renamed", np.asarray(col, dtype=str))
+    q1 = copy.deepcopy(query)
+    run(q1)
+    got = np.asarray(q1.obs["cell_type"], dtype=str)
+    assert (got[first == victim] == "renamed").all() and victim not in set(got)
+
+    # 2. the reference embedding edited in place (same ndarray object): rows reversed
+    emb = ref.obsm["X_pca_harmony"]
+    emb[:] = emb[::-1].copy()
+    q2, o2 = copy.deepcopy(query), copy.deepcopy(query)
+    run(q2)
+    oracle(o2)
+    assert (np.asarray(q2.obs["cell_type"], dtype=str) == np.asarray(o2.obs["cell_type"], dtype=str)).mean() >= 0.999
+    assert (np.asarray(q2.obs["cell_type"], dtype=str) != got).mean() > 0.3   # the edit really changed the answer
+
+    # 3. gene statistics and loadings edited in place (re-scaling / re-running PCA keeps shapes and key names)
+    ref.var["mean"] = np.asarray(ref.var["mean"]) * 1.5 + 0.1
+    ref.varm["PCs"][:] = ref.varm["PCs"][:, ::-1].copy()
+    q3, o3 = copy.deepcopy(query), copy.deepcopy(query)
+    run(q3)
+    oracle(o3)
+    assert row_rel_err(q3.obsm["X_pca_reference"], o3.obsm["X_pca_reference"]) < EMB_TOL
+    assert row_rel_err(q3.obsm["X_pca_reference"], q2.obsm["X_pca_reference"]) > 1e-2
+
+
+def test_in_place_edit_of_query_embedding_between_calls(cuda_device):
+    """`transfer_labels_kNN` reads `obsm[query_basis]` as it is NOW, not the device copy `map_embedding` produced."""
+    quiet()
+    query, ref = synth.small_case(N=700, M=2500, G=256, d=20, K=30, L=6, levels=(1,), seed=6)
+    tl.clear_caches()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        tl.map_embedding(query, ref, key=None)
+        emb = query.obsm["X_pca_harmony"]
+        emb[:] = np.asarray(ref.obsm["X_pca_harmony"])[: emb.shape[0]]      # every query cell sits ON a reference cell
+        tl.transfer_labels_kNN(query, ref, "cell_type", n_neighbors=1)
+    want = np.asarray(ref.obs["cell_type"], dtype=str)[: emb.shape[0]]
+    assert (np.asarray(query.obs["cell_type"], dtype=str) == want).all()

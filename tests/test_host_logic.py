@@ -274,3 +274,94 @@ def test_c_program_links_and_calls_the_library(tmp_path, built_library):
                     "-lsymphony_b200", f"-Wl,-rpath,{libdir}"], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
     assert int(out[0]) > 0 and int(out[1]) == 100   # host-only entry points: no GPU needed
+
+
+# ------------------------------------------------------------------------------ round 2: host logic without N-row string work
+def test_design_codes_categorical_with_unused_and_missing_levels():
+    """Categorical columns go through their codes: unused categories give no column, int categories sort as
+    strings; a missing value becomes its own level "nan" (pandas < 3 `astype(str)` semantics for NaN)."""
+    rng = np.random.default_rng(3)
+    n = 300
+    obs = pd.DataFrame({
+        "a": pd.Categorical(rng.choice(["u", "v"], n), categories=["z_unused", "v", "u"]),
+        "b": pd.Categorical(rng.choice([10, 2, 9], n)),
+        "c": pd.Series(rng.choice(["p", "q", None], n), dtype=object),
+        "d": pd.Categorical(rng.choice(["m", "n", None], n)),
+    })
+    q = AnnDataLite(np.zeros((n, 2), dtype=np.float32), obs=obs)
+    codes, levels = _design.batch_codes(q, ["c", "d"])
+    assert levels == [["nan", "p", "q"], ["m", "n", "nan"]]
+    assert (codes[0] == 0).sum() == obs["c"].isna().sum() and (codes[1] == 2).sum() == obs["d"].isna().sum()
+    for key in ("a", "b", ["b", "a"]):
+        codes, levels = _design.batch_codes(q, key)
+        phi_, _ = so.build_design(q, key, None)
+        n_levels = [len(lv) for lv in levels]
+        mine = np.zeros_like(phi_)
+        mine[0] = 1
+        off = 1
+        for v, lv in enumerate(n_levels):
+            mine[off + codes[v], np.arange(n)] = 1
+            off += lv
+        np.testing.assert_array_equal(mine, phi_)
+
+
+def test_design_codes_never_stringify_all_rows(monkeypatch):
+    """1M cells: the codes come from factorize / cat.codes; `Series.astype(str)` only ever sees the distinct values."""
+    n = 1_000_000
+    rng = np.random.default_rng(0)
+    obs = pd.DataFrame({"batch": pd.Categorical.from_codes(rng.integers(0, 100, n), [f"b{i}" for i in range(100)]),
+                        "num": rng.integers(0, 7, n)})
+    q = AnnDataLite(np.zeros((n, 1), dtype=np.float32), obs=obs)
+    longest = [0]
+    orig = pd.Series.astype
+
+    def spy(self, dtype, *a, **k):
+        if dtype is str:
+            longest[0] = max(longest[0], len(self))
+        return orig(self, dtype, *a, **k)
+
+    monkeypatch.setattr(pd.Series, "astype", spy)
+    codes, levels = _design.batch_codes(q, ["batch", "num"])
+    assert longest[0] <= 100
+    assert levels[0] == sorted(f"b{i}" for i in range(100)) and levels[1] == [str(i) for i in range(7)]
+    np.testing.assert_array_equal(np.asarray(levels[0], dtype=object)[codes[0]], np.asarray(obs["batch"].astype(object)))
+    np.testing.assert_array_equal(codes[1], obs["num"].to_numpy())
+
+
+def test_content_digest_notices_in_place_edits():
+    a = np.random.default_rng(0).standard_normal((300_000, 30))          # 72 MB: goes through the threaded path
+    d0 = tl.content_digest(a)
+    assert tl.content_digest(a) == d0 and tl.content_digest(a.copy()) == d0
+    a[123_456, 7] += 1e-9
+    d1 = tl.content_digest(a)
+    assert d1 != d0
+    a[[0, 1]] = a[[1, 0]]                                                   # a row swap is a change too
+    assert tl.content_digest(a) != d1
+    assert tl.content_digest(a.astype(np.float32)) != tl.content_digest(a)
+    assert tl.content_digest(a[:, :15]) == tl.content_digest(np.ascontiguousarray(a[:, :15]))
+    assert tl.content_digest(None, np.arange(3)) != tl.content_digest(np.arange(3), None)
+    lab = np.array(["x", "y", "x"], dtype=object)
+    e0 = tl.content_digest(lab)
+    lab[1] = "z"
+    assert tl.content_digest(lab) != e0
+
+
+@pytest.mark.parametrize("kind", ["category", "str", "object", "int", "category_unused", "bool"])
+def test_encode_labels_equals_numpy_unique(kind):
+    rng = np.random.default_rng(1)
+    n = 5000
+    if kind in ("int",):
+        col = pd.Series(rng.choice([7, -3, 100, 12], n))
+    elif kind == "bool":
+        col = pd.Series(rng.choice([True, False], n))
+    else:
+        vals = rng.choice(["T cell", "B cell", "b cell", "NK", "10", "2"], n)
+        col = pd.Series(vals, dtype=object if kind == "object" else None)
+        if kind == "category":
+            col = col.astype("category")
+        if kind == "category_unused":
+            col = pd.Series(pd.Categorical(vals, categories=["zz", "NK", "10", "2", "b cell", "B cell", "T cell", "aa"]))
+    classes, codes = tl._encode_labels(col, "cpu")
+    want_classes, want_inv = np.unique(np.asarray(col), return_inverse=True)   # sklearn: classes_ = np.unique(y)
+    assert list(classes) == list(want_classes)
+    np.testing.assert_array_equal(codes.numpy(), want_inv)

@@ -24,5 +24,6 @@ wt = max(v[4], 1)
 print(f"knn_search {t0.elapsed_time(t1):.1f} ms; selection warp-tiles {v[4]}")
 print(f"  per warp-tile cycles: wait_full {v[0]/wt:.0f}  ld {v[1]/wt:.0f}  examine {v[2]/wt:.0f}  flush {v[3]/wt:.0f}  total {(v[0]+v[1]+v[2]+v[3])/wt:.0f}")
 print(f"  warp-tiles with a walk {v[5]/wt:.3f}; lane hits per warp-tile {v[6]/wt:.3f}")
+print(f"  examine: mins + vote {v[7]/wt:.0f} cycles per warp-tile; inside tc_hits {v[13]/max(v[14],1):.0f} cycles per visiting lane ({v[14]/wt:.3f} visits per warp-tile)")
 it = max(v[12], 1)
 print(f"  issuer per tile cycles: wait ref tile {v[8]/it:.0f}  wait free acc {v[9]/it:.0f}  wait turn {v[10]/it:.0f}  issue {v[11]/it:.0f}")
