@@ -532,7 +532,7 @@ def ref_anndata(st):
     w = st["w"]
     if w.get("knn_only"):
         import torch
-        X8, c8 = torch.zeros((8, 8), device=st["Zref"].device), torch.zeros((1, 8), dtype=torch.int32, device=st["Zref"].device)
+        X8, c8 = torch.zeros((8, w["G"]), device=st["Zref"].device), torch.zeros((1, 8), dtype=torch.int32, device=st["Zref"].device)
     else:
         X8, c8 = st["X"][:8], st["codes"][:, :8]
     _, ref = synth.to_anndata(st["model"], st["Zref"], st["comp"], st["C"], st["Nr"], X8, c8, w["K"], seed=0)

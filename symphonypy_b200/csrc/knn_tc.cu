@@ -22,7 +22,7 @@
 // query tile (warp 1 owns the TMEM allocation); warps 4-11 = selection, thread <-> query row <-> TMEM lane.  A
 // selection thread pulls the 128 scores of its row with four tcgen05.ld, hands the accumulator back, folds the
 // scores with 3-input min against its row's kc-th best (one straight-line block), and only on a hit locates the
-// candidates and updates the row's 4-ary heap in shared memory.
+// candidate groups and appends them to the row's buffer in shared memory (compacted to the kc best when full).
 // The scan over-selects (kc = k + 8); the float64 re-rank in knn.cu certifies the margin with the scores recorded
 // here (error bound per row: measured FP16 rounding residuals, or 6e-5 relative for BF16x3) and flags the rows
 // that have to be re-run with the next tier.
@@ -213,8 +213,9 @@ constexpr uint32_t TC_IDESC_F16 = (1u << 4) | ((TC_BN >> 3) << 17) | ((TC_BM >> 
 
 #ifdef TC_PROFILE
 // Cycle accounting of the scan (build with -DTC_PROFILE; read back with sym_debug_tc_profile):
-//  [0] selection: wait for a finished accumulator   [1] tcgen05.ld + wait   [2] examine (4 chunks)   [3] flush
-//  [4] selection warp-tiles   [5] warp-tiles in which some lane walked a chunk   [6] lane heap updates
+//  [0] selection: wait for a finished accumulator   [1] tcgen05.ld + wait   [2] examine (mins, park)   [3] drain
+//  [4] selection warp-tiles   [5] warp-tiles in which some lane had a hit   [6] lanes with a hit   [7] mins + vote
+//  [14] periodic drains   [15] early drains (full FIFO)
 //  [8] issuer: wait reference tile   [9] wait free accumulator   [10] wait turn   [11] issue   [12] issuer tiles
 __device__ unsigned long long tc_prof[16];
 #define TC_CLK(x) const long long x = clock64()
@@ -235,7 +236,26 @@ __device__ unsigned long long tc_prof[16];
 //
 // Selection per tile: four tcgen05.ld (128 scores per row), the accumulator handed back, 16 independent
 // 3-input-min chains over groups of 8, one compare against the row's kc-th best; only on a hit are the groups
-// examined and the (single, out-of-line) heap update called.
+// located and appended to the row's candidate buffer.
+
+__device__ __forceinline__ float tc_min8(const uint32_t *v) {
+    float m = fmin3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
+    m = fmin3(m, __uint_as_float(v[3]), __uint_as_float(v[4]));
+    m = fmin3(m, __uint_as_float(v[5]), __uint_as_float(v[6]));
+    return fminf(m, __uint_as_float(v[7]));
+}
+
+// (Padding needs no bounds check: padded reference rows carry ||r||^2 = +inf and padded query rows are all-zero
+// operands, so their scores are +inf / NaN and never pass `s < thr`.)
+// The common case (no hit anywhere in the tile) is one straight-line block: the group minima of ALL chunks of
+// the tile (16 independent 3-input-min chains for 128 scores), one overall minimum, one compare, one vote.
+struct TcMins {
+    float g0, g1, g2, g3;
+};
+__device__ __forceinline__ TcMins tc_mins32(const uint32_t (&v)[32]) {
+    return TcMins{tc_min8(v), tc_min8(v + 8), tc_min8(v + 16), tc_min8(v + 24)};
+}
+__device__ __forceinline__ float tc_min4(const TcMins &m) { return fminf(fmin3(m.g0, m.g1, m.g2), m.g3); }
 
 // The row's kc best candidates form a 4-ary MAX-HEAP of 64-bit keys (score bits | position) in shared memory;
 // the root is the kc-th best = the row's threshold.  A hit replaces the root and sifts down: ~log4(kc) levels of
@@ -276,93 +296,55 @@ __device__ __forceinline__ float tc_insert(unsigned long long *heap, int kc, flo
     return root;
 }
 
-__device__ __forceinline__ float tc_min8(const uint32_t *v) {
-    float m = fmin3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
-    m = fmin3(m, __uint_as_float(v[3]), __uint_as_float(v[4]));
-    m = fmin3(m, __uint_as_float(v[5]), __uint_as_float(v[6]));
-    return fminf(m, __uint_as_float(v[7]));
-}
-
-// (Padding needs no bounds check: padded reference rows carry ||r||^2 = +inf and padded query rows are all-zero
-// operands, so their scores are +inf / NaN and never pass `s < thr`.)
-// The common case (no hit anywhere in the tile) is one straight-line block: the group minima of ALL chunks of
-// the tile (16 independent 3-input-min chains for 128 scores), one overall minimum, one compare, one vote.
-struct TcMins {
-    float g0, g1, g2, g3;
-};
-__device__ __forceinline__ TcMins tc_mins32(const uint32_t (&v)[32]) {
-    return TcMins{tc_min8(v), tc_min8(v + 8), tc_min8(v + 16), tc_min8(v + 24)};
-}
-__device__ __forceinline__ float tc_min4(const TcMins &m) { return fminf(fmin3(m.g0, m.g1, m.g2), m.g3); }
 
 // ---- what is selected: GROUPS of 8 consecutive reference positions, keyed by the group's minimum score ----
 // The fast path already has the minimum of every group of 8 scores (the leaves of its min tree).  Selecting groups
-// instead of single references means the slow path never has to look INSIDE a group (registers cannot be indexed:
-// round 1 walked the 8 scores of a hit group through a 16-way switch, ~250 instructions and 4.5 KB of code per
-// event): a hit is (group minimum, first position of the group), read off the 16 minima by a select tree.  The
-// float64 re-rank expands each of a row's kc candidate groups into its 8 members and ranks those whose exact score
-// is below the row's threshold.  The certificate is unchanged: a reference outside the candidate groups has
+// instead of single references means nothing ever has to look INSIDE a group (registers cannot be indexed: round 1
+// walked the 8 scores of a hit group through a 16-way switch, ~250 instructions and 4.5 KB of code per event).
+// The float64 re-rank expands each of a row's kc candidate groups into its 8 members and ranks those whose exact
+// score is below the row's threshold.  The certificate is unchanged: a reference outside the candidate groups has
 // score >= its group's minimum >= the row's final threshold.
 //
-// ---- hits are queued, not inserted where they are found ----
-// Round 1 updated the row's heap right away (a ~400-cycle update with 1-2 of 32 lanes active, on the critical
-// path of a warp that three other warps wait for).  Now a hit is appended to the lane's own small queue in shared
-// memory (one 8-byte store) and the queues of all 32 rows of the warp are drained TOGETHER every `flush` tiles (or
-// when a lane's queue is full): the same heap updates with most lanes active at once.  The threshold of a row is
-// stale by what sits in its queue (never too small): rejected scores are >= the threshold in force at that time
-// >= the final threshold, which is all the certificate needs.  A queued score is re-checked against the root when
-// it is drained — tc_insert must never be given a score that is not below the current root, it would evict a
-// better candidate and void the certificate.
-//
-// ---- code size ----
-// Measured (profiles/r2a_*): rarely executed code ran at 10-20 cycles per instruction — the kernel is ~32 KB of
-// SASS, the selection warps share a ~6 KB L0 instruction cache with the issuer, and every visit to the slow path
-// re-fetched it.  The slow path is therefore written for FEW BYTES, not few executed instructions: loops are kept
-// rolled (`#pragma unroll 1`), the drain is one out-of-line function, nothing is specialised per group.
-#ifndef TC_QCAP
-#define TC_QCAP 8                 // queue entries per row
-#endif
-constexpr int TC_GROUP = 8;       // reference positions per candidate group
+// ---- a hit is parked raw; all rows of the CTA are brought up to date at the SAME tiles ----
+// Measured (profiles/r2b, ncu source view): every instruction of a selection warp costs 5-10 cycles (two warps per
+// scheduler, dependent chains, ~15 cycles per taken branch), and the four warps that share an accumulator advance
+// at the pace of the slowest.  A warp has a hit in 26 % of its tiles, so in 70 % of the tiles one of the four is on
+// its slow path — whatever that path costs sits on everybody's critical path (a located + appended hit: ~85
+// instructions, ~800 cycles; 36 % of a selection warp's time was spent waiting for an accumulator).
+// So the hit path does next to nothing: a lane whose row minimum is below its threshold stores the 16 group
+// minima of the tile (four 16-byte stores) and the tile's first position into its row's small FIFO.  Every
+// `period` tiles — the same tiles for every warp of the CTA — all rows are drained, lanes in lock-step: the parked
+// minima are compared with the threshold and the hit groups go into the row's heap.  Between drains the threshold
+// is stale (never too small: rejected scores are >= the threshold in force >= the final one, which is all the
+// certificate needs; a parked score is re-checked against the root when it is drained — tc_insert must never be
+// given a score that is not below the current root).  A full FIFO drains the whole warp early.
+constexpr int TC_GROUP = 8;        // reference positions per candidate group
+constexpr int TC_FIFO_WORDS = 20;  // one parked tile of a row: 16 group minima, the tile's first position, padding
+// row stride of the FIFOs in words: an odd number of 16-byte units, so that the 128-bit accesses of 8 consecutive
+// rows fall into 8 different bank groups
+__host__ __device__ inline int tc_fifo_stride(int depth) { return 4 * ((depth * (TC_FIFO_WORDS / 4)) | 1); }
 
-__device__ __noinline__ float tc_drain(unsigned long long *heap, int kc, const unsigned long long *queue, int qn,
-                                       float thr) {
+__device__ __noinline__ float tc_drain(unsigned long long *heap, int kc, const float *fifo, int cnt, float thr) {
 #pragma unroll 1
-    for (int j = 0; j < qn; ++j) {
-        const unsigned long long e = queue[j];
-        const float s = __uint_as_float((uint32_t)(e >> 32));
-        if (s < thr) thr = tc_insert(heap, kc, s, (uint32_t)e);
-    }
-    return thr;
-}
-
-// Slow path of a tile for ONE lane whose row has a group minimum below its threshold (typically one lane of the
-// warp, one group): mask of the hit groups, then per hit a 15-select tree over the 16 minima and one queue append.
-__device__ __forceinline__ void tc_hits(const TcMins &m0, const TcMins &m1, const TcMins &m2, const TcMins &m3,
-                                        float &thr, uint32_t ref0, unsigned long long *heap, int kc,
-                                        unsigned long long *queue, int &qn) {
-    unsigned hm = 0;
+    for (int e = 0; e < cnt; ++e) {
+        const float *f = fifo + e * TC_FIFO_WORDS;
+        const float4 a = *reinterpret_cast<const float4 *>(f), b = *reinterpret_cast<const float4 *>(f + 4);
+        const float4 c = *reinterpret_cast<const float4 *>(f + 8), d = *reinterpret_cast<const float4 *>(f + 12);
+        const uint32_t ref0 = __float_as_uint(f[16]);
+        unsigned hm = 0;
 #define TC_BIT(GV, B) hm |= (GV < thr) ? (1u << (B)) : 0u;
-    TC_BIT(m0.g0, 0) TC_BIT(m0.g1, 1) TC_BIT(m0.g2, 2) TC_BIT(m0.g3, 3)
-    TC_BIT(m1.g0, 4) TC_BIT(m1.g1, 5) TC_BIT(m1.g2, 6) TC_BIT(m1.g3, 7)
-    TC_BIT(m2.g0, 8) TC_BIT(m2.g1, 9) TC_BIT(m2.g2, 10) TC_BIT(m2.g3, 11)
-    TC_BIT(m3.g0, 12) TC_BIT(m3.g1, 13) TC_BIT(m3.g2, 14) TC_BIT(m3.g3, 15)
+        TC_BIT(a.x, 0) TC_BIT(a.y, 1) TC_BIT(a.z, 2) TC_BIT(a.w, 3) TC_BIT(b.x, 4) TC_BIT(b.y, 5) TC_BIT(b.z, 6) TC_BIT(b.w, 7)
+        TC_BIT(c.x, 8) TC_BIT(c.y, 9) TC_BIT(c.z, 10) TC_BIT(c.w, 11) TC_BIT(d.x, 12) TC_BIT(d.y, 13) TC_BIT(d.z, 14) TC_BIT(d.w, 15)
 #undef TC_BIT
 #pragma unroll 1
-    while (hm) {
-        const int gi = __ffs(hm) - 1;
-        hm &= hm - 1;
-        const bool b0 = gi & 1, b1 = gi & 2, b2 = gi & 4, b3 = gi & 8;
-        const float s0 = b0 ? m0.g1 : m0.g0, s1 = b0 ? m0.g3 : m0.g2, s2 = b0 ? m1.g1 : m1.g0, s3 = b0 ? m1.g3 : m1.g2;
-        const float s4 = b0 ? m2.g1 : m2.g0, s5 = b0 ? m2.g3 : m2.g2, s6 = b0 ? m3.g1 : m3.g0, s7 = b0 ? m3.g3 : m3.g2;
-        const float t0 = b1 ? s1 : s0, t1 = b1 ? s3 : s2, t2 = b1 ? s5 : s4, t3 = b1 ? s7 : s6;
-        const float u0 = b2 ? t1 : t0, u1 = b2 ? t3 : t2;
-        const float gm = b3 ? u1 : u0;
-        if (qn == TC_QCAP) {   // (the mask may now hold groups that are no longer hits: harmless, re-checked at the drain)
-            thr = tc_drain(heap, kc, queue, qn, thr);
-            qn = 0;
+        while (hm) {
+            const int gi = __ffs(hm) - 1;
+            hm &= hm - 1;
+            const float gm = f[gi];
+            if (gm < thr) thr = tc_insert(heap, kc, gm, ref0 + (uint32_t)(gi * TC_GROUP));
         }
-        queue[qn++] = ((unsigned long long)__float_as_uint(gm) << 32) | (ref0 + (uint32_t)(gi * TC_GROUP));
     }
+    return thr;
 }
 
 template <int TC_QT>
@@ -370,16 +352,17 @@ __global__ void __launch_bounds__(128 + 128 * TC_QT, 1)
 knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char *__restrict__ rpack, int64_t N,
                    const int32_t *__restrict__ q_perm, const int32_t *__restrict__ q_code,
                    const int32_t *__restrict__ cl_tile, int64_t M, int kp, int kc, int stages, int nbuf,
-                   int tiles_per_split, int ntiles_all, int ss_mode, uint32_t idesc, int flush_mask,
+                   int tiles_per_split, int ntiles_all, int ss_mode, uint32_t idesc, int fifo_depth, int period_mask,
                    unsigned long long *__restrict__ cand_out, float *__restrict__ thr_out) {
     extern __shared__ __align__(1024) unsigned char smraw[];
     const uint32_t tile_bytes = (uint32_t)tc_tile_bytes(kp);
-    const int ks = tc_heap_stride(kc);  // odd row stride: the 32 rows of a warp hit 32 different banks
     unsigned char *r_s = smraw;                                        // [stages][tile_bytes]
     // one selection warp per (query tile, TMEM lane quadrant) examines all 128 columns of a tile
-    unsigned long long *heap_s = (unsigned long long *)(r_s + (size_t)stages * tile_bytes);  // [TC_QT][TC_BM][ks]
-    unsigned long long *queue_s = heap_s + (size_t)TC_QT * ks * TC_BM;                       // [TC_QT][TC_BM][TC_QCAP]
-    uint64_t *bars = (uint64_t *)(queue_s + (size_t)TC_QT * TC_BM * TC_QCAP);
+    const int ks = tc_heap_stride(kc);       // odd row stride: the 32 rows of a warp hit 32 different banks
+    const int fs = tc_fifo_stride(fifo_depth);
+    float *fifo_s = (float *)(r_s + (size_t)stages * tile_bytes);                            // [TC_QT][TC_BM][fs]
+    unsigned long long *heap_s = (unsigned long long *)(fifo_s + (size_t)TC_QT * TC_BM * fs);  // [TC_QT][TC_BM][ks]
+    uint64_t *bars = (uint64_t *)(heap_s + (size_t)TC_QT * TC_BM * ks);
     uint64_t *r_full = bars;                      // [TC_MAX_STAGES]
     uint64_t *r_empty = r_full + TC_MAX_STAGES;   // [TC_MAX_STAGES]
     uint64_t *t_full = r_empty + TC_MAX_STAGES;   // [4]  accumulator buffers, used in rotation by all query tiles
@@ -490,9 +473,9 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
 #endif
         for (int i = 0; i < ntiles; ++i) {
             TC_CLK(c0);
-            mbar_wait(&r_full[s], ph);
+            mbar_wait_handoff(&r_full[s], ph);
             TC_CLK(c1);
-            mbar_wait(&t_empty[buf], (use & 1) ^ 1);
+            mbar_wait_handoff(&t_empty[buf], (use & 1) ^ 1);
             TC_CLK(c2);
             if (ordered) {
                 const uint32_t seq = (uint32_t)(i * TC_QT + q);
@@ -533,22 +516,22 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
         // ===== selection =====
         const int qt = (warp - 4) >> 2, quad = warp & 3;
         const int row = quad * 32 + lane;
-        unsigned long long *heap = heap_s + ((size_t)qt * TC_BM + row) * ks;         // this thread's row
-        unsigned long long *queue = queue_s + ((size_t)qt * TC_BM + row) * TC_QCAP;  // its queue of hits not yet inserted
+        unsigned long long *heap = heap_s + ((size_t)qt * TC_BM + row) * ks;   // this thread's row: its kc best groups
+        float *fifo = fifo_s + ((size_t)qt * TC_BM + row) * fs;                // and its parked tiles
         float thr = INFINITY;
-        int qn = 0;
+        int qn = 0;                                                            // parked tiles
         const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + acc0;
         int buf = qt % nbuf, use = qt / nbuf;   // chain (i, qt) = sequence number i*QT + qt
         int t_cur = t_home;
 #ifdef TC_PROFILE
-        long long prof_0 = 0, prof_1 = 0, prof_2 = 0, prof_3 = 0, prof_5 = 0, prof_6 = 0, prof_7 = 0, prof_13 = 0, prof_14 = 0;
+        long long prof_0 = 0, prof_1 = 0, prof_2 = 0, prof_3 = 0, prof_5 = 0, prof_6 = 0, prof_7 = 0, prof_14 = 0, prof_15 = 0;
 #endif
         for (int i = 0; i < ntiles; ++i) {
             TC_CLK(c0);
 #ifdef TC_SLEEPY_SELECT
             mbar_wait_sleepy(&t_full[buf], use & 1);
 #else
-            mbar_wait(&t_full[buf], use & 1);
+            mbar_wait_handoff(&t_full[buf], use & 1);
 #endif
             tc_fence_after();
             const uint32_t ref0 = (uint32_t)(t_cur * TC_BN);
@@ -576,50 +559,52 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
             const TcMins m0 = tc_mins32(v0), m1 = tc_mins32(v1), m2 = tc_mins32(v2), m3 = tc_mins32(v3);
             const float mall = fminf(fmin3(tc_min4(m0), tc_min4(m1), tc_min4(m2)), tc_min4(m3));
 #ifndef TC_EXPERIMENT_NO_WALK
-            const bool any_hit = __any_sync(0xffffffffu, mall < thr);
-#ifdef TC_PROFILE
-            const long long c2a = clock64();
-            prof_7 += c2a - c2;
-#endif
+            const bool hit = mall < thr;
+            const bool any_hit = __any_sync(0xffffffffu, hit);
+            TC_CLK(c2a);
+            TC_ACC(7, c2a - c2);
             if (any_hit) {
-#ifdef TC_PROFILE
-                const int qn0 = qn;
-                const float thr0 = thr;
-#endif
-                if (mall < thr) {
-#ifdef TC_PROFILE
-                    const long long h0 = clock64();
-#endif
-                    tc_hits(m0, m1, m2, m3, thr, ref0, heap, kc, queue, qn);
-#ifdef TC_PROFILE
-                    prof_13 += clock64() - h0;
-                    prof_14 += 1;
-#endif
+                // a hit row with a full FIFO: the whole warp drains first (rare; lanes in lock-step)
+                if (__any_sync(0xffffffffu, hit && qn == fifo_depth)) {
+                    thr = tc_drain(heap, kc, fifo, qn, thr);
+                    qn = 0;
+                    TC_ACC(15, 1);
+                }
+                if (hit) {   // park the tile's 16 group minima and its first position; nothing else happens here
+                    float *f = fifo + qn * TC_FIFO_WORDS;
+                    *reinterpret_cast<float4 *>(f) = make_float4(m0.g0, m0.g1, m0.g2, m0.g3);
+                    *reinterpret_cast<float4 *>(f + 4) = make_float4(m1.g0, m1.g1, m1.g2, m1.g3);
+                    *reinterpret_cast<float4 *>(f + 8) = make_float4(m2.g0, m2.g1, m2.g2, m2.g3);
+                    *reinterpret_cast<float4 *>(f + 12) = make_float4(m3.g0, m3.g1, m3.g2, m3.g3);
+                    f[16] = __uint_as_float(ref0);
+                    ++qn;
                 }
                 __syncwarp();
 #ifdef TC_PROFILE
                 prof_5 += 1;
-                prof_6 += __popc(__ballot_sync(0xffffffffu, qn != qn0 || thr != thr0));
+                prof_6 += __popc(__ballot_sync(0xffffffffu, hit));
 #endif
             }
 #else
             if (mall < -1e30f) thr = 0.f;
 #endif
             TC_CLK(c3);
-            if ((i & flush_mask) == flush_mask && __any_sync(0xffffffffu, qn != 0)) {   // periodic drain, lanes in lock-step
-                thr = tc_drain(heap, kc, queue, qn, thr);
+            // every `period` tiles (the same tiles for all warps of the CTA) the parked tiles go into the heaps
+            if ((i & period_mask) == period_mask && __any_sync(0xffffffffu, qn != 0)) {
+                thr = tc_drain(heap, kc, fifo, qn, thr);
                 qn = 0;
+                TC_ACC(14, 1);
             }
             __syncwarp();
 #ifdef TC_PROFILE
             prof_0 += c1 - c0; prof_1 += c2 - c1; prof_2 += c3 - c2; prof_3 += clock64() - c3;
 #endif
 #endif
-            // advance the rotation by TC_QT chains
+            // advance the rotation by TC_QT chains (TC_QT <= nbuf)
             buf += TC_QT;
-            while (buf >= nbuf) { buf -= nbuf; ++use; }
+            if (buf >= nbuf) { buf -= nbuf; ++use; }
         }
-        if (qn != 0) thr = tc_drain(heap, kc, queue, qn, thr);
+        if (qn != 0) thr = tc_drain(heap, kc, fifo, qn, thr);
         __syncwarp();
 #ifdef TC_PROFILE
         if (lane == 0) {
@@ -627,9 +612,7 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
             atomicAdd(&tc_prof[2], (unsigned long long)prof_2); atomicAdd(&tc_prof[3], (unsigned long long)prof_3);
             atomicAdd(&tc_prof[4], (unsigned long long)ntiles); atomicAdd(&tc_prof[5], (unsigned long long)prof_5);
             atomicAdd(&tc_prof[6], (unsigned long long)prof_6); atomicAdd(&tc_prof[7], (unsigned long long)prof_7);
-        }
-        if (prof_14) {   // per hit lane: cycles inside tc_hits, number of visits
-            atomicAdd(&tc_prof[13], (unsigned long long)prof_13); atomicAdd(&tc_prof[14], (unsigned long long)prof_14);
+            atomicAdd(&tc_prof[14], (unsigned long long)prof_14); atomicAdd(&tc_prof[15], (unsigned long long)prof_15);
         }
 #endif
         // results: the row's candidates as (score, position) keys (unordered) and its final threshold
@@ -725,7 +708,7 @@ tc_debug_kernel(const unsigned char *__restrict__ qpack, const unsigned char *__
 // ------------------------------------------------------------------------------------------ host side
 namespace {
 struct TcPlan {
-    int kp, kc, qt, stages, nbuf, nsplit, tiles_per_split, ntiles, ss, flush_mask;
+    int kp, kc, fifo, period_mask, qt, stages, nbuf, nsplit, tiles_per_split, ntiles, ss;
     int64_t qtiles;
     size_t smem, qpack_bytes, cand_bytes, thr_bytes, dq_bytes;
     bool ok;
@@ -738,6 +721,12 @@ TcPlan tc_plan(int64_t N, int64_t M, int d, int k, int prec) {
     int kc = k + (force_pad ? atoi(force_pad) : TC_PAD);
     if (kc > M) kc = (int)M;
     p.kc = kc;
+    const char *force_fifo = getenv("SYM_TC_FIFO");      // tuning / experiments only
+    const char *force_period = getenv("SYM_TC_PERIOD");
+    int period = force_period ? atoi(force_period) : 16;   // tiles between two drains (power of two)
+    if (period < 1) period = 1;
+    while (period & (period - 1)) period &= period - 1;
+    p.period_mask = period - 1;
     const size_t tile = tc_tile_bytes(p.kp);
     const size_t budget = 227 * 1024;
     size_t fixed = 0;
@@ -754,9 +743,14 @@ TcPlan tc_plan(int64_t N, int64_t M, int d, int k, int prec) {
         const int qt = cfg[c][0], ss = cfg[c][1];
         if (force_qt && atoi(force_qt) != qt) continue;
         if (force_ss && (atoi(force_ss) != 0) != (ss != 0)) continue;
-        fixed = (size_t)qt * (tc_heap_stride(kc) + TC_QCAP) * TC_BM * 8 + 256 /* barriers */ + 1024 /* alignment slack */ +
-                (ss ? (size_t)qt * tile + 1024 : 0);
-        stages = budget > fixed ? (int)((budget - fixed) / tile) : 0;
+        // parked tiles per row: 2 when there is room for them beside >= 3 reference stages, else 1
+        for (p.fifo = force_fifo ? atoi(force_fifo) : 2; p.fifo >= 1; --p.fifo) {
+            fixed = (size_t)qt * TC_BM * ((size_t)tc_heap_stride(kc) * 8 + (size_t)tc_fifo_stride(p.fifo) * 4) +
+                    256 /* barriers */ + 1024 /* alignment slack */ + (ss ? (size_t)qt * tile + 1024 : 0);
+            stages = budget > fixed ? (int)((budget - fixed) / tile) : 0;
+            if (stages >= 3 || p.fifo == 1 || force_fifo) break;
+        }
+        if (p.fifo < 1) p.fifo = 1;
         if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
         p.qt = qt;
         p.ss = ss;
@@ -765,12 +759,6 @@ TcPlan tc_plan(int64_t N, int64_t M, int d, int k, int prec) {
         if (force_nbuf && atoi(force_nbuf) >= 1 && atoi(force_nbuf) <= p.nbuf) p.nbuf = atoi(force_nbuf);
         if (stages >= 3 && p.nbuf >= 2) break;
     }
-    // tiles between two lock-step drains of the rows' hit queues (power of two)
-    const char *force_flush = getenv("SYM_TC_FLUSH");
-    int flush = force_flush ? atoi(force_flush) : 32;
-    if (flush < 1) flush = 1;
-    while (flush & (flush - 1)) flush &= flush - 1;
-    p.flush_mask = flush - 1;
     p.stages = stages;
     p.ok = stages >= 2 && p.nbuf >= 1 && p.kp <= 256 && d <= 84;
     p.smem = fixed + (size_t)(stages > 0 ? stages : 0) * tile;
@@ -854,7 +842,7 @@ int knn_tc_scan(const float *Q, int ldq, int64_t N, const int32_t *q_perm, const
                                                                      cl_tile, M, p.kp, p.kc, p.stages, p.nbuf,        \
                                                                      p.tiles_per_split, p.ntiles, p.ss,               \
                                                                      prec ? TC_IDESC_F16 : TC_IDESC_BF16,             \
-                                                                     p.flush_mask, cand_w, thr_w);                    \
+                                                                     p.fifo, p.period_mask, cand_w, thr_w);                    \
     } while (0)
     if (p.qt == 2) SYM_TC_LAUNCH(2);
     else SYM_TC_LAUNCH(1);

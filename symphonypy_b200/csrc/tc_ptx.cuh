@@ -25,6 +25,52 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "}" ::"r"(smem_u32(bar)), "r"(parity)
         : "memory");
 }
+// Hand-off waits of the scan kernel (TC_WAIT_MODE, experiments: -DTC_WAIT_MODE=n -DTC_WAIT_NS=m):
+//   0  busy-poll (mbar_wait above)
+//   1  poll with a nanosleep back-off between polls: a spinning warp sends one SYNCS per few cycles into the same
+//      memory-I/O queue that the shared-memory loads and stores of the OTHER warps' slow paths go through
+//   2  suspending try_wait with an explicit time hint
+#ifndef TC_WAIT_MODE
+#define TC_WAIT_MODE 0
+#endif
+#ifndef TC_WAIT_NS
+#define TC_WAIT_NS 32
+#endif
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_handoff(uint64_t *bar, uint32_t parity) {
+#if TC_WAIT_MODE == 1
+    while (!mbar_test(bar, parity)) __nanosleep(TC_WAIT_NS);
+#elif TC_WAIT_MODE == 2
+    while (!mbar_try(bar, parity, TC_WAIT_NS)) {}
+#else
+    mbar_wait(bar, parity);
+#endif
+}
 // Suspending wait for the producer, which runs far ahead and is never on the critical path.
 __device__ __forceinline__ void mbar_wait_sleepy(uint64_t *bar, uint32_t parity) {
     asm volatile(

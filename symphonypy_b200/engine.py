@@ -31,7 +31,12 @@ def _stream(device) -> int:
 
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:
-    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
+    t = t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
+    if t.dim() == 2 and t.shape[0] <= 1 and t.stride(0) != t.shape[1]:
+        # 0- and 1-row tensors are "contiguous" whatever their row stride is (an empty array from numpy has
+        # stride 0); the C ABI takes the row stride as the leading dimension and requires ld >= d
+        t = torch.empty(t.shape, device=t.device, dtype=t.dtype).copy_(t)
+    return t
 
 
 def require_cuda(device=None) -> torch.device:
