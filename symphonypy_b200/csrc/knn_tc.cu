@@ -29,6 +29,8 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "knn_common.cuh"
 #include "tc_ptx.cuh"
 
@@ -38,7 +40,7 @@ constexpr int TC_BM = 128;        // query rows per CTA (UMMA M)
 constexpr int TC_BN = 128;        // reference rows per tile (UMMA N)
 // query tiles per CTA: QT = 2 (256 rows share every reference tile) when shared memory allows, else 1;
 // TMEM accumulator buffers per query tile: 4 / QT  (QT * ACC * 128 = 512 columns)
-constexpr int TC_MAX_STAGES = 6;
+constexpr int TC_MAX_STAGES = 16;   // reference tiles in flight (a bulk copy takes 1-2 us from L2: ~2000+ cycles of prefetch distance)
 constexpr int TC_PAD = 8;         // over-selection: kc = k + TC_PAD
 
 // operand precision: 0 = BF16x3 (three split products, K' = 3d+3), 1 = single FP16 (K' = d+2)
@@ -319,22 +321,59 @@ __device__ __forceinline__ float tc_insert(unsigned long long *heap, int kc, flo
 // certificate needs; a parked score is re-checked against the root when it is drained — tc_insert must never be
 // given a score that is not below the current root).  A full FIFO drains the whole warp early.
 constexpr int TC_GROUP = 8;        // reference positions per candidate group
-constexpr int TC_FIFO_WORDS = 20;  // one parked tile of a row: 16 group minima, the tile's first position, padding
-// row stride of the FIFOs in words: an odd number of 16-byte units, so that the 128-bit accesses of 8 consecutive
-// rows fall into 8 different bank groups
-__host__ __device__ inline int tc_fifo_stride(int depth) { return 4 * ((depth * (TC_FIFO_WORDS / 4)) | 1); }
+// one parked tile of a row: GN group minima, the first position, padding up to an ODD number of 16-byte units
+// (GN = 16: 20 words; GN = 8: 12 words), so that the 128-bit accesses of 8 consecutive rows fall into 8 bank groups
+__host__ __device__ inline int tc_fifo_words(int gn) { return gn + 4; }
+__host__ __device__ inline int tc_fifo_stride(int depth, int gn) { return 4 * ((depth * (tc_fifo_words(gn) / 4)) | 1); }
 
-__device__ __noinline__ float tc_drain(unsigned long long *heap, int kc, const float *fifo, int cnt, float thr) {
-#pragma unroll 1
-    for (int e = 0; e < cnt; ++e) {
-        const float *f = fifo + e * TC_FIFO_WORDS;
-        const float4 a = *reinterpret_cast<const float4 *>(f), b = *reinterpret_cast<const float4 *>(f + 4);
-        const float4 c = *reinterpret_cast<const float4 *>(f + 8), d = *reinterpret_cast<const float4 *>(f + 12);
-        const uint32_t ref0 = __float_as_uint(f[16]);
+// ---- two warps per (query tile, lane quadrant) ----
+// With 128 scores per thread only 8 selection warps fit in the register file (two per scheduler), and a lone warp
+// issues an instruction every 5-10 cycles (dependent chains, branches).  With HV = 2 a row is served by TWO threads
+// in different warps (same TMEM lanes): each pulls 64 of the tile's 128 columns, has its own FIFO of parked tiles
+// (8 group minima each) and its own copy of the threshold, and needs ~100 registers — four selection warps per
+// scheduler.  The row still has ONE heap: a warp drains its FIFO into it under the pair's lock (a shared-memory
+// word, taken by lane 0 for the whole warp; drains are rare), starting from the heap's current root, which its
+// partner may have lowered in the meantime.  A warp's threshold copy is then as fresh as its own last drain — stale
+// the safe way round.
+__device__ __forceinline__ void tc_pair_lock(uint32_t *lock, int lane) {
+    if (lane == 0) {
+        while (atomicCAS(lock, 0u, 1u) != 0u) {}
+    }
+    __syncwarp();
+    __threadfence_block();
+}
+__device__ __forceinline__ void tc_pair_unlock(uint32_t *lock, int lane) {
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) atomicExch(lock, 0u);
+}
+
+// One drain step: every row of the warp that has parked tiles puts its NEWEST one into its heap (the order does not
+// matter) and keeps the others for the next step.  One tile per row and step makes all steps — and so the drains of
+// the four warps that share an accumulator, which happen at the same tiles — take about the same time: a step used
+// to take as long as the fullest FIFO of the warp (a second tile in one of 32 rows doubled it; the other three warps
+// then waited for this one at the next accumulator).  Only ~3 % of the rows with a parked tile have a second one.
+template <int GN>
+__device__ __noinline__ float tc_drain(unsigned long long *heap, int kc, const float *fifo, int cnt, float thr,
+                                       uint32_t *lock, int lane) {
+    constexpr int FW = GN + 4;
+    if (lock != nullptr) {
+        tc_pair_lock(lock, lane);
+        thr = __uint_as_float((uint32_t)(heap[0] >> 32));   // the root as the partner left it
+    }
+    if (cnt > 0) {
+        const float *f = fifo + (cnt - 1) * FW;
+        const uint32_t ref0 = __float_as_uint(f[GN]);
         unsigned hm = 0;
 #define TC_BIT(GV, B) hm |= (GV < thr) ? (1u << (B)) : 0u;
-        TC_BIT(a.x, 0) TC_BIT(a.y, 1) TC_BIT(a.z, 2) TC_BIT(a.w, 3) TC_BIT(b.x, 4) TC_BIT(b.y, 5) TC_BIT(b.z, 6) TC_BIT(b.w, 7)
-        TC_BIT(c.x, 8) TC_BIT(c.y, 9) TC_BIT(c.z, 10) TC_BIT(c.w, 11) TC_BIT(d.x, 12) TC_BIT(d.y, 13) TC_BIT(d.z, 14) TC_BIT(d.w, 15)
+        {
+            const float4 a = *reinterpret_cast<const float4 *>(f), b = *reinterpret_cast<const float4 *>(f + 4);
+            TC_BIT(a.x, 0) TC_BIT(a.y, 1) TC_BIT(a.z, 2) TC_BIT(a.w, 3) TC_BIT(b.x, 4) TC_BIT(b.y, 5) TC_BIT(b.z, 6) TC_BIT(b.w, 7)
+        }
+        if (GN == 16) {
+            const float4 c = *reinterpret_cast<const float4 *>(f + 8), d = *reinterpret_cast<const float4 *>(f + 12);
+            TC_BIT(c.x, 8) TC_BIT(c.y, 9) TC_BIT(c.z, 10) TC_BIT(c.w, 11) TC_BIT(d.x, 12) TC_BIT(d.y, 13) TC_BIT(d.z, 14) TC_BIT(d.w, 15)
+        }
 #undef TC_BIT
 #pragma unroll 1
         while (hm) {
@@ -344,24 +383,47 @@ __device__ __noinline__ float tc_drain(unsigned long long *heap, int kc, const f
             if (gm < thr) thr = tc_insert(heap, kc, gm, ref0 + (uint32_t)(gi * TC_GROUP));
         }
     }
+    if (lock != nullptr) tc_pair_unlock(lock, lane);
     return thr;
 }
 
-template <int TC_QT>
-__global__ void __launch_bounds__(128 + 128 * TC_QT, 1)
+// One chain of MMAs: D[tmem] = A (shared-memory descriptor or tensor memory) x B (shared-memory descriptor), KS
+// slices of K = 16 (KS = 0: `ksteps` at run time).  Everything the chain needs is computed BEFORE the issuer waits for
+// the accumulator: what follows the wait is on the critical path of every tile (accumulator released -> refilled).
+template <bool SS, int KS>
+__device__ __forceinline__ void tc_issue_chain(uint32_t d_tmem, uint64_t q_desc, uint32_t a_tmem, uint64_t r_desc,
+                                               uint32_t idesc, int ksteps) {
+    if (KS > 0) {
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {   // one K=16 slice: 8 TMEM columns of A, 4096 B (256 units) of B
+            if (SS) tc_mma_bf16(d_tmem, q_desc + (uint64_t)(k * 256), r_desc + (uint64_t)(k * 256), idesc, k > 0);
+            else tc_mma_bf16_ts(d_tmem, a_tmem + (uint32_t)(k * 8), r_desc + (uint64_t)(k * 256), idesc, k > 0);
+        }
+    } else {
+#pragma unroll 1
+        for (int k = 0; k < ksteps; ++k) {
+            if (SS) tc_mma_bf16(d_tmem, q_desc + (uint64_t)(k * 256), r_desc + (uint64_t)(k * 256), idesc, k > 0);
+            else tc_mma_bf16_ts(d_tmem, a_tmem + (uint32_t)(k * 8), r_desc + (uint64_t)(k * 256), idesc, k > 0);
+        }
+    }
+}
+
+template <int TC_QT, int HV, int SS_MODE>
+__global__ void __launch_bounds__(128 + 128 * TC_QT * HV, 1)
 knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char *__restrict__ rpack, int64_t N,
                    const int32_t *__restrict__ q_perm, const int32_t *__restrict__ q_code,
                    const int32_t *__restrict__ cl_tile, int64_t M, int kp, int kc, int stages, int nbuf,
-                   int tiles_per_split, int ntiles_all, int ss_mode, uint32_t idesc, int fifo_depth, int period_mask,
+                   int tiles_per_split, int ntiles_all, uint32_t idesc, int fifo_depth, int period_mask,
                    unsigned long long *__restrict__ cand_out, float *__restrict__ thr_out) {
     extern __shared__ __align__(1024) unsigned char smraw[];
     const uint32_t tile_bytes = (uint32_t)tc_tile_bytes(kp);
     unsigned char *r_s = smraw;                                        // [stages][tile_bytes]
-    // one selection warp per (query tile, TMEM lane quadrant) examines all 128 columns of a tile
+    // HV selection warps per (query tile, TMEM lane quadrant), each examining 128 / HV columns of every tile
+    constexpr int GN = 16 / HV;              // candidate groups per warp and tile
     const int ks = tc_heap_stride(kc);       // odd row stride: the 32 rows of a warp hit 32 different banks
-    const int fs = tc_fifo_stride(fifo_depth);
-    float *fifo_s = (float *)(r_s + (size_t)stages * tile_bytes);                            // [TC_QT][TC_BM][fs]
-    unsigned long long *heap_s = (unsigned long long *)(fifo_s + (size_t)TC_QT * TC_BM * fs);  // [TC_QT][TC_BM][ks]
+    const int fs = tc_fifo_stride(fifo_depth, GN);
+    float *fifo_s = (float *)(r_s + (size_t)stages * tile_bytes);                                  // [HV][TC_QT][TC_BM][fs]
+    unsigned long long *heap_s = (unsigned long long *)(fifo_s + (size_t)HV * TC_QT * TC_BM * fs);   // [TC_QT][TC_BM][ks]
     uint64_t *bars = (uint64_t *)(heap_s + (size_t)TC_QT * TC_BM * ks);
     uint64_t *r_full = bars;                      // [TC_MAX_STAGES]
     uint64_t *r_empty = r_full + TC_MAX_STAGES;   // [TC_MAX_STAGES]
@@ -369,8 +431,9 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
     uint64_t *t_empty = t_full + 4;               // [4]
     uint32_t *tmem_slot = (uint32_t *)(t_empty + 4);
     volatile uint32_t *turn = tmem_slot + 1;      // sequence number of the next chain allowed to issue
+    uint32_t *pair_lock = tmem_slot + 4;          // [TC_QT * 4] one per (query tile, quadrant): serialises heap drains (HV = 2)
     // SS experiment: the query operand stays in shared memory (UMMA tile layout) instead of tensor memory
-    unsigned char *q_s = (unsigned char *)(((uintptr_t)(tmem_slot + 4) + 1023) & ~(uintptr_t)1023);   // [TC_QT][tile_bytes]
+    unsigned char *q_s = (unsigned char *)(((uintptr_t)(tmem_slot + 4 + 4 * TC_QT) + 1023) & ~(uintptr_t)1023);   // [TC_QT][tile_bytes]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int split = blockIdx.y, nsplit = gridDim.y;
@@ -387,13 +450,15 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
         t_home = min(max(t, t_beg), t_end - 1);
     }
     // tensor memory map: A operand of query tile q in columns [q*kp/2, (q+1)*kp/2); accumulator b at acc0 + b*128
+    constexpr bool ss_mode = SS_MODE != 0;
     const uint32_t a_cols = ss_mode ? 0u : (uint32_t)(kp / 2);
     const uint32_t acc0 = 512u - (uint32_t)nbuf * TC_BN;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < TC_MAX_STAGES; ++i) { mbar_init(&r_full[i], 1); mbar_init(&r_empty[i], TC_QT); }
-        for (int i = 0; i < 4; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4 * HV); }
         *turn = 0u;
+        for (int i = 0; i < 4 * TC_QT; ++i) pair_lock[i] = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {  // TMEM: all 512 columns, owned by this warp
@@ -402,7 +467,7 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (warp >= 4) {  // selection threads initialise their row's heap (all slots empty = the largest key)
+    if (warp >= 4 && warp < 4 + 4 * TC_QT) {  // one thread per row initialises its heap (all slots empty = the largest key)
         const int list = (warp - 4) >> 2, row = (warp & 3) * 32 + lane;   // list = query tile
         for (int e = 0; e < ks; ++e)
             heap_s[((size_t)list * TC_BM + row) * ks + e] = ((e < kc ? 0x7f800000ull : 0xff800000ull) << 32) | 0xffffffffull;
@@ -411,7 +476,7 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if (warp >= 4) {
+    if (warp >= 4 && warp < 4 + 4 * TC_QT) {
         // park this thread's query row (BF16x3, kp values) in tensor memory: it is the A operand of every MMA
         const int qt = (warp - 4) >> 2, quad = warp & 3;
         const int64_t n = ((int64_t)blockIdx.x * TC_QT + qt) * TC_BM + quad * 32 + lane;
@@ -434,8 +499,14 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
     // Register reallocation between the warp groups (the launch bound of 168 registers per thread is what 384
     // threads can share evenly): the producer / issuer group needs few, the selection warps hold a whole
     // accumulator row (128 scores) plus the group minima and spill without the extra room.
-    if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
-    else asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    // (setmaxnreg moves registers only within what the CTA was launched with: what the four service warps give up
+    // must cover what the selection warps ask for, or the last of them spins in the allocation forever.)
+    if (TC_QT * HV == 4) {
+        // 640 threads x 96 registers at launch; a selection thread holds 64 scores and needs < 96: nothing to move
+    } else {
+        if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    }
     if (warp == 0) {
         // ===== producer: one bulk copy per reference tile =====
         if (lane == 0) {
@@ -471,7 +542,16 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
 #ifdef TC_PROFILE
         long long prof_8 = 0, prof_9 = 0, prof_10 = 0, prof_11 = 0;
 #endif
+        // (the loop is instantiated per chain length — 2 and 4 slices cover the single-FP16 operands up to d = 62 —
+        // so that no dispatch sits between the accumulator hand-off and the first MMA)
+        auto issue_loop = [&](auto ks_tag) {
+        constexpr int KS = decltype(ks_tag)::value;
+        uint64_t r_desc = r_desc0;
         for (int i = 0; i < ntiles; ++i) {
+            // operands of this chain, ready before the waits
+            const uint32_t d_tmem = tmem_base + acc0 + (uint32_t)(buf * TC_BN);
+            const uint32_t full_bar = smem_u32(&t_full[buf]), empty_bar = smem_u32(&r_empty[s]);
+            asm volatile("" ::"l"(r_desc), "r"(d_tmem), "r"(full_bar), "r"(empty_bar));
             TC_CLK(c0);
             mbar_wait_handoff(&r_full[s], ph);
             TC_CLK(c1);
@@ -485,24 +565,24 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
             tc_fence_after();
             if (leader) {
 #ifndef TC_EXPERIMENT_NO_MMA
-                const uint64_t r_desc = r_desc0 + (uint64_t)((uint32_t)s * r_step);
-                const uint32_t d_tmem = tmem_base + acc0 + (uint32_t)(buf * TC_BN);
-#pragma unroll 2
-                for (int k = 0; k < ksteps; ++k)   // one K=16 slice: 8 TMEM columns of A, 4096 B (256 units) of B
-                    if (ss_mode) tc_mma_bf16(d_tmem, q_desc + (uint64_t)(k * 256), r_desc + (uint64_t)(k * 256), idesc, k > 0);
-                    else tc_mma_bf16_ts(d_tmem, a_tmem + (uint32_t)(k * 8), r_desc + (uint64_t)(k * 256), idesc, k > 0);
+                tc_issue_chain<ss_mode, KS>(d_tmem, q_desc, a_tmem, r_desc, idesc, ksteps);
 #endif
-                tc_commit(&t_full[buf]);    // this chain's accumulator is complete
-                tc_commit(&r_empty[s]);     // and this issuer is done with the shared-memory stage
+                tc_commit_addr(full_bar);    // this chain's accumulator is complete
+                tc_commit_addr(empty_bar);   // and this issuer is done with the shared-memory stage
                 if (ordered) *turn = (uint32_t)(i * TC_QT + q) + 1u;
             }
             __syncwarp();
             TC_CLK(c4);
             TC_ACC(8, c1 - c0); TC_ACC(9, c2 - c1); TC_ACC(10, c3 - c2); TC_ACC(11, c4 - c3);
-            if (++s == stages) { s = 0; ph ^= 1; }
+            r_desc += r_step;
+            if (++s == stages) { s = 0; ph ^= 1; r_desc = r_desc0; }
             buf += TC_QT;
-            while (buf >= nbuf) { buf -= nbuf; ++use; }
+            if (buf >= nbuf) { buf -= nbuf; ++use; }
         }
+        };
+        if (ksteps == 2) issue_loop(std::integral_constant<int, 2>{});
+        else if (ksteps == 4) issue_loop(std::integral_constant<int, 4>{});
+        else issue_loop(std::integral_constant<int, 0>{});
 #ifdef TC_PROFILE
         if (lane == 0) {
             atomicAdd(&tc_prof[8], (unsigned long long)prof_8); atomicAdd(&tc_prof[9], (unsigned long long)prof_9);
@@ -514,15 +594,22 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
         // spare warp(s): nothing to do until the final barrier
     } else {
         // ===== selection =====
-        const int qt = (warp - 4) >> 2, quad = warp & 3;
+        const int sel = warp - 4;
+        const int half = sel / (4 * TC_QT);                  // which 128 / HV columns of every tile this warp examines
+        const int qt = (sel % (4 * TC_QT)) >> 2, quad = warp & 3;
         const int row = quad * 32 + lane;
-        unsigned long long *heap = heap_s + ((size_t)qt * TC_BM + row) * ks;   // this thread's row: its kc best groups
-        float *fifo = fifo_s + ((size_t)qt * TC_BM + row) * fs;                // and its parked tiles
+        unsigned long long *heap = heap_s + ((size_t)qt * TC_BM + row) * ks;   // the row's kc best groups
+        float *fifo = fifo_s + ((size_t)(half * TC_QT + qt) * TC_BM + row) * fs;   // this thread's parked tiles
+        uint32_t *lock = HV == 2 ? pair_lock + qt * 4 + quad : nullptr;
         float thr = INFINITY;
         int qn = 0;                                                            // parked tiles
-        const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + acc0;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + acc0 + (uint32_t)(half * (TC_BN / HV));
+        const uint32_t col0 = (uint32_t)(half * (TC_BN / HV));
         int buf = qt % nbuf, use = qt / nbuf;   // chain (i, qt) = sequence number i*QT + qt
-        int t_cur = t_home;
+        // first position of the current tile's columns; wraps once, from the end of the split back to its start
+        // (the wrap target is recomputed from the launch parameters: nothing extra stays live across the loop)
+        uint32_t ref_cur = (uint32_t)(t_home * TC_BN) + col0;
+        int until_wrap = t_end - t_home;
 #ifdef TC_PROFILE
         long long prof_0 = 0, prof_1 = 0, prof_2 = 0, prof_3 = 0, prof_5 = 0, prof_6 = 0, prof_7 = 0, prof_14 = 0, prof_15 = 0;
 #endif
@@ -534,8 +621,9 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
             mbar_wait_handoff(&t_full[buf], use & 1);
 #endif
             tc_fence_after();
-            const uint32_t ref0 = (uint32_t)(t_cur * TC_BN);
-            if (++t_cur == t_end) t_cur = t_beg;
+            const uint32_t ref0 = ref_cur;
+            ref_cur += TC_BN;
+            if (--until_wrap == 0) ref_cur = (uint32_t)(blockIdx.y * tiles_per_split * TC_BN) + col0;
             const uint32_t acc = lane_base + (uint32_t)(buf * TC_BN);
 #ifdef TC_EXPERIMENT_NO_SELECT
             tc_fence_before();
@@ -546,18 +634,30 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
             // then run while this tile is examined (the buffer is held for one load latency).  (Splitting the load
             // in two with a wait in between, to fold the first half while the second is in flight, was slower:
             // 211 vs 131 cycles — the scoreboard already lets the min chains start as each LDTM lands.)
-            uint32_t v0[32], v1[32], v2[32], v3[32];
+            uint32_t v0[32], v1[32];
+            TcMins m0, m1, m2, m3;
             TC_CLK(c1);
             tc_ld32(acc, v0);
             tc_ld32(acc + 32, v1);
-            tc_ld32(acc + 64, v2);
-            tc_ld32(acc + 96, v3);
-            tc_wait_ld();
-            tc_fence_before();
-            if (lane == 0) mbar_arrive(&t_empty[buf]);
+            if (HV == 1) {
+                uint32_t v2[32], v3[32];
+                tc_ld32(acc + 64, v2);
+                tc_ld32(acc + 96, v3);
+                tc_wait_ld();
+                tc_fence_before();
+                if (lane == 0) mbar_arrive(&t_empty[buf]);
+                m2 = tc_mins32(v2);
+                m3 = tc_mins32(v3);
+            } else {
+                tc_wait_ld();
+                tc_fence_before();
+                if (lane == 0) mbar_arrive(&t_empty[buf]);
+            }
             TC_CLK(c2);
-            const TcMins m0 = tc_mins32(v0), m1 = tc_mins32(v1), m2 = tc_mins32(v2), m3 = tc_mins32(v3);
-            const float mall = fminf(fmin3(tc_min4(m0), tc_min4(m1), tc_min4(m2)), tc_min4(m3));
+            m0 = tc_mins32(v0);
+            m1 = tc_mins32(v1);
+            const float mall = HV == 1 ? fminf(fmin3(tc_min4(m0), tc_min4(m1), tc_min4(m2)), tc_min4(m3))
+                                       : fminf(tc_min4(m0), tc_min4(m1));
 #ifndef TC_EXPERIMENT_NO_WALK
             const bool hit = mall < thr;
             const bool any_hit = __any_sync(0xffffffffu, hit);
@@ -566,17 +666,19 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
             if (any_hit) {
                 // a hit row with a full FIFO: the whole warp drains first (rare; lanes in lock-step)
                 if (__any_sync(0xffffffffu, hit && qn == fifo_depth)) {
-                    thr = tc_drain(heap, kc, fifo, qn, thr);
-                    qn = 0;
+                    thr = tc_drain<GN>(heap, kc, fifo, qn, thr, lock, lane);
+                    qn = max(qn - 1, 0);
                     TC_ACC(15, 1);
                 }
                 if (hit) {   // park the tile's 16 group minima and its first position; nothing else happens here
-                    float *f = fifo + qn * TC_FIFO_WORDS;
+                    float *f = fifo + qn * (GN + 4);
                     *reinterpret_cast<float4 *>(f) = make_float4(m0.g0, m0.g1, m0.g2, m0.g3);
                     *reinterpret_cast<float4 *>(f + 4) = make_float4(m1.g0, m1.g1, m1.g2, m1.g3);
-                    *reinterpret_cast<float4 *>(f + 8) = make_float4(m2.g0, m2.g1, m2.g2, m2.g3);
-                    *reinterpret_cast<float4 *>(f + 12) = make_float4(m3.g0, m3.g1, m3.g2, m3.g3);
-                    f[16] = __uint_as_float(ref0);
+                    if (HV == 1) {
+                        *reinterpret_cast<float4 *>(f + 8) = make_float4(m2.g0, m2.g1, m2.g2, m2.g3);
+                        *reinterpret_cast<float4 *>(f + 12) = make_float4(m3.g0, m3.g1, m3.g2, m3.g3);
+                    }
+                    f[GN] = __uint_as_float(ref0);
                     ++qn;
                 }
                 __syncwarp();
@@ -589,10 +691,11 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
             if (mall < -1e30f) thr = 0.f;
 #endif
             TC_CLK(c3);
-            // every `period` tiles (the same tiles for all warps of the CTA) the parked tiles go into the heaps
-            if ((i & period_mask) == period_mask && __any_sync(0xffffffffu, qn != 0)) {
-                thr = tc_drain(heap, kc, fifo, qn, thr);
-                qn = 0;
+            // at the same tiles for all warps of the CTA — every 4th tile at the start of a scan, when thresholds still
+            // move fast, every `period`-th later — a parked tile per row goes into the heaps
+            if ((i & (i < 128 ? 3 : period_mask)) == (i < 128 ? 3 : period_mask) && __any_sync(0xffffffffu, qn != 0)) {
+                thr = tc_drain<GN>(heap, kc, fifo, qn, thr, lock, lane);
+                qn = max(qn - 1, 0);
                 TC_ACC(14, 1);
             }
             __syncwarp();
@@ -604,8 +707,15 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
             buf += TC_QT;
             if (buf >= nbuf) { buf -= nbuf; ++use; }
         }
-        if (qn != 0) thr = tc_drain(heap, kc, fifo, qn, thr);
+        while (__any_sync(0xffffffffu, qn != 0)) {
+            thr = tc_drain<GN>(heap, kc, fifo, qn, thr, lock, lane);
+            qn = max(qn - 1, 0);
+        }
         __syncwarp();
+        if (HV == 2) {   // both warps of every pair are done with the heaps before they are read out
+            asm volatile("bar.sync 1, %0;" ::"r"(128 * TC_QT * HV) : "memory");
+            thr = __uint_as_float((uint32_t)(heap[0] >> 32));
+        }
 #ifdef TC_PROFILE
         if (lane == 0) {
             atomicAdd(&tc_prof[0], (unsigned long long)prof_0); atomicAdd(&tc_prof[1], (unsigned long long)prof_1);
@@ -617,7 +727,7 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
 #endif
         // results: the row's candidates as (score, position) keys (unordered) and its final threshold
         const int64_t n = ((int64_t)blockIdx.x * TC_QT + qt) * TC_BM + row;
-        if (n < N) {
+        if (n < N && half == 0) {
             const int64_t slot = n * nsplit + split;
             for (int e = 0; e < kc; ++e) {
                 const unsigned long long h = heap[e];
@@ -708,7 +818,7 @@ tc_debug_kernel(const unsigned char *__restrict__ qpack, const unsigned char *__
 // ------------------------------------------------------------------------------------------ host side
 namespace {
 struct TcPlan {
-    int kp, kc, fifo, period_mask, qt, stages, nbuf, nsplit, tiles_per_split, ntiles, ss;
+    int kp, kc, fifo, period_mask, hv, qt, stages, nbuf, nsplit, tiles_per_split, ntiles, ss;
     int64_t qtiles;
     size_t smem, qpack_bytes, cand_bytes, thr_bytes, dq_bytes;
     bool ok;
@@ -721,9 +831,14 @@ TcPlan tc_plan(int64_t N, int64_t M, int d, int k, int prec) {
     int kc = k + (force_pad ? atoi(force_pad) : TC_PAD);
     if (kc > M) kc = (int)M;
     p.kc = kc;
-    const char *force_fifo = getenv("SYM_TC_FIFO");      // tuning / experiments only
+    const char *force_hv = getenv("SYM_TC_HALVES");      // tuning / experiments only
+    // selection warps per (query tile, quadrant): 1.  Two (each examining 64 columns; four selection warps per scheduler)
+    // measured 5 % slower at config2: the per-tile overheads double and the pair's drains serialise on its lock.
+    p.hv = force_hv ? (atoi(force_hv) == 2 ? 2 : 1) : 1;
+    const int gn = 16 / p.hv;
+    const char *force_fifo = getenv("SYM_TC_FIFO");
     const char *force_period = getenv("SYM_TC_PERIOD");
-    int period = force_period ? atoi(force_period) : 16;   // tiles between two drains (power of two)
+    int period = force_period ? atoi(force_period) : 32;   // tiles between two drains (power of two)
     if (period < 1) period = 1;
     while (period & (period - 1)) period &= period - 1;
     p.period_mask = period - 1;
@@ -743,14 +858,16 @@ TcPlan tc_plan(int64_t N, int64_t M, int d, int k, int prec) {
         const int qt = cfg[c][0], ss = cfg[c][1];
         if (force_qt && atoi(force_qt) != qt) continue;
         if (force_ss && (atoi(force_ss) != 0) != (ss != 0)) continue;
-        // parked tiles per row: 2 when there is room for them beside >= 3 reference stages, else 1
-        for (p.fifo = force_fifo ? atoi(force_fifo) : 2; p.fifo >= 1; --p.fifo) {
-            fixed = (size_t)qt * TC_BM * ((size_t)tc_heap_stride(kc) * 8 + (size_t)tc_fifo_stride(p.fifo) * 4) +
-                    256 /* barriers */ + 1024 /* alignment slack */ + (ss ? (size_t)qt * tile + 1024 : 0);
+        // parked tiles per row: up to 4, as many as fit beside >= 3 reference stages
+        for (p.fifo = force_fifo ? atoi(force_fifo) : 4; p.fifo >= 1; --p.fifo) {
+            fixed = 64 /* pair locks */ + (size_t)qt * TC_BM * ((size_t)tc_heap_stride(kc) * 8 + (size_t)p.hv * tc_fifo_stride(p.fifo, gn) * 4) +
+                    512 /* barriers */ + 1024 /* alignment slack */ + (ss ? (size_t)qt * tile + 1024 : 0);
             stages = budget > fixed ? (int)((budget - fixed) / tile) : 0;
             if (stages >= 3 || p.fifo == 1 || force_fifo) break;
         }
         if (p.fifo < 1) p.fifo = 1;
+        const char *force_stages = getenv("SYM_TC_STAGES");   // tuning / experiments only
+        if (force_stages && atoi(force_stages) >= 2 && atoi(force_stages) < stages) stages = atoi(force_stages);
         if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
         p.qt = qt;
         p.ss = ss;
@@ -834,18 +951,24 @@ int knn_tc_scan(const float *Q, int ldq, int64_t N, const int32_t *q_perm, const
         SYM_LAUNCH_CHECK("tc_pack_rows_kernel(query)");
     }
     dim3 grid((unsigned)p.qtiles, (unsigned)p.nsplit);
-#define SYM_TC_LAUNCH(QT)                                                                                             \
+#define SYM_TC_LAUNCH(QT, HV, SS)                                                                                     \
     do {                                                                                                              \
-        SYM_CUDA(cudaFuncSetAttribute(knn_scan_tc_kernel<QT>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+        SYM_CUDA(cudaFuncSetAttribute(knn_scan_tc_kernel<QT, HV, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                       (int)p.smem));                                                                  \
-        knn_scan_tc_kernel<QT><<<grid, 128 + 128 * QT, p.smem, st>>>(qpack, prec ? pk.tc16 : pk.tc, N, q_perm, q_code,   \
-                                                                     cl_tile, M, p.kp, p.kc, p.stages, p.nbuf,        \
-                                                                     p.tiles_per_split, p.ntiles, p.ss,               \
-                                                                     prec ? TC_IDESC_F16 : TC_IDESC_BF16,             \
-                                                                     p.fifo, p.period_mask, cand_w, thr_w);                    \
+        knn_scan_tc_kernel<QT, HV, SS><<<grid, 128 + 128 * QT * HV, p.smem, st>>>(                                    \
+            qpack, prec ? pk.tc16 : pk.tc, N, q_perm, q_code, cl_tile, M, p.kp, p.kc, p.stages, p.nbuf,               \
+            p.tiles_per_split, p.ntiles, prec ? TC_IDESC_F16 : TC_IDESC_BF16, p.fifo, p.period_mask, cand_w, thr_w);   \
     } while (0)
-    if (p.qt == 2) SYM_TC_LAUNCH(2);
-    else SYM_TC_LAUNCH(1);
+#define SYM_TC_LAUNCH_SS(QT, HV)                                                                                      \
+    do {                                                                                                              \
+        if (p.ss) SYM_TC_LAUNCH(QT, HV, 1);                                                                           \
+        else SYM_TC_LAUNCH(QT, HV, 0);                                                                                \
+    } while (0)
+    if (p.qt == 2 && p.hv == 2) SYM_TC_LAUNCH_SS(2, 2);
+    else if (p.qt == 2) SYM_TC_LAUNCH_SS(2, 1);
+    else if (p.hv == 2) SYM_TC_LAUNCH_SS(1, 2);
+    else SYM_TC_LAUNCH_SS(1, 1);
+#undef SYM_TC_LAUNCH_SS
 #undef SYM_TC_LAUNCH
     SYM_LAUNCH_CHECK("knn_scan_tc_kernel");
     *cand = cand_w;

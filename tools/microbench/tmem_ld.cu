@@ -36,10 +36,9 @@ __global__ void bench(int iters, long long *cycles, uint32_t *sink) {
 #pragma unroll
         for (int f = 0; f < INFLIGHT; ++f) ld32(base + ((it * INFLIGHT + f) * 32) % 512, v[f]);
         wait_ld();
+        // light consumption (two of the 32 registers per load): the ALU pipe must not be what is measured
 #pragma unroll
-        for (int f = 0; f < INFLIGHT; ++f)
-#pragma unroll
-            for (int j = 0; j < 32; ++j) acc ^= v[f][j];
+        for (int f = 0; f < INFLIGHT; ++f) acc ^= v[f][0] ^ v[f][31];
     }
     long long t1 = clock64();
     if (threadIdx.x % 32 == 0) cycles[blockIdx.x * (blockDim.x / 32) + warp] = t1 - t0;
