@@ -85,6 +85,13 @@ int sym_project_csr(const float *data, const int32_t *indices, const int64_t *in
                     const int32_t *col_gene, const float *mu, const float *inv_sd, const float *U,
                     int32_t ldu, int32_t d, float clip, const float *z0, float *Z, int32_t ldz,
                     sym_stream_t stream);
+/* Same, and *not_canonical (device int32, zeroed by the caller) is set to 1 when some row's column indices are not
+ * strictly increasing: duplicated columns must be summed before the scale + clip (the reference densifies first,
+ * _utils.py:284-285), so the caller canonicalises the matrix and calls again.  not_canonical may be NULL. */
+int sym_project_csr_checked(const float *data, const int32_t *indices, const int64_t *indptr, int64_t N,
+                            const int32_t *col_gene, const float *mu, const float *inv_sd, const float *U,
+                            int32_t ldu, int32_t d, float clip, const float *z0, float *Z, int32_t ldz,
+                            int32_t *not_canonical, sym_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * (2) assign — replaces symphonypy/_utils.py:154-178.

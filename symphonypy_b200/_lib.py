@@ -28,6 +28,8 @@ SIGNATURES = {
                                       _P]),
     "sym_project_csr_bias": (c_int32, [_P, _P, _P, c_int32, c_int32, c_int32, c_float, _P, _P]),
     "sym_project_csr": (c_int32, [_P, _P, _P, c_int64, _P, _P, _P, _P, c_int32, c_int32, c_float, _P, _P, c_int32, _P]),
+    "sym_project_csr_checked": (c_int32, [_P, _P, _P, c_int64, _P, _P, _P, _P, c_int32, c_int32, c_float, _P, _P, c_int32,
+                                          _P, _P]),
     "sym_assign": (c_int32, [_P, c_int32, c_int64, c_int32, _P, c_int32, _P, _P, _P]),
     "sym_batch_order_workspace": (c_size_t, [c_int32]),
     "sym_batch_order": (c_int32, [_P, c_int64, c_int32, _P, _P, _P, _P, c_size_t, _P]),

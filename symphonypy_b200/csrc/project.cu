@@ -199,23 +199,35 @@ __global__ void project_csr_bias_kernel(const float *__restrict__ mu, const floa
 }
 
 // One warp per cell; lane l owns outputs l, l+32, l+64, l+96.
+// `not_canonical` (optional): set to 1 when a row's column indices are not strictly increasing — a duplicated column
+// has to be summed BEFORE the scale and clip (the reference densifies first, `_utils.py:284-285`), which this kernel
+// cannot do term by term; the host then canonicalises the matrix and runs again.  The check rides on the index loads
+// the kernel makes anyway (scipy's own `has_canonical_format` is an O(nnz) pass on one host core).
 __global__ void __launch_bounds__(256)
 project_csr_kernel(const float *__restrict__ data, const int32_t *__restrict__ indices,
                    const int64_t *__restrict__ indptr, int64_t N, const int32_t *__restrict__ col_gene,
                    const float *__restrict__ mu, const float *__restrict__ inv_sd, const float *__restrict__ U,
-                   int ldu, int d, float clip, const float *__restrict__ z0, float *__restrict__ Z, int ldz) {
+                   int ldu, int d, float clip, const float *__restrict__ z0, float *__restrict__ Z, int ldz,
+                   int32_t *__restrict__ not_canonical) {
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= N) return;
     const int64_t beg = indptr[row], end = indptr[row + 1];
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    bool bad = false;
     for (int64_t base = beg; base < end; base += 32) {
         // each lane fetches one non-zero and resolves its coefficient; the warp then walks them
         const int64_t j = base + lane;
         float coef = 0.f;
         int g = -1;
+        const int col = j < end ? indices[j] : 0x7fffffff;
+        if (not_canonical != nullptr) {
+            int prev = __shfl_up_sync(0xffffffffu, col, 1);
+            if (lane == 0) prev = base > beg ? indices[base - 1] : -1;
+            bad |= j < end && col <= prev;
+        }
         if (j < end) {
-            g = col_gene[indices[j]];
+            g = col_gene[col];
             if (g >= 0) {
                 const float s = inv_sd[g], m = mu[g];
                 coef = s != 0.f ? scale_clip(data[j], m, s, clip) - scale_clip(0.f, m, s, clip) : 0.f;
@@ -237,6 +249,7 @@ project_csr_kernel(const float *__restrict__ data, const int32_t *__restrict__ i
 #pragma unroll
     for (int q = 0; q < 4; ++q)
         if (lane + 32 * q < d) Z[row * ldz + lane + 32 * q] = z0[lane + 32 * q] + acc[q];
+    if (not_canonical != nullptr && __any_sync(0xffffffffu, bad) && lane == 0) atomicOr(not_canonical, 1);
 }
 
 template <int DPAD, bool GATHER>
@@ -286,10 +299,23 @@ extern "C" int sym_project_csr_bias(const float *mu, const float *inv_sd, const 
     return SYM_OK;
 }
 
+extern "C" int sym_project_csr_checked(const float *data, const int32_t *indices, const int64_t *indptr, int64_t N,
+                                       const int32_t *col_gene, const float *mu, const float *inv_sd, const float *U,
+                                       int32_t ldu, int32_t d, float clip, const float *z0, float *Z, int32_t ldz,
+                                       int32_t *not_canonical, sym_stream_t stream);
+
 extern "C" int sym_project_csr(const float *data, const int32_t *indices, const int64_t *indptr, int64_t N,
                                const int32_t *col_gene, const float *mu, const float *inv_sd, const float *U,
                                int32_t ldu, int32_t d, float clip, const float *z0, float *Z, int32_t ldz,
                                sym_stream_t stream) {
+    return sym_project_csr_checked(data, indices, indptr, N, col_gene, mu, inv_sd, U, ldu, d, clip, z0, Z, ldz, nullptr,
+                                   stream);
+}
+
+extern "C" int sym_project_csr_checked(const float *data, const int32_t *indices, const int64_t *indptr, int64_t N,
+                                       const int32_t *col_gene, const float *mu, const float *inv_sd, const float *U,
+                                       int32_t ldu, int32_t d, float clip, const float *z0, float *Z, int32_t ldz,
+                                       int32_t *not_canonical, sym_stream_t stream) {
     using namespace sym;
     SYM_REQUIRE(N >= 0 && d > 0 && d <= 128 && ldu >= d && ldz >= d, SYM_ERR_INVALID_ARGUMENT,
                 "sym_project_csr: bad sizes");
@@ -297,7 +323,7 @@ extern "C" int sym_project_csr(const float *data, const int32_t *indices, const 
     const int64_t grid = ceil_div(N, 8);
     SYM_REQUIRE(grid < (1ll << 31), SYM_ERR_UNSUPPORTED_SHAPE, "sym_project_csr: N too large");
     project_csr_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(data, indices, indptr, N, col_gene, mu, inv_sd,
-                                                                         U, ldu, d, clip, z0, Z, ldz);
+                                                                         U, ldu, d, clip, z0, Z, ldz, not_canonical);
     SYM_LAUNCH_CHECK("project_csr_kernel");
     return SYM_OK;
 }

@@ -123,23 +123,27 @@ def project_dense(X: torch.Tensor, ld: Loadings, gene_col: torch.Tensor | None =
 
 
 def project_csr(data: torch.Tensor, indices: torch.Tensor, indptr: torch.Tensor, N: int, col_gene: torch.Tensor,
-                ld: Loadings, out: torch.Tensor | None = None) -> torch.Tensor:
-    """CSR form of the same projection; the dense matrix of `_utils.py:240-243` is never built."""
+                ld: Loadings, out: torch.Tensor | None = None, not_canonical: torch.Tensor | None = None) -> torch.Tensor:
+    """CSR form of the same projection; the dense matrix of `_utils.py:240-243` is never built.
+    `indptr` may be a slice [s, e] of the matrix's row pointer with `data` / `indices` the WHOLE arrays (its values
+    are absolute offsets): rows s..e-1 are then projected into `out` (N = e - s).  `not_canonical` (int32[1], device):
+    set to 1 by the kernel when a row's column indices are not strictly increasing."""
     lib = _lib.load()
     dev = data.device
     assert data.dtype == torch.float32 and indices.dtype == torch.int32 and indptr.dtype == torch.int64
+    assert indptr.numel() == N + 1
     if ld.z0 is None:
         ld.z0 = torch.empty(ld.d, device=dev, dtype=torch.float32)
         _lib.check(lib.sym_project_csr_bias(ld.mu.data_ptr(), ld.inv_sd.data_ptr(), ld.U.data_ptr(), ld.U.stride(0),
                                             ld.G, ld.d, CLIP, ld.z0.data_ptr(), _stream(dev)), "sym_project_csr_bias")
     Z = out if out is not None else torch.empty((N, ld.d), device=dev, dtype=torch.float32)
-    _lib.check(lib.sym_project_csr(data.data_ptr(), indices.data_ptr(), indptr.data_ptr(), N, col_gene.data_ptr(),
-                                   ld.mu.data_ptr(), ld.inv_sd.data_ptr(), ld.U.data_ptr(), ld.U.stride(0), ld.d,
-                                   CLIP, ld.z0.data_ptr(), Z.data_ptr(), Z.stride(0), _stream(dev)), "sym_project_csr")
+    _lib.check(lib.sym_project_csr_checked(data.data_ptr(), indices.data_ptr(), indptr.data_ptr(), N, col_gene.data_ptr(),
+                                           ld.mu.data_ptr(), ld.inv_sd.data_ptr(), ld.U.data_ptr(), ld.U.stride(0), ld.d,
+                                           CLIP, ld.z0.data_ptr(), Z.data_ptr(), ld.d if N <= 1 else Z.stride(0),
+                                           _ptr(not_canonical), _stream(dev)), "sym_project_csr")
     return Z
 
 
-# ------------------------------------------------------------------------------------- assign
 def assign(Z: torch.Tensor, Y: torch.Tensor, inv_sigma: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
     """R [N, K] = softmax_k(-2 (1 - cos(z, Y_k)) / sigma_k)   (`_utils.py:154-178`)."""
     lib = _lib.load()

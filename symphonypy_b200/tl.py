@@ -165,50 +165,154 @@ def _pinned_stage(nbytes: int, slot: int) -> torch.Tensor:
     return buf
 
 
+# Host -> device streaming.  A cudaMemcpy out of pageable memory is staged by the driver at a few GB/s on one
+# thread; here the next chunk is copied (and, where needed, converted to the 32-bit type the kernels read) into a
+# page-locked ring by the host's threads while the previous chunk is on the PCIe bus, so that pageable numpy / scipy
+# inputs stream at close to the speed of pinned ones.
+_STAGE_CHUNK = 48 << 20      # bytes per staged chunk
+
+
+def _stage_copy(dst: torch.Tensor, src: np.ndarray) -> None:
+    """dst[...] = src for host arrays (1-D, same length; converts the dtype on the way).  torch's CPU copy is
+    parallel over its intra-op threads and runs at memory speed (a thread pool of numpy copies measured half of it)."""
+    if not src.flags.writeable:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            dst.copy_(torch.from_numpy(src))
+    else:
+        dst.copy_(torch.from_numpy(src))
+
+
+class _Stager:
+    """Ring of page-locked staging buffers + a copy stream.  `send(pairs)` stages each (host 1-D array -> device 1-D
+    tensor of a 32-bit dtype) pair of one chunk and enqueues its H2D; returns the event the compute stream waits on."""
+
+    def __init__(self, dev, nbuf: int = 3):
+        self.dev = dev
+        self.copy = torch.cuda.Stream(dev)
+        self.copy.wait_stream(torch.cuda.current_stream(dev))
+        self.nbuf = nbuf
+        self.done = [None] * nbuf
+        self.i = 0
+
+    def send(self, pairs) -> torch.cuda.Event:
+        b = self.i % self.nbuf
+        self.i += 1
+        if self.done[b] is not None:
+            self.done[b].synchronize()     # the H2D that last read this staging buffer has finished
+        need = sum(((dst.numel() * 4 + 255) & ~255) for _, dst in pairs)
+        stage = _pinned_stage(max(need, _STAGE_CHUNK + (1 << 20)), ("stager", b))
+        off = 0
+        with torch.cuda.stream(self.copy):
+            for src, dst in pairs:
+                n = dst.numel()
+                if n == 0:
+                    continue
+                view = stage[off:off + n * 4].view(dst.dtype)
+                _stage_copy(view, src)
+                dst.copy_(view, non_blocking=True)
+                off += (n * 4 + 255) & ~255
+            ev = torch.cuda.Event()
+            ev.record(self.copy)
+        self.done[b] = ev
+        return ev
+
+
 def _project_host_dense(Xh: torch.Tensor, ld: engine.Loadings, gene_col, Z: torch.Tensor, after_chunk=None) -> None:
     """Stream a host matrix through the GPU: H2D of chunk i+1 overlaps the projection of chunk i.
-    `after_chunk(Z, s, e)` runs on the compute stream right after rows [s, e) have been projected."""
+    `after_chunk(Z, s, e)` runs on the compute stream right after rows [s, e) have been projected.
+    Page-locked float32 input goes straight onto the bus; anything else (pageable, float64, integer counts) is
+    staged — and converted to float32 on the way — by `_Stager`."""
     dev = Z.device
     N, C = Xh.shape
     if N == 0:
         return
-    row_bytes = C * Xh.element_size()
-    rows = int(max(1, min(N, settings.h2d_chunk_bytes // max(1, row_bytes))))
-    pinned = Xh.is_pinned()
+    direct = Xh.is_pinned() and Xh.dtype == torch.float32
+    row_bytes = C * 4
+    chunk = settings.h2d_chunk_bytes if direct else _STAGE_CHUNK
+    rows = int(max(1, min(N, chunk // max(1, row_bytes))))
     compute = torch.cuda.current_stream(dev)
-    copy = torch.cuda.Stream(dev)
-    bufs = [torch.empty((rows, C), dtype=Xh.dtype, device=dev) for _ in range(2 if N > rows else 1)]
-    ready = [torch.cuda.Event() for _ in bufs]
-    free = [torch.cuda.Event() for _ in bufs]
-    copy.wait_stream(compute)
+    bufs = [torch.empty((rows, C), dtype=torch.float32, device=dev) for _ in range(2 if N > rows else 1)]
+    free = [None for _ in bufs]
+    if direct:
+        copy = torch.cuda.Stream(dev)
+        copy.wait_stream(compute)
+    else:
+        stager = _Stager(dev)
+        Xn = Xh.numpy()
     for i, s in enumerate(range(0, N, rows)):
         b = i % len(bufs)
         e = min(N, s + rows)
-        src = Xh[s:e]
-        with torch.cuda.stream(copy):
-            if i >= len(bufs):
-                copy.wait_event(free[b])
-            if not pinned:
-                if i >= len(bufs):
-                    ready[b].synchronize()  # the previous H2D out of this staging buffer has finished
-                stage = _pinned_stage(rows * row_bytes, b)[: (e - s) * row_bytes].view(Xh.dtype).view(e - s, C)
-                stage.copy_(src)
-                src = stage
-            bufs[b][: e - s].copy_(src, non_blocking=True)
-            ready[b].record(copy)
-        compute.wait_event(ready[b])
-        xb = bufs[b][: e - s]
-        if xb.dtype != torch.float32:
-            xb = xb.float()
-        engine.project_dense(xb, ld, gene_col, out=Z[s:e])
+        if direct:
+            with torch.cuda.stream(copy):
+                if free[b] is not None:
+                    copy.wait_event(free[b])
+                bufs[b][: e - s].copy_(Xh[s:e], non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(copy)
+        else:
+            if free[b] is not None:
+                stager.copy.wait_event(free[b])
+            ready = stager.send([(Xn[s:e].reshape(-1), bufs[b][: e - s].view(-1))])
+        compute.wait_event(ready)
+        engine.project_dense(bufs[b][: e - s], ld, gene_col, out=Z[s:e])
         if after_chunk is not None:
             after_chunk(Z, s, e)
+        free[b] = torch.cuda.Event()
         free[b].record(compute)
 
 
-def _project(adata_query, adata_ref, loadings_key, use_genes_column, dev, after_chunk=None) -> torch.Tensor:
+def _project_host_csr(Xc, col_gene: np.ndarray, ld: engine.Loadings, Z: torch.Tensor, after_chunk=None):
+    """Stream a scipy CSR matrix through the GPU in row chunks (its `data` / `indices` slices are contiguous): the
+    values and column indices of chunk i+1 are staged and sent while chunk i is projected; `after_chunk(Z, s, e)`
+    follows each chunk on the compute stream.  Returns the device flag "some row is not in canonical format"
+    (None when scipy already knows that the matrix is canonical)."""
+    dev = Z.device
+    N = Xc.shape[0]
+    indptr_h = np.ascontiguousarray(Xc.indptr)
+    nnz = int(indptr_h[-1]) if N > 0 else 0
+    compute = torch.cuda.current_stream(dev)
+    data = torch.empty(nnz, device=dev, dtype=torch.float32)
+    indices = torch.empty(nnz, device=dev, dtype=torch.int32)
+    indptr = torch.from_numpy(indptr_h.astype(np.int64, copy=False)).to(dev)
+    colg = torch.from_numpy(col_gene).to(dev)
+    known = getattr(Xc, "_has_canonical_format", None) is True     # scipy's cached flag; never computed here (O(nnz))
+    flag = None if known else torch.zeros(1, device=dev, dtype=torch.int32)
+    if N == 0:
+        return flag
+    stager = _Stager(dev)
+    per_chunk = max(1, _STAGE_CHUNK // 8)                          # non-zeros per chunk (4 B value + 4 B index)
+    bounds = [0]
+    while bounds[-1] < N:                                          # row boundaries: ~per_chunk non-zeros each
+        target = indptr_h[bounds[-1]] + per_chunk
+        nxt = int(np.searchsorted(indptr_h, target, side="right")) - 1
+        bounds.append(min(N, max(nxt, bounds[-1] + 1)))
+    d_h, i_h = Xc.data, Xc.indices
+    for s, e in zip(bounds[:-1], bounds[1:]):
+        lo, hi = int(indptr_h[s]), int(indptr_h[e])
+        for o in range(lo, hi, per_chunk):                         # (a single row wider than a chunk: several sends)
+            o2 = min(hi, o + per_chunk)
+            ready = stager.send([(d_h[o:o2], data[o:o2]), (i_h[o:o2], indices[o:o2])])
+        if hi > lo:
+            compute.wait_event(ready)
+        engine.project_csr(data, indices, indptr[s:e + 1], e - s, colg, ld, out=Z[s:e], not_canonical=flag)
+        if after_chunk is not None:
+            after_chunk(Z, s, e)
+    return flag
+
+
+class _NotCanonical(Exception):
+    """The CSR query has unsorted or duplicated column indices (found by the projection kernel)."""
+
+
+def _project(adata_query, adata_ref, loadings_key, use_genes_column, dev, after_chunk=None, X=None,
+             pending_checks: list | None = None) -> torch.Tensor:
     """`_map_query_to_ref` (`_utils.py:248-308`): returns Z [N, d] on the device.  `after_chunk(Z, s, e)` is called
-    on the compute stream whenever rows [s, e) of Z are final (once per H2D chunk for a host matrix)."""
+    on the compute stream whenever rows [s, e) of Z are final (once per H2D chunk for a host matrix).
+    `X` overrides `adata_query.X`; `pending_checks` receives device flags the caller reads at its next sync point
+    (CSR input: "not in canonical format" — the caller then canonicalises a copy and calls again)."""
+    if pending_checks is None:
+        pending_checks = []
     assert "mean" in adata_ref.var, "Gene expression means are expected to be saved in adata_ref.var"
     assert "std" in adata_ref.var, "Gene expression stds are expected to be saved in adata_ref.var"
     if use_genes_column is None:
@@ -238,25 +342,20 @@ def _project(adata_query, adata_ref, loadings_key, use_genes_column, dev, after_
     # key = full content of everything the device operands are built from (in-place edits of adata_ref are noticed)
     ld = _cached(("loadings", str(dev), content_digest(means_all, stds, hv, present, pcs)), build)
     G = ld.G
-    X = adata_query.X
+    if X is None:
+        X = adata_query.X
     N = X.shape[0]
     Z = torch.empty((N, ld.d), device=dev, dtype=torch.float32)
     identity = bool((q_idx == np.arange(G)).all())
 
     if issparse(X):
-        Xc = X.tocsr()
-        if not Xc.has_canonical_format:
-            Xc = Xc.copy()
-            Xc.sum_duplicates()
+        Xc = X.tocsr()     # (no copy when X already is CSR)
         col_gene = np.full(X.shape[1], -1, dtype=np.int32)
         ok = q_idx >= 0
         col_gene[q_idx[ok]] = np.arange(G, dtype=np.int32)[ok]
-        data = torch.from_numpy(np.ascontiguousarray(Xc.data)).to(dev, non_blocking=True).float()
-        indices = torch.from_numpy(np.ascontiguousarray(Xc.indices)).to(dev, non_blocking=True).int()
-        indptr = torch.from_numpy(np.ascontiguousarray(Xc.indptr)).to(dev, non_blocking=True).long()
-        engine.project_csr(data, indices, indptr, N, torch.from_numpy(col_gene).to(dev), ld, out=Z)
-        if after_chunk is not None and N > 0:
-            after_chunk(Z, 0, N)
+        flag = _project_host_csr(Xc, col_gene, ld, Z, after_chunk)
+        if flag is not None:
+            pending_checks.append(flag)
         return Z
 
     gene_col = None if identity else torch.from_numpy(q_idx.astype(np.int32)).to(dev)
@@ -448,9 +547,23 @@ def map_embedding(
     if "log1p" not in adata_query.uns:
         warnings.warn("Gene expressions in adata_query should be log1p-transformed")
 
+    args = (adata_query, adata_ref, key, lamb, sigma, use_genes_column, transferred_adjusted_basis, transferred_primary_basis)
+    try:
+        _map_embedding_once(*args)
+    except _NotCanonical:
+        # a CSR query with unsorted or duplicated column indices (rare: scipy and AnnData keep matrices canonical):
+        # duplicates must be summed before the scale + clip, as the reference's densification does
+        Xc = adata_query.X.tocsr().copy()
+        Xc.sum_duplicates()
+        _map_embedding_once(*args, X=Xc)
+
+
+def _map_embedding_once(adata_query, adata_ref, key, lamb, sigma, use_genes_column, transferred_adjusted_basis,
+                        transferred_primary_basis, X=None) -> None:
     dev = engine.require_cuda(settings.device)
     harmony_ref = adata_ref.uns["harmony"]
     ref_basis_loadings = harmony_ref["ref_basis_loadings"]  # `tl.py:347` overrides the keyword
+    checks: list = []
 
     with torch.cuda.device(dev):
         # soft-assignment operands first: the assignment of a chunk of cells runs right behind its projection
@@ -479,7 +592,8 @@ def map_embedding(
                     r_host[s:e].copy_(R[s:e], non_blocking=True)
 
         # 1. project
-        Z = _project(adata_query, adata_ref, ref_basis_loadings, use_genes_column, dev, after_chunk)
+        Z = _project(adata_query, adata_ref, ref_basis_loadings, use_genes_column, dev, after_chunk, X=X,
+                     pending_checks=checks)
         d = Z.shape[1]
         assert Yd.shape == (Kc, d), "harmony C must be [K, n_components]"
 
@@ -492,12 +606,15 @@ def map_embedding(
         Cd = torch.from_numpy(np.ascontiguousarray(Cn)).to(dev)
         R, Zc, info = pipeline.soft_assign_and_correct(Z, Yd, inv_sig, codes, n_levels, torch.from_numpy(lam).to(dev),
                                                        Nr, Cd, R=R)
+        if any(int(f.item()) for f in checks):   # (first sync point of the call)
+            raise _NotCanonical()
         pipeline.check_solve(info)
 
         # 4. results back into the AnnData, as the reference does (`tl.py:394-397`, `_utils.py:306`)
         zc_h = _to_host_async(Zc)
         torch.cuda.current_stream(dev).synchronize()
         d2h.synchronize()
+
         adata_query.obsm[transferred_primary_basis] = z_h
         adata_query.obsm[transferred_adjusted_basis] = zc_h
         _remember(z_h, Z)

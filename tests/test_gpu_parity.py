@@ -566,6 +566,68 @@ def test_input_container_variants(cuda_device, kind):
     assert row_rel_err(query.obsm["X_pca_harmony"], qo.obsm["X_pca_harmony"]) < EMB_TOL
 
 
+@pytest.mark.parametrize("kind", ["duplicates", "unsorted"])
+def test_csr_not_in_canonical_format(cuda_device, kind):
+    """A scipy CSR query whose rows hold duplicated or unsorted column indices: duplicates are summed before the
+    scale + clip, as the reference's densification does (`_utils.py:284-285`).  The projection kernel notices
+    (scipy's own O(nnz) check is never run) and the mapping is redone on a canonical copy."""
+    import scipy.sparse as sp
+
+    quiet()
+    query, ref = synth.small_case(N=700, M=500, G=160, d=20, K=12, L=4, levels=(3,), seed=29, missing_frac=0.1)
+    qo = copy.deepcopy(query)
+    X = sp.csr_matrix(np.asarray(query.X))
+    if kind == "duplicates":   # split every stored value into two entries of the same column
+        data = np.repeat(X.data * 0.5, 2).astype(np.float32)
+        indices = np.repeat(X.indices, 2)
+        indptr = X.indptr * 2
+    else:                      # reverse the column order inside every row
+        data, indices, indptr = X.data.copy(), X.indices.copy(), X.indptr
+        for r in range(X.shape[0]):
+            data[indptr[r]:indptr[r + 1]] = data[indptr[r]:indptr[r + 1]][::-1]
+            indices[indptr[r]:indptr[r + 1]] = indices[indptr[r]:indptr[r + 1]][::-1]
+    Xn = sp.csr_matrix((data, indices, indptr), shape=X.shape)
+    assert not Xn.has_canonical_format
+    Xn = sp.csr_matrix((data, indices, indptr), shape=X.shape)   # fresh object: no cached flags
+    query.X = Xn
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        so.map_embedding(qo, ref, key="batch0")
+        tl.map_embedding(query, ref, key="batch0")
+    assert row_rel_err(query.obsm["X_pca_reference"], qo.obsm["X_pca_reference"]) < EMB_TOL
+    assert row_rel_err(query.obsm["X_pca_harmony"], qo.obsm["X_pca_harmony"]) < EMB_TOL
+    assert query.X is Xn and query.X.nnz == Xn.nnz   # the caller's matrix is left as it was
+
+
+@pytest.mark.parametrize("kind", ["csr", "dense_pageable", "dense_float64", "dense_pinned"])
+def test_host_streaming_in_many_chunks(cuda_device, kind, monkeypatch):
+    """Host inputs stream through the GPU in chunks (staging ring, projection and soft assignment per chunk):
+    with a tiny chunk size the same small case goes through dozens of chunks and partial last chunks."""
+    import scipy.sparse as sp
+
+    quiet()
+    monkeypatch.setattr(tl, "_STAGE_CHUNK", 20_000)
+    monkeypatch.setattr(tl.settings, "h2d_chunk_bytes", 50_000)
+    query, ref = synth.small_case(N=1203, M=500, G=160, d=20, K=12, L=4, levels=(3,), seed=31)
+    qo = copy.deepcopy(query)
+    X = np.ascontiguousarray(np.asarray(query.X), dtype=np.float32)
+    if kind == "csr":
+        query.X = sp.csr_matrix(X)
+    elif kind == "dense_float64":
+        query.X = X.astype(np.float64)
+    elif kind == "dense_pinned":
+        query.X = torch.from_numpy(X).pin_memory().numpy()
+    else:
+        query.X = X
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        so.map_embedding(qo, ref, key="batch0")
+        tl.map_embedding(query, ref, key="batch0")
+    assert row_rel_err(query.obsm["X_pca_reference"], qo.obsm["X_pca_reference"]) < EMB_TOL
+    assert row_rel_err(query.obsm["X_pca_harmony"], qo.obsm["X_pca_harmony"]) < EMB_TOL
+    assert np.abs(query.obsm["X_pca_harmony_symphony_R"] - qo.obsm["X_pca_harmony_symphony_R"]).max() < R_TOL
+
+
 def test_many_batch_levels_and_large_k_clusters(cuda_device):
     """B = 140 levels (the largest ridge system the shared-memory solver takes at d = 20) and K = 300 clusters."""
     quiet()

@@ -10,8 +10,13 @@ N, M, G, d, K, k = int(os.environ.get("N", 1_000_000)), 500_000, 2000, 30, 100, 
 model = synth.make_model(G, d, 20, 0, dev)
 Zref, comp, C, Nr = synth.make_reference(model, M, K, 0)
 X, codes, _ = synth.make_query(model, N, [1], 1000)
-Xh = torch.empty((N, G), dtype=torch.float32).pin_memory(); Xh.copy_(X); del X
-q = AnnDataLite(Xh.numpy(), obs=pd.DataFrame(index=pd.RangeIndex(N).astype(str)),
+FMT = os.environ.get("FMT", "pinned")   # pinned | pageable | csr
+Xh = torch.empty((N, G), dtype=torch.float32, pin_memory=(FMT == "pinned")); Xh.copy_(X); del X
+Xq = Xh.numpy()
+if FMT == "csr":
+    import scipy.sparse as sp
+    Xq = sp.csr_matrix(Xq)
+q = AnnDataLite(Xq, obs=pd.DataFrame(index=pd.RangeIndex(N).astype(str)),
                 var=pd.DataFrame(index=pd.Index([f"g{i}" for i in range(G)])), uns={"log1p": {}})
 _, ref = synth.to_anndata(model, Zref, comp, C, Nr, Xh[:8].to(dev), codes[:, :8], K, seed=0)
 def step():
@@ -25,4 +30,4 @@ step()
 t0 = time.perf_counter(); t1 = step(); t2 = time.perf_counter()
 print(f"map_embedding {1e3*(t1-t0):.1f} ms, transfer {1e3*(t2-t1):.1f} ms")
 pr = cProfile.Profile(); pr.enable(); step(); pr.disable()
-pstats.Stats(pr).sort_stats("cumulative").print_stats(28)
+pstats.Stats(pr).sort_stats("cumulative").print_stats(int(os.environ.get("TOP", 28)))
