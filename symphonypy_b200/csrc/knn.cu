@@ -13,6 +13,7 @@
 // s = ||r||^2 - 2 q.r.  A candidate is examined further only if s <= the row's current kc-th best
 // (one compare per pair in the steady state); survivors go through a small per-row queue in
 // shared memory into the row's top-kc list (replace-the-maximum, warp cooperative).
+#include <cuda_fp16.h>
 #include <float.h>
 
 #include "common.cuh"
@@ -296,6 +297,7 @@ constexpr int RR_THREADS = 256;
 constexpr int RR_MAXC = 512;   // candidates per row the scan may hand over, and members per row that can be ranked
 constexpr int RR_DMAX = 128;
 constexpr size_t RR_SMEM = (size_t)(RR_THREADS / 32) * (RR_MAXC * (sizeof(double) + sizeof(int32_t)) + RR_DMAX * sizeof(float));
+constexpr size_t RR_SMEM_GROUPS = RR_SMEM + (size_t)(RR_THREADS / 32) * 512;   // + the packed operand row of each warp's query
 
 __global__ void __launch_bounds__(RR_THREADS)
 knn_rerank_kernel(const float *__restrict__ Q, int ldq, int64_t N, const float *__restrict__ Ref, int ldr,
@@ -420,6 +422,178 @@ knn_rerank_kernel(const float *__restrict__ Q, int ldq, int64_t N, const float *
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) kth = fmax(kth, __shfl_xor_sync(0xffffffffu, kth, o));
         bad |= nsurv < k;
+        if (lane == 0) unsafe[n] = (!bad && kth - qn + 2.0 * eps < tmin) ? 0 : 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ rerank of candidate GROUPS
+// The tcgen05 scans hand over groups of 8 consecutive packed positions.  Giving all 8 x kc members of a row their
+// float64 distance (the kernel above) costs a 32-byte sector per member group and dimension — 17 KB of gathers and
+// 4300 float64 FMAs per row at config2, 6.7 ms of a 57 ms step (profiles/r2k).  Here the members are first scored the
+// way the scan scored them, from the SAME packed operand tiles (one 128-byte line per group and k-unit: half the
+// bytes, fully coalesced) in FP32; only the members that can still be among the k nearest if the row certifies —
+// score below the row's threshold plus the error margin, ~kc of them — get the exact float64 distance from their
+// reference row.  One warp per query row; lane <-> member in pass A, lane <-> survivor in pass B.
+template <int PREC>   // 0: BF16x3 operands, 1: single FP16
+__global__ void __launch_bounds__(RR_THREADS)
+knn_rerank_groups_kernel(const float *__restrict__ Q, int ldq, int64_t N, const float *__restrict__ Ref, int ldr, int64_t M,
+                         int d, int k, const unsigned long long *__restrict__ cand, const float *__restrict__ thr, int ncand,
+                         int nsplit, double eps_rel, const KnnHeader *__restrict__ hdr, const int32_t *__restrict__ order,
+                         const int32_t *__restrict__ q_perm, const float *__restrict__ dq16,
+                         const unsigned char *__restrict__ qrows, const unsigned char *__restrict__ rtiles, int kp,
+                         int32_t *__restrict__ idx_out, float *__restrict__ dist_out, uint8_t *__restrict__ unsafe) {
+    extern __shared__ __align__(16) unsigned char rr_smem[];
+    constexpr int W = RR_THREADS / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // per warp: survivors (double distance | int32 id, RR_MAXC each), the float32 query row, its packed operand row
+    double *wd = reinterpret_cast<double *>(rr_smem) + (size_t)warp * RR_MAXC;
+    int32_t *wi = reinterpret_cast<int32_t *>(rr_smem + (size_t)W * RR_MAXC * sizeof(double)) + (size_t)warp * RR_MAXC;
+    float *wq = reinterpret_cast<float *>(rr_smem + (size_t)W * RR_MAXC * (sizeof(double) + sizeof(int32_t))) + (size_t)warp * RR_DMAX;
+    uint4 *wo = reinterpret_cast<uint4 *>(rr_smem + (size_t)W * (RR_MAXC * (sizeof(double) + sizeof(int32_t)) + RR_DMAX * sizeof(float))) +
+                (size_t)warp * (256 / 8);   // kp <= 256 operand values = 32 uint4
+    const int64_t row = (int64_t)blockIdx.x * W + warp;   // row of the scan (locality order)
+    if (row >= N) return;
+    const int64_t n = q_perm ? q_perm[row] : row;         // the query it stands for
+    const float *q = Q + n * ldq;
+    for (int c = lane; c < d; c += 32) wq[c] = q[c];
+    const int nunits = kp / 8;
+    for (int j = lane; j < nunits; j += 32) wo[j] = __ldg(reinterpret_cast<const uint4 *>(qrows + (size_t)row * kp * 2) + j);
+    __syncwarp();
+    double qn = 0.0;
+    for (int c = 0; c < d; ++c) {
+        const double v = (double)wq[c];
+        qn = fma(v, v, qn);
+    }
+    const double rmax2 = (double)hdr->rmax2;
+    double eps = eps_rel * (2.0 * sqrt(qn) * sqrt(rmax2) + rmax2);
+    double unscale = 1.0;   // scan scores and thresholds are in units of scale16^2 when the operands were single FP16
+    if (PREC == 1) {        // (error bound of the single-FP16 scores: see knn_rerank_kernel)
+        const double s = (double)hdr->scale16, dr = (double)hdr->dr16, dq = (double)dq16[row];
+        const double qs = 2.0 * s * sqrt(qn), rs = s * sqrt(rmax2);
+        unscale = 1.0 / (s * s);
+        eps += (qs * dr + dq * (rs + dr)) * unscale;
+    }
+    double tmin = INFINITY;
+    for (int s = 0; s < nsplit; ++s) tmin = fmin(tmin, (double)thr[row * nsplit + s]);
+    tmin *= unscale;
+    for (int e = lane; e < k; e += 32) {
+        idx_out[n * k + e] = -1;
+        dist_out[n * k + e] = INFINITY;
+    }
+    // ---- pass A: operand-precision scores of all members; survivors = members that may matter
+    const size_t tile_bytes = (size_t)kp * 256;
+    const float keep_below = (float)((tmin + 3.0 * eps) / unscale);   // in scan units (3 eps: the pass-A score is as far
+                                                                      // from the exact one as the scan's was)
+    int bad = 0, nsurv = 0;
+    const int total = ncand * 8;
+    float *ws = reinterpret_cast<float *>(wd);   // pass A parks (score | position) where pass B writes (distance | id)
+    for (int base = 0; base < total; base += 32) {
+        const int e = base + lane;
+        const unsigned long long key = e < total ? cand[row * ncand + (e >> 3)] : ~0ull;
+        const bool gvalid = key != ~0ull;
+        const int64_t pos = (int64_t)(uint32_t)(key & 0xffffffffull) + (e & 7);
+        const bool valid = gvalid && pos < M;
+        float sc = INFINITY;
+        if (gvalid) {   // (padding positions of the last tile hold +inf norms: their score is +inf)
+            const unsigned char *t = rtiles + (size_t)(pos >> 7) * tile_bytes + ((pos & 127) >> 3) * 128 + (pos & 7) * 16;
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll 4
+            for (int j = 0; j < nunits; ++j) {
+                const uint4 rv = __ldg(reinterpret_cast<const uint4 *>(t + (size_t)j * 2048));
+                const uint4 qv = wo[j];
+                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w}, qw[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float r0, r1, q0, q1;
+                    if (PREC == 1) {
+                        const float2 rf = __half22float2(*reinterpret_cast<const __half2 *>(&rw[u]));
+                        const float2 qf = __half22float2(*reinterpret_cast<const __half2 *>(&qw[u]));
+                        r0 = rf.x; r1 = rf.y; q0 = qf.x; q1 = qf.y;
+                    } else {
+                        r0 = __uint_as_float(rw[u] << 16); r1 = __uint_as_float(rw[u] & 0xffff0000u);
+                        q0 = __uint_as_float(qw[u] << 16); q1 = __uint_as_float(qw[u] & 0xffff0000u);
+                    }
+                    a0 = fmaf(q0, r0, a0);
+                    a1 = fmaf(q1, r1, a1);
+                }
+            }
+            sc = a0 + a1;
+        }
+        // the recorded group score is the minimum over the group as the tensor core computed it: the same operands
+        // and products, another summation order
+        float gmin = sc;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) gmin = fminf(gmin, __shfl_xor_sync(0xffffffffu, gmin, o));
+        if (gvalid && (e & 7) == 0) {
+            const float rec = knn_key_score(key);
+            bad |= !(fabs((double)rec - (double)gmin) * unscale <= eps);
+        }
+        const bool keep = valid && sc <= keep_below;
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        const int off = nsurv + __popc(m & ((1u << lane) - 1u));
+        if (keep && off < RR_MAXC) {
+            ws[2 * off] = sc;
+            wi[off] = (int32_t)pos;
+        }
+        nsurv += __popc(m);
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if (nsurv > RR_MAXC) {   // cannot rank them all: rank what fits, flag the row
+        nsurv = RR_MAXC;
+        bad = 1;
+    }
+    __syncwarp();
+    // ---- pass B: exact float64 distance of the survivors (sklearn's formula), from their reference rows
+    int nkeep = 0;
+    for (int base = 0; base < nsurv; base += 32) {
+        const int e = base + lane;
+        double s_exact = INFINITY;
+        int32_t id = 0x7fffffff;
+        float sA = 0.f;
+        if (e < nsurv) {
+            sA = ws[2 * e];
+            id = order[wi[e]];
+            const float *r = Ref + (int64_t)id * ldr;
+            double rn = 0.0, dot = 0.0;
+            for (int c = 0; c < d; ++c) {
+                const double rv = (double)__ldg(r + c);
+                rn = fma(rv, rv, rn);
+                dot = fma((double)wq[c], rv, dot);
+            }
+            s_exact = rn - 2.0 * dot;
+            bad |= !(fabs((double)sA * unscale - s_exact) <= eps);   // the error bound holds on the members that matter
+        }
+        __syncwarp();   // all lanes have read their (score | position) slots before they are overwritten
+        const bool keep = e < nsurv && s_exact <= tmin + 2.0 * eps;
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        const int off = nkeep + __popc(m & ((1u << lane) - 1u));
+        if (keep) {   // off <= e: slots below the read front
+            wd[off] = fmax(qn + s_exact, 0.0);  // sklearn: ||x||^2 - 2 x.y + ||y||^2, clamped at 0
+            wi[off] = id;
+        }
+        nkeep += __popc(m);
+        __syncwarp();
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    double kth = 0.0;
+    for (int e = lane; e < nkeep; e += 32) {
+        const double de = wd[e];
+        const int32_t ie = wi[e];
+        int rank = 0;
+        for (int f = 0; f < nkeep; ++f) {
+            const double df = wd[f];
+            rank += (df < de) || (df == de && wi[f] < ie);
+        }
+        if (rank < k) {
+            idx_out[n * k + rank] = ie;
+            dist_out[n * k + rank] = (float)de;
+        }
+        if (rank == k - 1) kth = de;
+    }
+    if (unsafe != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) kth = fmax(kth, __shfl_xor_sync(0xffffffffu, kth, o));
+        bad |= nkeep < k;
         if (lane == 0) unsafe[n] = (!bad && kth - qn + 2.0 * eps < tmin) ? 0 : 1;
     }
 }
@@ -644,12 +818,14 @@ extern "C" int sym_knn(const float *Q, int32_t ldq, int64_t N, const float *Ref,
     const unsigned long long *cand = nullptr;
     const float *thr = nullptr;
     const float *dq16 = nullptr;
+    const unsigned char *qrows = nullptr;   // tcgen05 scans: the packed operand rows of the queries (scan order) and their width
+    int kp = 0;
     if (method >= 2) {
         const int prec = method == 3 ? 1 : 0;
         SYM_REQUIRE(knn_tc_supported(N, M, d, k, prec), SYM_ERR_UNSUPPORTED_SHAPE,
                     "sym_knn: tcgen05 scan does not support this shape");
         int rc = knn_tc_scan(Q, ldq, N, q_perm, q_code, cl_tile, pk, M, d, k, prec, workspace, workspace_bytes, st, &cand,
-                             &thr, &ncand, &nsplit, &group, &eps_rel, &dq16);
+                             &thr, &ncand, &nsplit, &group, &eps_rel, &dq16, &qrows, &kp);
         if (rc != SYM_OK) return rc;
     } else {
         ScanPlan p;
@@ -669,6 +845,22 @@ extern "C" int sym_knn(const float *Q, int32_t ldq, int64_t N, const float *Ref,
         eps_rel = (double)(d + 4) * 5.97e-8;
     }
     SYM_REQUIRE(ncand <= RR_MAXC, SYM_ERR_UNSUPPORTED_SHAPE, "sym_knn: internal: %d candidates per row", ncand);
+    if (group == 8) {   // tcgen05 scans: candidate groups, scored from the packed tiles first
+        const unsigned grid = (unsigned)ceil_div(N, RR_THREADS / 32);
+        if (method == 3) {
+            SYM_CUDA(cudaFuncSetAttribute(knn_rerank_groups_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RR_SMEM_GROUPS));
+            knn_rerank_groups_kernel<1><<<grid, RR_THREADS, RR_SMEM_GROUPS, st>>>(
+                Q, ldq, N, Ref, ldr, M, d, k, cand, thr, ncand, nsplit, eps_rel, pk.hdr, pk.order, q_perm, dq16, qrows, pk.tc16, kp,
+                idx, dist2, unsafe);
+        } else {
+            SYM_CUDA(cudaFuncSetAttribute(knn_rerank_groups_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RR_SMEM_GROUPS));
+            knn_rerank_groups_kernel<0><<<grid, RR_THREADS, RR_SMEM_GROUPS, st>>>(
+                Q, ldq, N, Ref, ldr, M, d, k, cand, thr, ncand, nsplit, eps_rel, pk.hdr, pk.order, q_perm, dq16, qrows, pk.tc, kp,
+                idx, dist2, unsafe);
+        }
+        SYM_LAUNCH_CHECK("knn_rerank_groups_kernel");
+        return SYM_OK;
+    }
     SYM_CUDA(cudaFuncSetAttribute(knn_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RR_SMEM));
     knn_rerank_kernel<<<(unsigned)ceil_div(N, RR_THREADS / 32), RR_THREADS, RR_SMEM, st>>>(
         Q, ldq, N, Ref, ldr, pk.refT, pk.Mpad, M, d, k, cand, thr, ncand, nsplit, group, eps_rel, pk.hdr, pk.order, q_perm,

@@ -87,6 +87,6 @@ int knn_tc_fit(const float *Ref, int ldr, int64_t M, int d, const int32_t *order
 int knn_tc_scan(const float *Q, int ldq, int64_t N, const int32_t *q_perm, const int32_t *q_code,
                 const int32_t *cl_tile, KnnPacked pk, int64_t M, int d, int k, int prec, void *workspace,
                 size_t workspace_bytes, cudaStream_t st, const unsigned long long **cand, const float **thr, int *ncand,
-                int *nsplit, int *group, double *eps_rel, const float **dq16);
+                int *nsplit, int *group, double *eps_rel, const float **dq16, const unsigned char **qrows, int *kp);
 
 }  // namespace sym

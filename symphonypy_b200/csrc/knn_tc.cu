@@ -934,7 +934,8 @@ int knn_tc_fit(const float *Ref, int ldr, int64_t M, int d, const int32_t *order
 int knn_tc_scan(const float *Q, int ldq, int64_t N, const int32_t *q_perm, const int32_t *q_code,
                 const int32_t *cl_tile, KnnPacked pk, int64_t M, int d, int k, int prec, void *workspace,
                 size_t workspace_bytes, cudaStream_t st, const unsigned long long **cand, const float **thr,
-                int *ncand, int *nsplit, int *group, double *eps_rel, const float **dq16) {
+                int *ncand, int *nsplit, int *group, double *eps_rel, const float **dq16, const unsigned char **qrows,
+                int *kp) {
     TcPlan p = tc_plan(N, M, d, k, prec);
     SYM_REQUIRE(p.ok, SYM_ERR_UNSUPPORTED_SHAPE, "tcgen05 scan: d=%d k=%d does not fit", d, k);
     SYM_REQUIRE(workspace_bytes >= knn_tc_workspace(N, M, d, k, prec) - 1024, SYM_ERR_WORKSPACE_TOO_SMALL,
@@ -981,6 +982,8 @@ int knn_tc_scan(const float *Q, int ldq, int64_t N, const int32_t *q_perm, const
     // eps_rel then only covers the FP32 accumulation of the kp products and the two-piece ||r||^2
     *eps_rel = prec ? 1.0e-5 : 6.0e-5;
     *dq16 = dq_w;
+    *qrows = qpack;
+    *kp = p.kp;
     return SYM_OK;
 }
 
