@@ -208,6 +208,18 @@ int sym_cluster_cov(const float *X, int32_t ldx, int64_t M, int32_t d, const flo
 int sym_cell_confidence(const float *Xq, int32_t ldq, int64_t N, int32_t d, const float *Rq, int32_t K,
                         const float *mean, const float *inv_cov, float *out, sym_stream_t stream);
 
+/* k-means++ seeding of the no-Harmony fallback — replaces sklearn's greedy k-means++ inside
+ * KMeans(init="k-means++") at symphonypy/_utils.py:323-325 (sklearn/cluster/_kmeans.py, _kmeans_plusplus).
+ *   centre_ids[0] = first;  for c = 1..K-1: `trials` candidate rows are drawn with probability proportional to the
+ *   squared distance to the nearest centre so far — searchsorted(cumsum(closest), rand[c-1][t] * sum(closest)) — and
+ *   the candidate that lowers the total potential most becomes centre c (first one on ties).
+ *   rand [K-1, trials] f64 uniform draws in [0,1) (device);  centre_ids [K] i32 out (device): rows of X.
+ *   Distances are ||x||^2 - 2 x.c + ||c||^2 in float64 (sklearn's formula).  N < 2^31, d <= 128, trials <= 16.
+ */
+size_t sym_kmeanspp_workspace(int64_t N, int32_t trials);
+int sym_kmeanspp(const float *X, int32_t ldx, int64_t N, int32_t d, int32_t K, int32_t trials, int64_t first,
+                 const double *rand, int32_t *centre_ids, void *workspace, size_t workspace_bytes, sym_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * (6) per-cluster mapping confidence — replaces the per-group numpy of symphonypy/_utils.py:422-465
  *     (tl.per_cluster_confidence, tl.py:114-179).  Cells are grouped by a user-given

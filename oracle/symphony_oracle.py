@@ -263,6 +263,32 @@ def soft_kmeans_summary(Z, C, sigma=0.1, ref_basis="X_pca", ref_basis_loadings="
             "ref_basis_adjusted": ref_basis, "vars_use": None, "harmony_kwargs": {}, "converged": True, "R": R}
 
 
+def kmeans_plusplus_ids(X, K, first, rand):
+    """Greedy k-means++ as scikit-learn 1.9.0 runs it inside `KMeans(init="k-means++")` (`symphonypy/_utils.py:323-325`;
+    sklearn/cluster/_kmeans.py, `_kmeans_plusplus`, unit sample weights), with the random numbers made explicit:
+    `first` = row of the first centre, `rand[c-1]` = the `n_local_trials` uniform draws for centre c.
+    Returns the chosen rows [K].  Pinned to sklearn in tests/test_oracle.py by feeding it sklearn's own draws."""
+    from sklearn.metrics.pairwise import euclidean_distances
+
+    X = np.asarray(X, dtype=np.float64)
+    n = X.shape[0]
+    x2 = np.einsum("ij,ij->i", X, X)
+    ids = np.empty(K, dtype=np.int64)
+    ids[0] = first
+    closest = euclidean_distances(X[first][None, :], X, Y_norm_squared=x2, squared=True)[0]
+    pot = closest.sum()
+    for c in range(1, K):
+        rand_vals = np.asarray(rand[c - 1], dtype=np.float64) * pot
+        cand = np.searchsorted(np.cumsum(closest, dtype=np.float64), rand_vals)
+        np.clip(cand, None, n - 1, out=cand)
+        dist = euclidean_distances(X[cand], X, Y_norm_squared=x2, squared=True)
+        np.minimum(closest, dist, out=dist)
+        pots = dist.sum(axis=1)
+        best = int(np.argmin(pots))
+        pot, closest, ids[c] = pots[best], dist[best], cand[best]
+    return ids
+
+
 def run_soft_kmeans(adata_ref, ref_basis="X_pca", K=None, ref_basis_loadings="PCs", sigma=0.1, random_state=None):
     """`_utils.py:311-352` with the reference's estimator call (random_state is ours, for repeatable tests)."""
     from sklearn.cluster import KMeans

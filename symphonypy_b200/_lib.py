@@ -40,6 +40,8 @@ SIGNATURES = {
                                 c_int32, _P, c_int32, _P]),
     "sym_knn_packed_bytes": (c_size_t, [c_int64, c_int32]),
     "sym_knn_fit": (c_int32, [_P, c_int32, c_int64, c_int32, _P, _P, _P]),
+    "sym_kmeanspp_workspace": (c_size_t, [c_int64, c_int32]),
+    "sym_kmeanspp": (c_int32, [_P, c_int32, c_int64, c_int32, c_int32, c_int32, c_int64, _P, _P, _P, c_size_t, _P]),
     "sym_nearest_centroid": (c_int32, [_P, c_int32, c_int64, c_int32, _P, c_int32, _P, _P]),
     "sym_knn_workspace": (c_size_t, [c_int64, c_int64, c_int32, c_int32, c_int32]),
     "sym_knn_method_supported": (c_int32, [c_int64, c_int64, c_int32, c_int32, c_int32]),

@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_C")
 LIB = os.path.join(OUT_DIR, "libsymphony_b200.so")
-SOURCES = ["abi.cu", "project.cu", "project_tc.cu", "assign.cu", "moe.cu", "knn.cu", "knn_tc.cu", "confidence.cu"]
+SOURCES = ["abi.cu", "project.cu", "project_tc.cu", "assign.cu", "moe.cu", "knn.cu", "knn_tc.cu", "confidence.cu", "kmeans.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + os.environ.get("SYM_NVCC_EXTRA", "").split()

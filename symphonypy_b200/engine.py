@@ -472,30 +472,34 @@ def group_moments(X: torch.Tensor, codes: torch.Tensor, n_groups: int):
 
 
 # ------------------------------------------------------------------------------------- k-means (no-Harmony fallback)
-def _kmeanspp(X: torch.Tensor, Xd: torch.Tensor, x2: torch.Tensor, K: int, gen: torch.Generator) -> torch.Tensor:
-    """Greedy k-means++ seeding (Arthur & Vassilvitskii; 2 + log K candidate draws per centre, the variant
-    sklearn's `init="k-means++"` uses).  K sequential D^2 draws, all on the device, no host synchronisation."""
+def kmeanspp_draws(N: int, K: int, gen: torch.Generator, dev):
+    """The random numbers one greedy k-means++ seeding consumes: the first centre's row and, for each further centre,
+    2 + int(ln K) uniform draws (sklearn's `n_local_trials`)."""
+    trials = 2 + int(np.log(K))
+    first = int(torch.randint(N, (1,), generator=gen, device=dev).item())
+    rand = torch.rand((max(K - 1, 1), trials), generator=gen, device=dev, dtype=torch.float64)
+    return first, rand
+
+
+def kmeanspp_ids(X: torch.Tensor, K: int, first: int, rand: torch.Tensor) -> torch.Tensor:
+    """Rows of X chosen by greedy k-means++ (`sym_kmeanspp`) for the given draws: [K] int32."""
+    lib = _lib.load()
+    X = _f32c(X)
     N, d = X.shape
     dev = X.device
-    trials = 2 + int(np.log(K))
-    cent = torch.empty((K, d), device=dev, dtype=torch.float32)
-    first = torch.randint(N, (1,), generator=gen, device=dev)
-    cent[0] = X[first[0]]
-    c0 = Xd[first]
-    closest = (x2 - 2.0 * (Xd @ c0.T)[:, 0] + (c0 ** 2).sum()).clamp_min_(0.0)
-    pot = closest.sum()
-    for c in range(1, K):
-        r = torch.rand(trials, generator=gen, device=dev, dtype=torch.float64) * pot
-        ids = torch.searchsorted(torch.cumsum(closest, 0), r).clamp_max_(N - 1)
-        cand = Xd[ids]                                                       # [trials, d]
-        dc = (x2[:, None] - 2.0 * (Xd @ cand.T) + (cand ** 2).sum(1)[None, :]).clamp_min_(0.0)
-        dc = torch.minimum(dc, closest[:, None])
-        pots = dc.sum(0)
-        b = torch.argmin(pots)
-        closest = dc[:, b].contiguous()
-        pot = pots[b]
-        cent[c] = X[ids[b]]
-    return cent
+    trials = int(rand.shape[1])
+    assert rand.dtype == torch.float64 and rand.is_contiguous() and rand.shape[0] >= K - 1
+    ws = torch.empty(int(lib.sym_kmeanspp_workspace(N, trials)), device=dev, dtype=torch.uint8)
+    ids = torch.empty(K, device=dev, dtype=torch.int32)
+    _lib.check(lib.sym_kmeanspp(X.data_ptr(), X.stride(0), N, d, K, trials, int(first), rand.data_ptr(), ids.data_ptr(),
+                                ws.data_ptr(), ws.numel(), _stream(dev)), "sym_kmeanspp")
+    return ids
+
+
+def _kmeanspp(X: torch.Tensor, K: int, gen: torch.Generator) -> torch.Tensor:
+    """Greedy k-means++ centres [K, d] f32 (sklearn's `_kmeans_plusplus`), chosen on the device."""
+    first, rand = kmeanspp_draws(X.shape[0], K, gen, X.device)
+    return X[kmeanspp_ids(X, K, first, rand).long()].contiguous()
 
 
 def kmeans(X: torch.Tensor, K: int, n_init: int = 10, max_iter: int = 25, tol: float = 1e-4, seed: int | None = None):
@@ -516,7 +520,7 @@ def kmeans(X: torch.Tensor, K: int, n_init: int = 10, max_iter: int = 25, tol: f
     tol_abs = float(tol * Xd.var(dim=0, unbiased=False).mean())
     best_inertia, best_cent = None, None
     for _ in range(max(1, n_init)):
-        cent32 = _kmeanspp(X, Xd, x2, K, gen)
+        cent32 = _kmeanspp(X, K, gen)
         cent = cent32.double()
         inertia = None
         for _it in range(max_iter):

@@ -777,6 +777,24 @@ def test_kmeans_quality_matches_sklearn(cuda_device, M, d, K):
     assert inertia <= sk.inertia_ * 1.02
 
 
+@pytest.mark.parametrize("N,d,K", [(5000, 20, 30), (70000, 30, 100), (1500, 8, 200), (257, 3, 1)])
+def test_kmeanspp_kernel_matches_sklearn_restatement(cuda_device, N, d, K):
+    """`sym_kmeanspp` (sampling, trial potentials, selection and D^2 update on the device) picks the rows that
+    scikit-learn's greedy k-means++ picks for the same random draws (oracle restatement, pinned to sklearn in
+    tests/test_oracle.py).  The data is float32-representable, as the kernel holds X in float32."""
+    rng = np.random.default_rng(N + K)
+    cent = rng.normal(0, 4, size=(9, d))
+    X = (cent[rng.integers(0, 9, N)] + rng.normal(size=(N, d))).astype(np.float32)
+    Xd = torch.from_numpy(X).to(cuda_device)
+    gen = torch.Generator(device=cuda_device)
+    gen.manual_seed(N)
+    first, rand = engine.kmeanspp_draws(N, K, gen, cuda_device)
+    got = engine.kmeanspp_ids(Xd, K, first, rand).cpu().numpy()
+    want = so.kmeans_plusplus_ids(X.astype(np.float64), K, first, rand.cpu().numpy())
+    assert got[0] == first
+    assert np.array_equal(got, want), f"{(got != want).sum()} of {K} centres differ"
+
+
 def test_map_embedding_without_harmony_uses_soft_kmeans(cuda_device):
     quiet()
     query, ref = synth.small_case(N=500, M=3000, G=200, d=20, K=10, L=6, levels=(2,), seed=47)

@@ -184,3 +184,22 @@ def test_soft_kmeans_summary_matches_live_reference():
     np.testing.assert_allclose(mine["Nr"], h["Nr"], rtol=1e-12)
     for k in ("K", "sigma", "ref_basis_loadings", "ref_basis_adjusted", "vars_use", "harmony_kwargs", "converged"):
         assert mine[k] == h[k]
+
+
+def test_kmeans_plusplus_restatement_matches_sklearn():
+    """The oracle's greedy k-means++ (explicit random draws) picks the rows scikit-learn's own `kmeans_plusplus`
+    picks when it is fed the numbers sklearn's RandomState would draw: pins the restatement to sklearn 1.9.0
+    (`symphonypy/_utils.py:323-325` calls it through KMeans)."""
+    from sklearn.cluster import kmeans_plusplus
+
+    rng = np.random.default_rng(5)
+    for n, d, K, seed in ((600, 8, 12, 0), (2500, 20, 40, 3), (300, 5, 100, 11)):
+        X = np.concatenate([rng.normal(c, 0.6, size=(n // 4, d)) for c in (-3, 0, 2, 5)]).astype(np.float32).astype(np.float64)
+        _, want = kmeans_plusplus(X, K, random_state=seed)
+        # the same stream of draws: choice(n) for the first centre, then uniform(size=trials) per centre
+        rs = np.random.RandomState(seed)
+        trials = 2 + int(np.log(K))
+        first = rs.choice(X.shape[0], p=np.full(X.shape[0], 1.0 / X.shape[0]))
+        rand = np.stack([rs.uniform(size=trials) for _ in range(K - 1)])
+        got = so.kmeans_plusplus_ids(X, K, first, rand)
+        assert np.array_equal(got, want)
