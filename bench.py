@@ -87,6 +87,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline and the parity block")
     ap.add_argument("--knn-method", type=int, default=0)
+    ap.add_argument("--knn-prune", action="store_true",
+                    help="opt-in exact tile pruning of the kNN scan (same results; the headline is the full scan)")
     ap.add_argument("--extras", action="store_true", help="also time the next-row kernels (per_cell_confidence)")
     ap.add_argument("--cpu-n-map", type=int, default=20_000)
     ap.add_argument("--cpu-n-knn", type=int, default=20_000)
@@ -271,7 +273,7 @@ def workload_config(w, name, n_rank, world, args):
             "pcs": w["d"], "clusters": w["K"], "k": w["k"], "batch_levels": w["levels"],
             "l2": ("inputs larger than L2 (X is %.1f GB per step)" % (n_rank * w["G"] * 4 / 1e9)) if not w.get("knn_only")
                   else "inputs larger than L2 (embeddings + packed reference %.1f GB)" % ((n_rank + 3 * w["M"]) * w["d"] * 4 / 1e9),
-            "knn_method": args.knn_method}
+            "knn_method": args.knn_method, "knn_prune": bool(args.knn_prune)}
 
 
 # ------------------------------------------------------------------------------------------ ours
@@ -414,7 +416,7 @@ def run_device(st, ctx, steps: int, warmup: int):
             R, Zc, info = pipeline.soft_assign_and_correct(Z, st["Y"], st["inv_sigma"], st["codes"], w["levels"], st["lam"],
                                                            st["Nr"], st["C"], mark)
         lab, conf, idx, dist2, n_rep = pipeline.knn_transfer(st["index"], Zc, w["k"], st["ref_codes"], args.knn_method, mark,
-                                                             scan_events if record else None)
+                                                             scan_events if record else None, prune=args.knn_prune)
         if record:
             repaired[0] += n_rep
         last[0] = (lab, conf, info)
@@ -466,6 +468,15 @@ def roofline_of(st, ctx, res, name):
             "rows_repaired_per_step": res["repaired"],
             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400 (profiling guide)",
             "algorithmic_flops_per_launch": flops}
+    roof["kernel"] = roof["kernel"].replace("project_tc_kernel", "project_tma_kernel")
+    if args.knn_prune and st["index"].scan_stats is not None:
+        # opt-in tile pruning: the rate is counted on the tiles that were actually scanned
+        scanned, full = (int(v) for v in st["index"].scan_stats.cpu())
+        roof["pruning"] = {"tiles_scanned": scanned, "tiles_full_scan": full, "scanned_frac": scanned / max(full, 1),
+                           "note": "achieved / frac count the flops of the scanned tiles only"}
+        roof["achieved"] = ach * scanned / max(full, 1)
+        roof["frac"] = roof["achieved"] / peak_tf
+        roof["algorithmic_flops_per_launch"] = flops * scanned / max(full, 1)
     try:   # DRAM bytes of one launch: from the committed ncu capture of this workload (not measurable inside the run)
         prof = json.load(open(os.path.join(ROOT, "profiles", "knn_traffic.json"))).get(name, {})
         if prof.get("dram_bytes_per_launch") is not None and ctx.world == 1 and prof.get("cells") in (None, N):
@@ -478,7 +489,7 @@ def roofline_of(st, ctx, res, name):
         sm = res["stage_ms"]
         other = []
         for stage, kern, bytes_cell in (
-                ("project", "project_tc_kernel (tcgen05 FP16x3, X streaming)", 4.0 * G + 4.0 * d),
+                ("project", "project_tma_kernel (tcgen05 FP16x3, X tiles by TMA)", 4.0 * G + 4.0 * d),
                 ("assign", "assign_kernel", 4.0 * d + 4.0 * K),
                 ("moe_stats", "moe_stats_kernel (+ counting sort)", 4.0 * d + 4.0 * K + 4.0 * V),
                 ("moe_solve_apply", "moe_solve_kernel + moe_apply_kernel", 8.0 * d + 4.0 * K + 4.0 * V)):
@@ -756,6 +767,7 @@ def main():
     ctx = Ctx(args)
     tl.settings.device = ctx.dev
     tl.settings.knn_method = args.knn_method
+    tl.settings.knn_prune = bool(args.knn_prune)
     quiet()
     _lib.load()
     rank = ctx.rank

@@ -177,7 +177,14 @@ int sym_moe_apply(const float *Zin, int32_t ldzin, const float *R, int64_t N, in
  *   codes of the k neighbours; conf[n] = winning votes / k.  ref_codes [M]; entries of idx outside [0, M) are
  *   ignored (label -1 if a row has no valid neighbour).  dist2 NULL: weights="uniform"; dist2 [N,k] (squared
  *   distances from sym_knn): weights="distance" (1/distance, sklearn's zero-distance rule), conf = winning weight share.
- */
+  * Exact tile pruning (opt-in): OR `SYM_KNN_PRUNE` into `method` (2 or 3).  sym_knn_fit stores a bounding ball for
+ *   every 128-row tile of the packed reference; a scan CTA (256 query rows) then skips the tiles whose ball cannot hold
+ *   a candidate of any of its rows:  max(0, |c_q - c_t| - r_q - r_t)^2 >= max over its rows of (threshold + ||q||^2).
+ *   Results are identical to the full scan (every skipped reference is provably farther than the row's threshold;
+ *   the certificate of the re-rank is unchanged).  The first two uint64 of `workspace` then hold
+ *   {tiles scanned, tiles a full scan visits}, summed over the scan's CTAs.  Data dependent: nothing is skipped for
+ *   unclustered data.
+*/
 size_t sym_knn_packed_bytes(int64_t M, int32_t d);
 int sym_knn_fit(const float *Ref, int32_t ldr, int64_t M, int32_t d, const int32_t *order, void *packed,
                 sym_stream_t stream);
@@ -185,6 +192,7 @@ int sym_nearest_centroid(const float *X, int32_t ldx, int64_t N, int32_t d, cons
                          int32_t *code, sym_stream_t stream);
 size_t sym_knn_workspace(int64_t N, int64_t M, int32_t d, int32_t k, int32_t method);
 int sym_knn_method_supported(int64_t N, int64_t M, int32_t d, int32_t k, int32_t method);
+#define SYM_KNN_PRUNE 0x100
 int sym_knn(const float *Q, int32_t ldq, int64_t N, const float *Ref, int32_t ldr, int64_t M,
             const void *packed, int32_t d, int32_t k, int32_t method, const int32_t *q_perm, const int32_t *q_code,
             const int32_t *cl_tile, int32_t *idx, float *dist2, uint8_t *unsafe, void *workspace,

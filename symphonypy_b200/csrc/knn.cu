@@ -804,6 +804,8 @@ extern "C" int sym_knn(const float *Q, int32_t ldq, int64_t N, const float *Ref,
                 "sym_knn: Expected n_neighbors <= n_samples_fit, but n_neighbors = %d, n_samples_fit = %lld", k,
                 (long long)M);
     SYM_REQUIRE(k <= 120 && d <= 128, SYM_ERR_UNSUPPORTED_SHAPE, "sym_knn: k=%d (<=120) d=%d (<=128) unsupported", k, d);
+    const int prune = (method & SYM_KNN_PRUNE) ? 1 : 0;   // opt-in exact tile pruning (tcgen05 scans)
+    method &= ~SYM_KNN_PRUNE;
     SYM_REQUIRE(method >= 0 && method <= 3, SYM_ERR_INVALID_ARGUMENT, "sym_knn: unknown method %d", method);
     SYM_REQUIRE(workspace_bytes >= sym_knn_workspace(N, M, d, k, method), SYM_ERR_WORKSPACE_TOO_SMALL,
                 "sym_knn: workspace too small");
@@ -824,7 +826,7 @@ extern "C" int sym_knn(const float *Q, int32_t ldq, int64_t N, const float *Ref,
         const int prec = method == 3 ? 1 : 0;
         SYM_REQUIRE(knn_tc_supported(N, M, d, k, prec), SYM_ERR_UNSUPPORTED_SHAPE,
                     "sym_knn: tcgen05 scan does not support this shape");
-        int rc = knn_tc_scan(Q, ldq, N, q_perm, q_code, cl_tile, pk, M, d, k, prec, workspace, workspace_bytes, st, &cand,
+        int rc = knn_tc_scan(Q, ldq, N, q_perm, q_code, cl_tile, pk, M, d, k, prec, prune, workspace, workspace_bytes, st, &cand,
                              &thr, &ncand, &nsplit, &group, &eps_rel, &dq16, &qrows, &kp);
         if (rc != SYM_OK) return rc;
     } else {

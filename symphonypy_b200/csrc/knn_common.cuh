@@ -16,7 +16,7 @@ struct KnnHeader {
 };
 
 // Layout of the opaque "packed reference" buffer produced by sym_knn_fit:
-//   [KnnHeader | norm2 f32[Mpad] | refT f32[d4][Mpad] | BF16x3 tiles | FP16 tiles | order i32[Mpad]]
+//   [KnnHeader | norm2 f32[Mpad] | refT f32[d4][Mpad] | BF16x3 tiles | FP16 tiles | order i32[Mpad] | tile_c | tile_r]
 struct KnnPacked {
     KnnHeader *hdr;
     float *norm2;
@@ -24,6 +24,9 @@ struct KnnPacked {
     unsigned char *tc;    // tensor-core operand section, BF16x3 (layout private to knn_tc.cu)
     unsigned char *tc16;  // tensor-core operand section, single FP16
     int32_t *order;     // [Mpad] packed position -> original reference row (identity when no order was given)
+    // bounding ball of every 128-position tile of the packed reference (opt-in exact tile pruning of the tcgen05 scans)
+    float *tile_c;      // [Mpad / 128][d4] centre (mean of the tile's rows)
+    float *tile_r;      // [Mpad / 128] radius (largest distance of a row to the centre, rounded up)
     int64_t Mpad;
     int d4;
     size_t total;
@@ -54,6 +57,12 @@ inline KnnPacked knn_packed_layout(void *base, int64_t M, int d) {
     off = (off + 255) & ~(size_t)255;
     p.order = (int32_t *)(b + off);
     off += (size_t)p.Mpad * sizeof(int32_t);
+    off = (off + 255) & ~(size_t)255;
+    p.tile_c = (float *)(b + off);
+    off += (size_t)(p.Mpad / 128) * p.d4 * sizeof(float);
+    p.tile_r = (float *)(b + off);
+    off += (size_t)(p.Mpad / 128) * sizeof(float);
+    off = (off + 255) & ~(size_t)255;
     p.total = off;
     return p;
 }
@@ -82,10 +91,12 @@ __device__ __forceinline__ float knn_key_score(unsigned long long key) {
 // `prec`: 0 = BF16x3 split operands (FP32-class scores), 1 = single FP16 operands (three times fewer MMAs;
 // the scan reports the exact rounding residual of every query row in *dq16 for the re-rank's error bound)
 bool knn_tc_supported(int64_t N, int64_t M, int d, int k, int prec);
-size_t knn_tc_workspace(int64_t N, int64_t M, int d, int k, int prec);
+size_t knn_tc_workspace(int64_t N, int64_t M, int d, int k, int prec, int prune = 1);
 int knn_tc_fit(const float *Ref, int ldr, int64_t M, int d, const int32_t *order, KnnPacked pk, cudaStream_t st);
+// `prune`: skip reference tiles whose bounding ball cannot hold a candidate of any row of the CTA (exact; opt-in).
+// The first 16 bytes of the workspace then receive {tiles scanned, tiles a full scan visits} (two uint64).
 int knn_tc_scan(const float *Q, int ldq, int64_t N, const int32_t *q_perm, const int32_t *q_code,
-                const int32_t *cl_tile, KnnPacked pk, int64_t M, int d, int k, int prec, void *workspace,
+                const int32_t *cl_tile, KnnPacked pk, int64_t M, int d, int k, int prec, int prune, void *workspace,
                 size_t workspace_bytes, cudaStream_t st, const unsigned long long **cand, const float **thr, int *ncand,
                 int *nsplit, int *group, double *eps_rel, const float **dq16, const unsigned char **qrows, int *kp);
 

@@ -387,6 +387,100 @@ __device__ __noinline__ float tc_drain(unsigned long long *heap, int kc, const f
     return thr;
 }
 
+// ------------------------------------------------------------------------------------------ exact tile pruning (opt-in)
+// Every 128-position tile of the packed reference (positions are in coarse-cluster order, so a tile is a compact
+// piece of the data) has a bounding ball (centre, radius), computed once at fit time; every CTA of a scan has one for
+// its 256 query rows.  No row of the CTA can have a neighbour closer than  LB = max(0, |c_q - c_t| - r_q - r_t)^2  in
+// the tile, so the tile is skipped when LB >= max over the CTA's rows of (row threshold + ||q||^2): every reference of
+// a skipped tile has EXACT score >= that row's threshold at the time >= its final threshold — the certificate of the
+// re-rank holds as it stands (for skipped references even without the scan's rounding error).
+// The producer warp decides, 32 tiles at a time (one per lane), from the thresholds the selection threads publish after
+// every drain (stale = larger = safe); the tiles that remain flow to the issuers and the selection warps through a ring
+// of tile numbers in shared memory, closed by a -1.
+struct TcPrune {
+    const float *tile_c, *tile_r;   // reference tiles: centre [ntiles][d4], radius [ntiles]
+    const float *qb_c, *qb_r;       // groups of 32 query rows: centre [groups][d4], radius [groups] (-1: empty group)
+    const float *qn2;               // ||q||^2 per row, scan order
+    const KnnHeader *hdr;
+    unsigned long long *stats;      // {tiles scanned, tiles of a full scan}
+    int d, d4, prec;
+};
+__device__ __forceinline__ float tc_round_up(float x) { return x + fabsf(x) * 1e-4f; }
+constexpr int TC_RING = 32;         // tile numbers in flight between producer and selection (stages + accumulators < 32)
+
+// one warp per reference tile: centre = mean of its rows, radius = largest distance to it (rounded up)
+__global__ void __launch_bounds__(256)
+tc_tile_bounds_kernel(const float *__restrict__ refT, int64_t Mpad, int64_t M, int d, int d4, float *__restrict__ tile_c,
+                      float *__restrict__ tile_r) {
+    const int lane = threadIdx.x & 31;
+    const int64_t tile = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (tile >= Mpad / TC_BN) return;
+    const int64_t p0 = tile * TC_BN + lane * 4;
+    const int cnt = (int)max((int64_t)0, min((int64_t)TC_BN, M - tile * TC_BN));
+    float *c = tile_c + tile * d4;
+    float r2[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < d4; ++j) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < d) v = *reinterpret_cast<const float4 *>(refT + (int64_t)j * Mpad + p0);   // padding positions hold 0
+        float sum = (v.x + v.y) + (v.z + v.w);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mean = cnt > 0 ? sum / (float)cnt : 0.f;
+        if (lane == 0) c[j] = mean;
+        r2[0] = fmaf(v.x - mean, v.x - mean, r2[0]);
+        r2[1] = fmaf(v.y - mean, v.y - mean, r2[1]);
+        r2[2] = fmaf(v.z - mean, v.z - mean, r2[2]);
+        r2[3] = fmaf(v.w - mean, v.w - mean, r2[3]);
+    }
+    float m = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+        if (p0 + e < M) m = fmaxf(m, r2[e]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) tile_r[tile] = sqrtf(m) * 1.0001f + 1e-30f;
+}
+
+// one warp per group of 32 query rows (= the rows of one selection warp), `rows`/32 groups per scan CTA: centre and
+// radius of the group (radius -1: no real row in the group), ||q||^2 of every row (scan order).
+// (One ball per CTA is not enough: a CTA that straddles two clusters of the sorted queries has a ball as large as the
+// distance between them and prunes nothing.)
+__global__ void __launch_bounds__(256)
+tc_qbounds_kernel(const float *__restrict__ Q, int ldq, int64_t N, const int32_t *__restrict__ q_perm, int d, int d4,
+                  float *__restrict__ qb_c, float *__restrict__ qb_r, float *__restrict__ qn2) {
+    __shared__ float c_s[8][128];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t group = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    const int64_t row = group * 32 + lane;
+    const bool real = row < N;
+    const float *q = Q + (real ? (q_perm ? (int64_t)q_perm[row] : row) : 0) * ldq;
+    const int cnt = __popc(__ballot_sync(0xffffffffu, real));
+    float n2 = 0.f;
+    for (int j = 0; j < d4; ++j) {
+        const float v = (real && j < d) ? q[j] : 0.f;
+        n2 = fmaf(v, v, n2);
+        float sum = v;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mean = cnt > 0 ? sum / (float)cnt : 0.f;
+        if (lane == 0) {
+            c_s[warp][j] = mean;
+            qb_c[group * d4 + j] = mean;
+        }
+    }
+    __syncwarp();
+    float r2 = 0.f;
+    if (real)
+        for (int j = 0; j < d; ++j) {
+            const float df = q[j] - c_s[warp][j];
+            r2 = fmaf(df, df, r2);
+        }
+    qn2[row] = n2;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r2 = fmaxf(r2, __shfl_xor_sync(0xffffffffu, r2, o));
+    if (lane == 0) qb_r[group] = cnt > 0 ? sqrtf(r2) * 1.0001f + 1e-30f : -1.f;
+}
+
 // One chain of MMAs: D[tmem] = A (shared-memory descriptor or tensor memory) x B (shared-memory descriptor), KS
 // slices of K = 16 (KS = 0: `ksteps` at run time).  Everything the chain needs is computed BEFORE the issuer waits for
 // the accumulator: what follows the wait is on the critical path of every tile (accumulator released -> refilled).
@@ -408,13 +502,13 @@ __device__ __forceinline__ void tc_issue_chain(uint32_t d_tmem, uint64_t q_desc,
     }
 }
 
-template <int TC_QT, int HV, int SS_MODE>
+template <int TC_QT, int HV, int SS_MODE, int PRUNE>
 __global__ void __launch_bounds__(128 + 128 * TC_QT * HV, 1)
 knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char *__restrict__ rpack, int64_t N,
                    const int32_t *__restrict__ q_perm, const int32_t *__restrict__ q_code,
                    const int32_t *__restrict__ cl_tile, int64_t M, int kp, int kc, int stages, int nbuf,
                    int tiles_per_split, int ntiles_all, uint32_t idesc, int fifo_depth, int period_mask,
-                   unsigned long long *__restrict__ cand_out, float *__restrict__ thr_out) {
+                   unsigned long long *__restrict__ cand_out, float *__restrict__ thr_out, const TcPrune pr) {
     extern __shared__ __align__(1024) unsigned char smraw[];
     const uint32_t tile_bytes = (uint32_t)tc_tile_bytes(kp);
     unsigned char *r_s = smraw;                                        // [stages][tile_bytes]
@@ -432,8 +526,13 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
     uint32_t *tmem_slot = (uint32_t *)(t_empty + 4);
     volatile uint32_t *turn = tmem_slot + 1;      // sequence number of the next chain allowed to issue
     uint32_t *pair_lock = tmem_slot + 4;          // [TC_QT * 4] one per (query tile, quadrant): serialises heap drains (HV = 2)
+    // pruning: tile numbers on their way from the producer to the selection warps, the rows' published thresholds,
+    // the CTA's centre (after the 1 KB that holds the barriers; unused otherwise)
+    int *ring_s = (int *)(tmem_slot + 4 + 4 * TC_QT);           // [TC_RING]
+    float *rowT_s = (float *)(ring_s + TC_RING);                 // [TC_QT * TC_BM]
+    float *cq_s = rowT_s + TC_QT * TC_BM;                        // [TC_QT * 4][d4 <= 84]: centres of the CTA's row groups
     // SS experiment: the query operand stays in shared memory (UMMA tile layout) instead of tensor memory
-    unsigned char *q_s = (unsigned char *)(((uintptr_t)(tmem_slot + 4 + 4 * TC_QT) + 1023) & ~(uintptr_t)1023);   // [TC_QT][tile_bytes]
+    unsigned char *q_s = (unsigned char *)(((uintptr_t)(cq_s + TC_QT * 4 * 84) + 1023) & ~(uintptr_t)1023);   // [TC_QT][tile_bytes]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int split = blockIdx.y, nsplit = gridDim.y;
@@ -459,6 +558,12 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
         for (int i = 0; i < 4; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4 * HV); }
         *turn = 0u;
         for (int i = 0; i < 4 * TC_QT; ++i) pair_lock[i] = 0u;
+    }
+    if (PRUNE) {
+        for (int i = threadIdx.x; i < TC_QT * TC_BM; i += blockDim.x) rowT_s[i] = INFINITY;
+        for (int i = threadIdx.x; i < TC_QT * 4 * pr.d4; i += blockDim.x) cq_s[i] = pr.qb_c[(size_t)blockIdx.x * TC_QT * 4 * pr.d4 + i];
+    }
+    if (threadIdx.x == 0) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {  // TMEM: all 512 columns, owned by this warp
@@ -509,7 +614,75 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
     }
     if (warp == 0) {
         // ===== producer: one bulk copy per reference tile =====
-        if (lane == 0) {
+        if (PRUNE) {
+            // the whole warp walks the cyclic tile order 32 tiles at a time: lane <-> tile, bound against the CTA's
+            // largest published (threshold + ||q||^2); lane 0 issues the copies of the tiles that remain
+            constexpr int NG = TC_QT * 4;   // groups of 32 rows (one per selection warp), each with its own ball
+            float rq[NG];
+#pragma unroll
+            for (int g = 0; g < NG; ++g) rq[g] = pr.qb_r[(size_t)blockIdx.x * NG + g];
+            int s = 0, issued = 0;
+            uint32_t ph = 0;
+            for (int base = 0; base < ntiles; base += 32) {
+                float tc[NG];   // per group: the largest published (threshold + ||q||^2) of its rows
+                bool all_finite = true;
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    float v = ((volatile float *)rowT_s)[g * 32 + lane];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+                    tc[g] = v;
+                    all_finite &= v < INFINITY;
+                }
+                const int i = base + lane;
+                int t = t_home + i;
+                if (t >= t_end) t -= ntiles;
+                bool keep = i < ntiles;
+                if (keep && all_finite) {
+                    const float *c = pr.tile_c + (size_t)t * pr.d4;
+                    float d2[NG];
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) d2[g] = 0.f;
+                    for (int j = 0; j < pr.d; ++j) {
+                        const float cj = __ldg(c + j);
+#pragma unroll
+                        for (int g = 0; g < NG; ++g) {
+                            const float df = cq_s[g * pr.d4 + j] - cj;
+                            d2[g] = fmaf(df, df, d2[g]);
+                        }
+                    }
+                    const float rt = __ldg(pr.tile_r + t);
+                    keep = false;
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) {
+                        if (rq[g] < 0.f) continue;   // no real row in this group
+                        const float gap = sqrtf(d2[g]) * 0.9999f - rq[g] - rt;   // (rounded towards "keep")
+                        keep |= !(gap > 0.f && gap * gap * 0.9999f >= tc[g]);
+                    }
+                }
+                unsigned mask = __ballot_sync(0xffffffffu, keep);
+                while (mask) {
+                    const int b = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const int tb = __shfl_sync(0xffffffffu, t, b);
+                    if (lane == 0) {
+                        mbar_wait_sleepy(&r_empty[s], ph ^ 1);
+                        ring_s[issued & (TC_RING - 1)] = tb;
+                        mbar_arrive_expect_tx(&r_full[s], tile_bytes);
+                        bulk_g2s(r_s + (size_t)s * tile_bytes, rpack + (size_t)tb * tile_bytes, tile_bytes, &r_full[s]);
+                    }
+                    ++issued;
+                    if (++s == stages) { s = 0; ph ^= 1; }
+                }
+            }
+            if (lane == 0) {   // end of the tile stream
+                mbar_wait_sleepy(&r_empty[s], ph ^ 1);
+                ring_s[issued & (TC_RING - 1)] = -1;
+                mbar_arrive(&r_full[s]);
+                atomicAdd(pr.stats, (unsigned long long)issued);
+                atomicAdd(pr.stats + 1, (unsigned long long)ntiles);
+            }
+        } else if (lane == 0) {
             int s = 0, t = t_home;
             uint32_t ph = 0;  // ring position and phase kept incrementally: no integer division on any per-tile path
             for (int i = 0; i < ntiles; ++i) {
@@ -547,7 +720,7 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
         auto issue_loop = [&](auto ks_tag) {
         constexpr int KS = decltype(ks_tag)::value;
         uint64_t r_desc = r_desc0;
-        for (int i = 0; i < ntiles; ++i) {
+        for (int i = 0; PRUNE || i < ntiles; ++i) {
             // operands of this chain, ready before the waits
             const uint32_t d_tmem = tmem_base + acc0 + (uint32_t)(buf * TC_BN);
             const uint32_t full_bar = smem_u32(&t_full[buf]), empty_bar = smem_u32(&r_empty[s]);
@@ -563,6 +736,14 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
             }
             TC_CLK(c3);
             tc_fence_after();
+            if (PRUNE && ring_s[i & (TC_RING - 1)] < 0) {   // end of the tile stream: wake the selection warps, stop
+                if (leader) {
+                    mbar_arrive(&t_full[buf]);
+                    if (ordered) *turn = (uint32_t)(i * TC_QT + q) + 1u;
+                }
+                __syncwarp();
+                break;
+            }
             if (leader) {
 #ifndef TC_EXPERIMENT_NO_MMA
                 tc_issue_chain<ss_mode, KS>(d_tmem, q_desc, a_tmem, r_desc, idesc, ksteps);
@@ -613,7 +794,17 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
 #ifdef TC_PROFILE
         long long prof_0 = 0, prof_1 = 0, prof_2 = 0, prof_3 = 0, prof_5 = 0, prof_6 = 0, prof_7 = 0, prof_14 = 0, prof_15 = 0;
 #endif
-        for (int i = 0; i < ntiles; ++i) {
+        // pruning: what this row publishes after a drain is (threshold + ||q||^2) in exact units
+        float pub_scale = 1.f, pub_add = -INFINITY;
+        if (PRUNE) {
+            const int64_t n_row = ((int64_t)blockIdx.x * TC_QT + qt) * TC_BM + row;
+            if (pr.prec) {
+                const float s16 = pr.hdr->scale16;
+                pub_scale = 1.f / (s16 * s16);
+            }
+            if (n_row < N) pub_add = pr.qn2[n_row];   // (rows past the end never hold a tile back)
+        }
+        for (int i = 0; PRUNE || i < ntiles; ++i) {
             TC_CLK(c0);
 #ifdef TC_SLEEPY_SELECT
             mbar_wait_sleepy(&t_full[buf], use & 1);
@@ -621,9 +812,16 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
             mbar_wait_handoff(&t_full[buf], use & 1);
 #endif
             tc_fence_after();
-            const uint32_t ref0 = ref_cur;
-            ref_cur += TC_BN;
-            if (--until_wrap == 0) ref_cur = (uint32_t)(blockIdx.y * tiles_per_split * TC_BN) + col0;
+            uint32_t ref0;
+            if (PRUNE) {
+                const int t = ring_s[i & (TC_RING - 1)];
+                if (t < 0) break;   // end of the tile stream
+                ref0 = (uint32_t)(t * TC_BN) + col0;
+            } else {
+                ref0 = ref_cur;
+                ref_cur += TC_BN;
+                if (--until_wrap == 0) ref_cur = (uint32_t)(blockIdx.y * tiles_per_split * TC_BN) + col0;
+            }
             const uint32_t acc = lane_base + (uint32_t)(buf * TC_BN);
 #ifdef TC_EXPERIMENT_NO_SELECT
             tc_fence_before();
@@ -669,6 +867,7 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
                     thr = tc_drain<GN>(heap, kc, fifo, qn, thr, lock, lane);
                     qn = max(qn - 1, 0);
                     TC_ACC(15, 1);
+                    if (PRUNE) rowT_s[qt * TC_BM + row] = tc_round_up(fmaf(thr, pub_scale, pub_add));
                 }
                 if (hit) {   // park the tile's 16 group minima and its first position; nothing else happens here
                     float *f = fifo + qn * (GN + 4);
@@ -697,6 +896,7 @@ knn_scan_tc_kernel(const unsigned char *__restrict__ qrows, const unsigned char 
                 thr = tc_drain<GN>(heap, kc, fifo, qn, thr, lock, lane);
                 qn = max(qn - 1, 0);
                 TC_ACC(14, 1);
+                if (PRUNE) rowT_s[qt * TC_BM + row] = tc_round_up(fmaf(thr, pub_scale, pub_add));
             }
             __syncwarp();
 #ifdef TC_PROFILE
@@ -820,7 +1020,7 @@ namespace {
 struct TcPlan {
     int kp, kc, fifo, period_mask, hv, qt, stages, nbuf, nsplit, tiles_per_split, ntiles, ss;
     int64_t qtiles;
-    size_t smem, qpack_bytes, cand_bytes, thr_bytes, dq_bytes;
+    size_t smem, qpack_bytes, cand_bytes, thr_bytes, dq_bytes, prune_bytes;
     bool ok;
 };
 
@@ -861,7 +1061,7 @@ TcPlan tc_plan(int64_t N, int64_t M, int d, int k, int prec) {
         // parked tiles per row: up to 4, as many as fit beside >= 3 reference stages
         for (p.fifo = force_fifo ? atoi(force_fifo) : 4; p.fifo >= 1; --p.fifo) {
             fixed = 64 /* pair locks */ + (size_t)qt * TC_BM * ((size_t)tc_heap_stride(kc) * 8 + (size_t)p.hv * tc_fifo_stride(p.fifo, gn) * 4) +
-                    512 /* barriers */ + 1024 /* alignment slack */ + (ss ? (size_t)qt * tile + 1024 : 0);
+                    512 /* barriers */ + 4096 /* pruning: ring, thresholds, centres */ + 1024 /* alignment slack */ + (ss ? (size_t)qt * tile + 1024 : 0);
             stages = budget > fixed ? (int)((budget - fixed) / tile) : 0;
             if (stages >= 3 || p.fifo == 1 || force_fifo) break;
         }
@@ -895,6 +1095,8 @@ TcPlan tc_plan(int64_t N, int64_t M, int d, int k, int prec) {
     p.nsplit = (int)ceil_div(p.ntiles, p.tiles_per_split);
     p.qpack_bytes = (size_t)p.qtiles * p.qt * TC_BM * p.kp * 2;  // row-major query operand rows
     p.dq_bytes = prec ? (((size_t)p.qtiles * p.qt * TC_BM * sizeof(float) + 255) & ~(size_t)255) : 0;
+    // pruning: CTA centres [qtiles][d4], radii [qtiles], ||q||^2 [rows]
+    p.prune_bytes = (((size_t)p.qtiles * p.qt * 4 * (((d + 3) & ~3) + 1) + (size_t)p.qtiles * p.qt * TC_BM) * sizeof(float) + 255) & ~(size_t)255;
     p.cand_bytes = ((size_t)N * p.nsplit * kc * 8 + 255) & ~(size_t)255;
     p.thr_bytes = ((size_t)N * p.nsplit * 4 + 255) & ~(size_t)255;
     return p;
@@ -911,10 +1113,11 @@ bool knn_tc_supported(int64_t N, int64_t M, int d, int k, int prec) {
     return tc_plan(N, M, d, k, prec).ok;
 }
 
-size_t knn_tc_workspace(int64_t N, int64_t M, int d, int k, int prec) {
+size_t knn_tc_workspace(int64_t N, int64_t M, int d, int k, int prec, int) {
     if (!knn_tc_supported(N, M, d, k, prec)) return 0;
     TcPlan p = tc_plan(N, M, d, k, prec);
-    return ((p.qpack_bytes + 255) & ~(size_t)255) + p.cand_bytes + p.thr_bytes + p.dq_bytes + 1024;
+    return 256 /* scan statistics */ + ((p.qpack_bytes + 255) & ~(size_t)255) + p.cand_bytes + p.thr_bytes + p.dq_bytes +
+           p.prune_bytes + 1024;
 }
 
 int knn_tc_fit(const float *Ref, int ldr, int64_t M, int d, const int32_t *order, KnnPacked pk, cudaStream_t st) {
@@ -922,6 +1125,9 @@ int knn_tc_fit(const float *Ref, int ldr, int64_t M, int d, const int32_t *order
     const int64_t rows_pad = knn_mpad(M);
     tc_scale_kernel<<<1, 1, 0, st>>>(pk.hdr);   // after knn_fit_kernel (same stream): needs header.rmax2
     SYM_LAUNCH_CHECK("tc_scale_kernel");
+    tc_tile_bounds_kernel<<<(unsigned)ceil_div(rows_pad / TC_BN, 8), 256, 0, st>>>(pk.refT, pk.Mpad, M, d, pk.d4, pk.tile_c,
+                                                                                    pk.tile_r);   // after knn_fit_kernel: needs refT
+    SYM_LAUNCH_CHECK("tc_tile_bounds_kernel");
     for (int prec = 0; prec < 2; ++prec) {
         const int kp = tc_kp(d, prec);
         dim3 grid((unsigned)ceil_div(rows_pad, 256), (unsigned)(kp / 8));
@@ -932,7 +1138,7 @@ int knn_tc_fit(const float *Ref, int ldr, int64_t M, int d, const int32_t *order
 }
 
 int knn_tc_scan(const float *Q, int ldq, int64_t N, const int32_t *q_perm, const int32_t *q_code,
-                const int32_t *cl_tile, KnnPacked pk, int64_t M, int d, int k, int prec, void *workspace,
+                const int32_t *cl_tile, KnnPacked pk, int64_t M, int d, int k, int prec, int prune, void *workspace,
                 size_t workspace_bytes, cudaStream_t st, const unsigned long long **cand, const float **thr,
                 int *ncand, int *nsplit, int *group, double *eps_rel, const float **dq16, const unsigned char **qrows,
                 int *kp) {
@@ -941,10 +1147,22 @@ int knn_tc_scan(const float *Q, int ldq, int64_t N, const int32_t *q_perm, const
     SYM_REQUIRE(workspace_bytes >= knn_tc_workspace(N, M, d, k, prec) - 1024, SYM_ERR_WORKSPACE_TOO_SMALL,
                 "tcgen05 scan: workspace too small");
     unsigned char *w = (unsigned char *)workspace;
+    unsigned long long *stats_w = (unsigned long long *)w; w += 256;
     unsigned char *qpack = w; w += (p.qpack_bytes + 255) & ~(size_t)255;
     unsigned long long *cand_w = (unsigned long long *)w; w += p.cand_bytes;
     float *thr_w = (float *)w; w += p.thr_bytes;
-    float *dq_w = prec ? (float *)w : nullptr;
+    float *dq_w = prec ? (float *)w : nullptr; w += p.dq_bytes;
+    const int d4 = (d + 3) & ~3;
+    const size_t ngroups = (size_t)p.qtiles * p.qt * 4;   // groups of 32 query rows
+    float *qbc_w = (float *)w, *qbr_w = qbc_w + ngroups * d4, *qn2_w = qbr_w + ngroups;
+    if (p.hv != 1) prune = 0;   // (the two-warps-per-quadrant experiment has no pruning instantiation)
+    TcPrune pr{};
+    if (prune) {
+        SYM_CUDA(cudaMemsetAsync(stats_w, 0, 16, st));
+        tc_qbounds_kernel<<<(unsigned)p.qtiles, p.qt * TC_BM, 0, st>>>(Q, ldq, N, q_perm, d, d4, qbc_w, qbr_w, qn2_w);
+        SYM_LAUNCH_CHECK("tc_qbounds_kernel");
+        pr = TcPrune{pk.tile_c, pk.tile_r, qbc_w, qbr_w, qn2_w, pk.hdr, stats_w, d, d4, prec};
+    }
     {
         const int64_t rows_pad = p.qtiles * p.qt * TC_BM;
         tc_pack_rows_kernel<<<(unsigned)ceil_div(rows_pad, 8), 256, 0, st>>>(Q, ldq, N, rows_pad, d, p.kp, q_perm, qpack,
@@ -952,23 +1170,26 @@ int knn_tc_scan(const float *Q, int ldq, int64_t N, const int32_t *q_perm, const
         SYM_LAUNCH_CHECK("tc_pack_rows_kernel(query)");
     }
     dim3 grid((unsigned)p.qtiles, (unsigned)p.nsplit);
-#define SYM_TC_LAUNCH(QT, HV, SS)                                                                                     \
+#define SYM_TC_LAUNCH(QT, HV, SS, PR)                                                                                 \
     do {                                                                                                              \
-        SYM_CUDA(cudaFuncSetAttribute(knn_scan_tc_kernel<QT, HV, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+        SYM_CUDA(cudaFuncSetAttribute(knn_scan_tc_kernel<QT, HV, SS, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                       (int)p.smem));                                                                  \
-        knn_scan_tc_kernel<QT, HV, SS><<<grid, 128 + 128 * QT * HV, p.smem, st>>>(                                    \
+        knn_scan_tc_kernel<QT, HV, SS, PR><<<grid, 128 + 128 * QT * HV, p.smem, st>>>(                                \
             qpack, prec ? pk.tc16 : pk.tc, N, q_perm, q_code, cl_tile, M, p.kp, p.kc, p.stages, p.nbuf,               \
-            p.tiles_per_split, p.ntiles, prec ? TC_IDESC_F16 : TC_IDESC_BF16, p.fifo, p.period_mask, cand_w, thr_w);   \
+            p.tiles_per_split, p.ntiles, prec ? TC_IDESC_F16 : TC_IDESC_BF16, p.fifo, p.period_mask, cand_w, thr_w,    \
+            pr);                                                                                                      \
     } while (0)
-#define SYM_TC_LAUNCH_SS(QT, HV)                                                                                      \
+#define SYM_TC_LAUNCH_SS(QT, HV, PR)                                                                                  \
     do {                                                                                                              \
-        if (p.ss) SYM_TC_LAUNCH(QT, HV, 1);                                                                           \
-        else SYM_TC_LAUNCH(QT, HV, 0);                                                                                \
+        if (p.ss) SYM_TC_LAUNCH(QT, HV, 1, PR);                                                                       \
+        else SYM_TC_LAUNCH(QT, HV, 0, PR);                                                                            \
     } while (0)
-    if (p.qt == 2 && p.hv == 2) SYM_TC_LAUNCH_SS(2, 2);
-    else if (p.qt == 2) SYM_TC_LAUNCH_SS(2, 1);
-    else if (p.hv == 2) SYM_TC_LAUNCH_SS(1, 2);
-    else SYM_TC_LAUNCH_SS(1, 1);
+    if (p.qt == 2 && p.hv == 2) SYM_TC_LAUNCH_SS(2, 2, 0);
+    else if (p.qt == 2 && prune) SYM_TC_LAUNCH_SS(2, 1, 1);
+    else if (p.qt == 2) SYM_TC_LAUNCH_SS(2, 1, 0);
+    else if (p.hv == 2) SYM_TC_LAUNCH_SS(1, 2, 0);
+    else if (prune) SYM_TC_LAUNCH_SS(1, 1, 1);
+    else SYM_TC_LAUNCH_SS(1, 1, 0);
 #undef SYM_TC_LAUNCH_SS
 #undef SYM_TC_LAUNCH
     SYM_LAUNCH_CHECK("knn_scan_tc_kernel");

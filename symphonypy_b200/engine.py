@@ -19,6 +19,7 @@ from . import _lib
 CLIP = 10.0  # `symphonypy/_utils.py:253`: max_value, fixed by the reference API
 KNN_AUTO, KNN_FFMA, KNN_TCGEN05, KNN_TC16 = 0, 1, 2, 3
 KNN_TC = KNN_TCGEN05
+KNN_PRUNE_FLAG = 0x100   # SYM_KNN_PRUNE: exact tile pruning, ORed into the method of a tcgen05 scan
 PROJECT_TC = os.environ.get("SYM_PROJECT_TC", "1") != "0"   # tensor-core projection when the layout allows
 
 
@@ -255,6 +256,7 @@ class KnnIndex:
     cl_tile: torch.Tensor | None = None     # [C] i32: first 128-row tile of the packed reference with rows of cluster c
     workspace: dict = field(default_factory=dict)
     first_tier: dict = field(default_factory=dict)   # k -> scan method to start with (see knn_search_certified)
+    scan_stats: torch.Tensor | None = None           # device [2] int64 of the last pruned scan: tiles scanned, tiles of a full scan
 
 
 LOCALITY_MIN_REF = 32768     # below this the whole reference is a few hundred tiles: no ordering
@@ -279,7 +281,16 @@ def _coarse_centroids(ref: torch.Tensor, C: int, iters: int = 4) -> torch.Tensor
     g = torch.Generator(device="cpu")
     g.manual_seed(12345)
     sample = ref[torch.randperm(M, generator=g)[: min(M, 128 * C)].to(ref.device)].contiguous()
-    cent = sample[:C].clone()
+    if os.environ.get("SYM_KNN_COARSE_INIT", "kpp") == "kpp":
+        # k-means++ seeding (sym_kmeanspp, fixed draws): with random starting points Lloyd often leaves two well
+        # separated groups of cells in one coarse cluster, whose tiles then mix both — large bounding balls, late
+        # thresholds
+        gd = torch.Generator(device=ref.device)
+        gd.manual_seed(12345)
+        first, rand = kmeanspp_draws(sample.shape[0], C, gd, ref.device)
+        cent = sample[kmeanspp_ids(sample, C, first, rand).long()].clone()
+    else:
+        cent = sample[:C].clone()
     for _ in range(iters):
         code = nearest_centroid(sample, cent).long()
         sums = torch.zeros_like(cent).index_add_(0, code, sample)
@@ -320,9 +331,11 @@ def knn_fit(ref: torch.Tensor, locality: bool = True) -> KnnIndex:
 
 
 def knn_search(index: KnnIndex, Q: torch.Tensor, k: int, method: int = KNN_AUTO, want_unsafe: bool = True,
-               events: list | None = None):
+               events: list | None = None, prune: bool = False):
     """idx [N,k] int32 (ascending by (distance, index)), dist2 [N,k] f32, unsafe [N] uint8 | None.
-    `events`, if given, receives a (start, end) pair of CUDA events bracketing the scan + re-rank launches."""
+    `events`, if given, receives a (start, end) pair of CUDA events bracketing the scan + re-rank launches.
+    `prune` (tcgen05 scans only): skip reference tiles that provably hold no candidate of a whole query CTA — same
+    results, data-dependent speed; `index.scan_stats` then holds {tiles scanned, tiles of a full scan}."""
     lib = _lib.load()
     Q = _f32c(Q)
     N, d = Q.shape
@@ -332,11 +345,26 @@ def knn_search(index: KnnIndex, Q: torch.Tensor, k: int, method: int = KNN_AUTO,
     dist2 = torch.empty((N, k), device=dev, dtype=torch.float32)
     unsafe = torch.empty(N, device=dev, dtype=torch.uint8) if want_unsafe else None
     q_perm = q_code = cl_tile = None
-    if index.centroids is not None and N >= LOCALITY_MIN_QUERY and method != KNN_FFMA:
+    if index.centroids is not None and (N >= LOCALITY_MIN_QUERY or prune) and method != KNN_FFMA and N > 0:
         q_code = nearest_centroid(Q, index.centroids)
-        q_perm = batch_order(q_code, index.centroids.shape[0]).perm
+        bo = batch_order(q_code, index.centroids.shape[0])
+        q_perm = bo.perm
         cl_tile = index.cl_tile
-    ws_bytes = int(lib.sym_knn_workspace(N, index.M, d, k, method))
+        if prune and method in (KNN_TC, KNN_TC16):
+            # Pruning bounds a group of 32 consecutive scan rows (one selection warp) by a ball: a group that straddles
+            # two clusters of the sorted queries has a ball as wide as the gap between them and holds back its whole CTA.
+            # Every cluster's run of rows is therefore padded to a multiple of 32 by repeating its last row (a repeated
+            # row is mapped twice and written twice with the same result).
+            cnt = bo.seg[1:] - bo.seg[:-1]
+            pad_cnt = (cnt + 31) // 32 * 32
+            pad_off = torch.cumsum(pad_cnt, 0) - pad_cnt
+            n_scan = int(pad_cnt.sum().item())
+            pos = torch.arange(n_scan, device=dev, dtype=torch.int64)
+            cl = torch.searchsorted(pad_off + pad_cnt, pos, right=True)          # cluster of each padded position
+            within = torch.minimum(pos - pad_off[cl], (cnt[cl] - 1).clamp_min(0))
+            q_perm = q_perm[(bo.seg[:-1][cl] + within)].contiguous()
+    n_rows = N if q_perm is None else int(q_perm.numel())   # scan rows (more than N only with the padding above)
+    ws_bytes = int(lib.sym_knn_workspace(n_rows, index.M, d, k, method))
     key = "ws"
     ws = index.workspace.get(key)
     if ws is None or ws.numel() < ws_bytes or ws.device != dev:
@@ -345,17 +373,21 @@ def knn_search(index: KnnIndex, Q: torch.Tensor, k: int, method: int = KNN_AUTO,
     if events is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    _lib.check(lib.sym_knn(Q.data_ptr(), Q.stride(0), N, index.ref.data_ptr(), index.ref.stride(0), index.M,
-                           index.packed.data_ptr(), d, k, method, _ptr(q_perm), _ptr(q_code), _ptr(cl_tile),
+    flag = KNN_PRUNE_FLAG if (prune and method in (KNN_TC, KNN_TC16) and N > 0) else 0
+    _lib.check(lib.sym_knn(Q.data_ptr(), Q.stride(0), n_rows, index.ref.data_ptr(), index.ref.stride(0), index.M,
+                           index.packed.data_ptr(), d, k, method | flag, _ptr(q_perm), _ptr(q_code), _ptr(cl_tile),
                            idx.data_ptr(), dist2.data_ptr(), _ptr(unsafe), ws.data_ptr(), ws.numel(), _stream(dev)),
                "sym_knn")
     if events is not None:
         e1.record()
         events.append((e0, e1))
+    if flag:
+        index.scan_stats = ws[:16].view(torch.int64).clone()
     return idx, dist2, unsafe
 
 
-def knn_search_certified(index: KnnIndex, Q: torch.Tensor, k: int, method: int = KNN_AUTO, events: list | None = None):
+def knn_search_certified(index: KnnIndex, Q: torch.Tensor, k: int, method: int = KNN_AUTO, events: list | None = None,
+                         prune: bool = False):
     """`knn_search` plus the repair passes.  Rows whose over-selection margin could not be certified (possible
     with the reduced-precision tensor-core scans, or with many exactly tied neighbours) are re-run with the next
     more accurate scan: single-FP16 tcgen05 -> BF16x3 tcgen05 -> FP32 FFMA.
@@ -378,7 +410,7 @@ def knn_search_certified(index: KnnIndex, Q: torch.Tensor, k: int, method: int =
             first = KNN_TC16 if fp16_on and supported(KNN_TC16, N) else (KNN_TC if supported(KNN_TC, N) else KNN_FFMA)
     else:
         first = method
-    idx, dist2, unsafe = knn_search(index, Q, k, first, events=events)
+    idx, dist2, unsafe = knn_search(index, Q, k, first, events=events, prune=prune)
     n_first = n_bad = int(unsafe.sum().item())
     if n_bad and os.environ.get("SYM_KNN_NO_REPAIR") != "1":  # (the switch exists for kernel timing experiments only)
         rows = torch.nonzero(unsafe, as_tuple=False).flatten()

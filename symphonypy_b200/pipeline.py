@@ -38,10 +38,11 @@ def check_solve(info: torch.Tensor) -> None:
         raise np.linalg.LinAlgError("Singular matrix")  # what `np.linalg.inv` raises at `_utils.py:208`
 
 
-def knn_transfer(index: engine.KnnIndex, Q, k: int, ref_codes, method=engine.KNN_AUTO, mark=None, events=None):
+def knn_transfer(index: engine.KnnIndex, Q, k: int, ref_codes, method=engine.KNN_AUTO, mark=None, events=None,
+                 prune: bool = False):
     """Q [N,d] -> (label codes [N], vote fraction [N], idx [N,k], dist2 [N,k], repaired rows)."""
     mark = mark or (lambda name: None)
-    idx, dist2, n_rep = engine.knn_search_certified(index, Q, k, method, events=events)
+    idx, dist2, n_rep = engine.knn_search_certified(index, Q, k, method, events=events, prune=prune)
     mark("knn")
     lab, conf = engine.vote(idx, ref_codes)
     mark("vote")

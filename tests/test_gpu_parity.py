@@ -777,6 +777,29 @@ def test_kmeans_quality_matches_sklearn(cuda_device, M, d, K):
     assert inertia <= sk.inertia_ * 1.02
 
 
+@pytest.mark.parametrize("method", [engine.KNN_TC16, engine.KNN_TC])
+@pytest.mark.parametrize("N,M,d,k,sep", [(45000, 60000, 30, 10, 6.0), (40000, 70000, 50, 30, 3.0), (700, 40000, 20, 5, 0.0), (9000, 40000, 30, 10, 6.0)])
+def test_knn_tile_pruning_is_exact(cuda_device, method, N, M, d, k, sep):
+    """Opt-in tile pruning (bounding balls of the cluster-ordered reference tiles against the query CTA's ball and
+    thresholds) returns exactly what the full scan returns, certifies the same way, and actually skips tiles when the
+    embedding is clustered (sep > 0) — and none of that depends on the data being clustered (sep = 0)."""
+    rng = np.random.default_rng(N + M)
+    cent = rng.normal(0, 1.0, size=(16, d)) * sep
+    ref = (cent[rng.integers(0, 16, M)] + rng.normal(size=(M, d))).astype(np.float32)
+    qry = (cent[rng.integers(0, 16, N)] + rng.normal(size=(N, d))).astype(np.float32)
+    R, Q = torch.from_numpy(ref).to(cuda_device), torch.from_numpy(qry).to(cuda_device)
+    index = engine.knn_fit(R)
+    i0, d0, n0 = engine.knn_search_certified(index, Q, k, method)
+    i1, d1, n1 = engine.knn_search_certified(index, Q, k, method, prune=True)
+    assert torch.equal(i0, i1) and torch.equal(d0, d1)
+    scanned, full = (int(v) for v in index.scan_stats.cpu())
+    assert 0 < scanned <= full
+    if sep >= 3.0 and N >= 148 * 256:   # (a query that fills the GPU without splitting the reference across CTAs)
+        assert scanned < 0.6 * full, f"clustered data: {scanned} of {full} tiles scanned"
+    want, _ = so.knn_indices(ref.astype(np.float64), qry.astype(np.float64), k)
+    assert (i1.cpu().numpy() == want).mean() > 0.9999   # (float32 inputs: exact ties aside)
+
+
 @pytest.mark.parametrize("N,d,K", [(5000, 20, 30), (70000, 30, 100), (1500, 8, 200), (257, 3, 1)])
 def test_kmeanspp_kernel_matches_sklearn_restatement(cuda_device, N, d, K):
     """`sym_kmeanspp` (sampling, trial potentials, selection and D^2 update on the device) picks the rows that

@@ -175,7 +175,7 @@ def test_knn_tier_logic_with_a_fake_scan(monkeypatch):
     monkeypatch.setattr(engine._lib, "load", lambda: FakeLib())
     calls = []
 
-    def fake_search(index, Q, k, method=engine.KNN_AUTO, want_unsafe=True, events=None):
+    def fake_search(index, Q, k, method=engine.KNN_AUTO, want_unsafe=True, events=None, prune=False):
         n = Q.shape[0]
         calls.append((method, n))
         tag = Q[:, 0].long()                      # row identity travels in column 0
