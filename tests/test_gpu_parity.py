@@ -628,6 +628,36 @@ def test_host_streaming_in_many_chunks(cuda_device, kind, monkeypatch):
     assert np.abs(query.obsm["X_pca_harmony_symphony_R"] - qo.obsm["X_pca_harmony_symphony_R"]).max() < R_TOL
 
 
+@pytest.mark.parametrize("kind", ["csr", "dense"])
+def test_repeated_host_inputs_are_pinned_in_place(cuda_device, kind, monkeypatch):
+    """With `settings.pin_repeated_inputs` the second call that passes the same host array page-locks it where it lies
+    (cudaHostRegister) and copies straight from it; results do not change, `clear_caches()` releases the registration."""
+    import scipy.sparse as sp
+
+    quiet()
+    monkeypatch.setattr(tl, "_PIN_MIN_BYTES", 1024)
+    monkeypatch.setattr(tl, "_STAGE_CHUNK", 40_000)
+    monkeypatch.setattr(tl.settings, "pin_repeated_inputs", True)   # opt-in
+    tl.clear_caches()
+    query, ref = synth.small_case(N=900, M=500, G=160, d=20, K=12, L=4, levels=(3,), seed=37)
+    qo = copy.deepcopy(query)
+    X = np.ascontiguousarray(np.asarray(query.X), dtype=np.float32)
+    query.X = sp.csr_matrix(X) if kind == "csr" else X
+    watched = [query.X.data, query.X.indices] if kind == "csr" else [query.X]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        so.map_embedding(qo, ref, key="batch0")
+        pinned = []
+        for _ in range(3):
+            tl.map_embedding(query, ref, key="batch0")
+            pinned.append(all(torch.from_numpy(a).is_pinned() for a in watched))
+            assert row_rel_err(query.obsm["X_pca_harmony"], qo.obsm["X_pca_harmony"]) < EMB_TOL
+            assert np.abs(query.obsm["X_pca_harmony_symphony_R"] - qo.obsm["X_pca_harmony_symphony_R"]).max() < R_TOL
+    assert pinned == [False, True, True]
+    tl.clear_caches()
+    assert not any(torch.from_numpy(a).is_pinned() for a in watched)
+
+
 def test_many_batch_levels_and_large_k_clusters(cuda_device):
     """B = 140 levels (the largest ridge system the shared-memory solver takes at d = 20) and K = 300 clusters."""
     quiet()
