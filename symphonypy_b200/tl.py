@@ -111,7 +111,9 @@ def content_digest(*arrays) -> str:
             h = _hash_bytes(mv)
         else:
             if not _HASH_POOL:
-                _HASH_POOL.append(ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)))
+                # (one process per GPU on one host: the ranks share its cores)
+                ranks = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1) if _dist.active() else 1
+                _HASH_POOL.append(ThreadPoolExecutor(max_workers=max(1, min(8, (os.cpu_count() or 1) // max(1, ranks)))))
             parts = list(_HASH_POOL[0].map(lambda o: _hash_bytes(mv[o:o + _HASH_CHUNK]), range(0, n, _HASH_CHUNK)))
             h = _hash_bytes(np.asarray(parts, dtype=np.uint64).tobytes())
         out.append(f"{a.dtype.str}{a.shape}{h:x}")
