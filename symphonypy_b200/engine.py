@@ -330,6 +330,20 @@ def knn_fit(ref: torch.Tensor, locality: bool = True) -> KnnIndex:
     return KnnIndex(ref=ref, packed=packed, M=M, d=d, centroids=centroids, cl_tile=cl_tile)
 
 
+def pad_runs(perm: torch.Tensor, seg: torch.Tensor, multiple: int) -> torch.Tensor:
+    """`perm` lists row numbers grouped into runs (`seg[c] .. seg[c+1]` = run c, as `batch_order` returns them).
+    Returns the list with every non-empty run padded to a multiple of `multiple` entries by repeating its last row."""
+    cnt = seg[1:] - seg[:-1]
+    pad_cnt = (cnt + multiple - 1) // multiple * multiple
+    pad_end = torch.cumsum(pad_cnt, 0)
+    pad_off = pad_end - pad_cnt
+    n_out = int(pad_end[-1].item()) if pad_end.numel() else 0
+    pos = torch.arange(n_out, device=perm.device, dtype=torch.int64)
+    run = torch.searchsorted(pad_end, pos, right=True)              # run of each padded position
+    within = torch.minimum(pos - pad_off[run], (cnt[run] - 1).clamp_min(0))
+    return perm[seg[:-1][run] + within].contiguous()
+
+
 def knn_search(index: KnnIndex, Q: torch.Tensor, k: int, method: int = KNN_AUTO, want_unsafe: bool = True,
                events: list | None = None, prune: bool = False):
     """idx [N,k] int32 (ascending by (distance, index)), dist2 [N,k] f32, unsafe [N] uint8 | None.
@@ -355,14 +369,7 @@ def knn_search(index: KnnIndex, Q: torch.Tensor, k: int, method: int = KNN_AUTO,
             # two clusters of the sorted queries has a ball as wide as the gap between them and holds back its whole CTA.
             # Every cluster's run of rows is therefore padded to a multiple of 32 by repeating its last row (a repeated
             # row is mapped twice and written twice with the same result).
-            cnt = bo.seg[1:] - bo.seg[:-1]
-            pad_cnt = (cnt + 31) // 32 * 32
-            pad_off = torch.cumsum(pad_cnt, 0) - pad_cnt
-            n_scan = int(pad_cnt.sum().item())
-            pos = torch.arange(n_scan, device=dev, dtype=torch.int64)
-            cl = torch.searchsorted(pad_off + pad_cnt, pos, right=True)          # cluster of each padded position
-            within = torch.minimum(pos - pad_off[cl], (cnt[cl] - 1).clamp_min(0))
-            q_perm = q_perm[(bo.seg[:-1][cl] + within)].contiguous()
+            q_perm = pad_runs(q_perm, bo.seg, 32)
     n_rows = N if q_perm is None else int(q_perm.numel())   # scan rows (more than N only with the padding above)
     ws_bytes = int(lib.sym_knn_workspace(n_rows, index.M, d, k, method))
     key = "ws"

@@ -365,3 +365,27 @@ def test_encode_labels_equals_numpy_unique(kind):
     want_classes, want_inv = np.unique(np.asarray(col), return_inverse=True)   # sklearn: classes_ = np.unique(y)
     assert list(classes) == list(want_classes)
     np.testing.assert_array_equal(codes.numpy(), want_inv)
+
+
+def test_pad_runs_pads_every_run_by_repeating_its_last_row():
+    """Host logic of the kNN tile pruning: the sorted query rows are padded so that no group of 32 scan rows straddles
+    two clusters (`engine.pad_runs`)."""
+    import torch
+
+    from symphonypy_b200 import engine
+
+    perm = torch.tensor([7, 3, 9, 1, 4, 8, 0, 2, 5, 6], dtype=torch.int32)
+    seg = torch.tensor([0, 3, 3, 4, 10], dtype=torch.int64)          # runs of 3, 0, 1 and 6 rows
+    out = engine.pad_runs(perm, seg, 4).tolist()
+    assert out == [7, 3, 9, 9, 1, 1, 1, 1, 4, 8, 0, 2, 5, 6, 6, 6]
+    assert engine.pad_runs(perm, seg, 1).tolist() == perm.tolist()
+    # every original row appears, padding only repeats rows of the same run
+    rng = np.random.default_rng(0)
+    code = torch.from_numpy(rng.integers(0, 13, 1000))
+    order = torch.argsort(code, stable=True).to(torch.int32)
+    counts = torch.bincount(code, minlength=13)
+    seg = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(counts, 0)])
+    out = engine.pad_runs(order, seg, 32)
+    assert out.numel() % 32 == 0 and set(out.tolist()) == set(range(1000))
+    groups = code[out.long()].reshape(-1, 32)
+    assert bool((groups == groups[:, :1]).all())                    # no group of 32 mixes two runs
