@@ -107,6 +107,10 @@ struct VarOffsets {
     int off[MOE_MAX_VARS];
 };
 
+// Thread layout: 16 x 16 threads, 8 clusters x 4 columns each (128 clusters x 64 columns of [Z|1] per pass), or — NARROW,
+// for d + 1 <= 32, where the wide layout leaves half of the threads without a column — 32 x 8 threads, 4 clusters x 4
+// columns each (128 clusters x 32 columns).
+template <bool NARROW>
 __global__ void __launch_bounds__(ST_THREADS)
 moe_stats_kernel(const float *__restrict__ Z, int ldz, const float *__restrict__ R, int64_t N, int d, int K,
                  const int32_t *__restrict__ codes, int V, VarOffsets var_offset, int v, int n_levels,
@@ -128,7 +132,8 @@ moe_stats_kernel(const float *__restrict__ Z, int ldz, const float *__restrict__
     __syncthreads();
 
     const int col = 1 + var_offset.off[v] + ch.level;  // design column of this level
-    const int tk = tid / 16, tc = tid % 16;         // 16 x 16 threads -> 128 clusters x 64 columns
+    constexpr int TCN = NARROW ? 8 : 16, KT = NARROW ? 4 : 8, CW = NARROW ? 32 : 64;   // column threads, clusters per thread, columns per pass
+    const int tk = tid / TCN, tc = tid % TCN;
     const bool r16 = (K % 4) == 0 && (reinterpret_cast<uintptr_t>(R) & 15) == 0;          // 16-byte copies of R rows
     const bool z8 = (d % 2) == 0 && (ldz % 2) == 0 && (reinterpret_cast<uintptr_t>(Z) & 7) == 0;   // 8-byte copies of Z rows
     const int kv = KP / 4, zv = z8 ? d / 2 : d;
@@ -161,10 +166,10 @@ moe_stats_kernel(const float *__restrict__ Z, int ldz, const float *__restrict__
         cp_async_commit();
     };
     for (int k0 = 0; k0 < K; k0 += 128) {
-        for (int c0 = 0; c0 < d + 1; c0 += 64) {
-            float acc[8][4];
+        for (int c0 = 0; c0 < d + 1; c0 += CW) {
+            float acc[KT][4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < KT; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
             __syncthreads();   // everyone is done with both stages of the previous pass
@@ -179,16 +184,16 @@ moe_stats_kernel(const float *__restrict__ Z, int ldz, const float *__restrict__
                 }
                 __syncthreads();
                 const float *Rs = smem + stage * stage_floats, *Zs = Rs + ST_SUB * KP;
-                const int kb = k0 + tk * 8, cb = c0 + tc * 4;
+                const int kb = k0 + tk * KT, cb = c0 + tc * 4;
                 if (kb < KP && cb < DP) {
 #pragma unroll 4
                     for (int c = 0; c < ST_SUB; ++c) {
                         const float4 r0 = *reinterpret_cast<const float4 *>(Rs + c * KP + kb);
-                        const float4 r1 = *reinterpret_cast<const float4 *>(Rs + c * KP + kb + 4);
+                        const float4 r1 = NARROW ? r0 : *reinterpret_cast<const float4 *>(Rs + c * KP + kb + 4);
                         const float4 z = *reinterpret_cast<const float4 *>(Zs + c * DP + cb);
                         const float r[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
+                        for (int i = 0; i < KT; ++i) {
                             acc[i][0] = fmaf(r[i], z.x, acc[i][0]);
                             acc[i][1] = fmaf(r[i], z.y, acc[i][1]);
                             acc[i][2] = fmaf(r[i], z.z, acc[i][2]);
@@ -198,9 +203,9 @@ moe_stats_kernel(const float *__restrict__ Z, int ldz, const float *__restrict__
                 }
                 __syncthreads();   // before the stage just read is refilled (two fills from now)
             }
-            const int kb = k0 + tk * 8, cb = c0 + tc * 4;
+            const int kb = k0 + tk * KT, cb = c0 + tc * 4;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < KT; ++i) {
                 const int k = kb + i;
                 if (k >= K) continue;
 #pragma unroll
@@ -321,10 +326,12 @@ moe_solve_kernel(const double *__restrict__ gram, const double *__restrict__ cro
 
 // ------------------------------------------------------------------------------------------
 // apply: Zout[n,:] = Zin[n,:] - R[n,:] @ W[:, col, :]
-// Thread tile 4 cells x 4 outputs; 256 threads = 64 cells x 64 outputs per pass.
+// Thread tile 4 cells x 4 outputs; 256 threads = 64 cells x 64 outputs per pass, or — NARROW, for d <= 32, where the
+// wide layout leaves half of the threads without an output — 128 cells x 32 outputs.
 constexpr int AP_THREADS = 256;
 constexpr int AP_KS = 32;  // clusters staged per step
 
+template <bool NARROW>
 __global__ void __launch_bounds__(AP_THREADS)
 moe_apply_kernel(const float *__restrict__ Zin, int ldzin, const float *__restrict__ R, int64_t N, int d, int K,
                  int var_offset, int n_levels, const int32_t *__restrict__ perm, const int64_t *__restrict__ seg,
@@ -336,8 +343,9 @@ moe_apply_kernel(const float *__restrict__ Zin, int ldzin, const float *__restri
     const int DP = (d + 3) & ~3;
     const int KP = (K + 3) & ~3;
     float *Ws = smem;                 // [KP][DP]   W[:, col, :]
-    float *Rs0 = Ws + (size_t)KP * DP; // 2 stages of [64][AP_KS + 4], filled by cp.async
-    constexpr int RS = 64 * (AP_KS + 4);
+    constexpr int RP = NARROW ? 128 : 64, TCN = NARROW ? 8 : 16, TRN = AP_THREADS / TCN;   // rows per pass, column / row threads
+    float *Rs0 = Ws + (size_t)KP * DP; // 2 stages of [RP][AP_KS + 4], filled by cp.async
+    constexpr int RS = RP * (AP_KS + 4);
     int32_t *ids = reinterpret_cast<int32_t *>(Rs0 + 2 * RS);
     const int tid = threadIdx.x;
     const int col = 1 + var_offset + ch.level;
@@ -347,18 +355,18 @@ moe_apply_kernel(const float *__restrict__ Zin, int ldzin, const float *__restri
         Ws[i] = (k < K && j < d) ? W[((int64_t)k * B1 + col) * d + j] : 0.f;
     }
     __syncthreads();
-    const int tr = tid / 16, tc = tid % 16;  // rows tr + 16*i (i<4), outputs tc*4..+3
+    const int tr = tid / TCN, tc = tid % TCN;  // rows tr + TRN*i (i<4), outputs tc*4..+3
     const bool r16 = (K % 4) == 0 && (reinterpret_cast<uintptr_t>(R) & 15) == 0;
-    auto fill = [&](int stage, int r0, int k0) {   // R[rows r0..r0+63, clusters k0..k0+31] -> stage
+    auto fill = [&](int stage, int r0, int k0) {   // R[rows r0..r0+RP-1, clusters k0..k0+31] -> stage
         float *Rs = Rs0 + stage * RS;
         if (r16) {
-            for (int i = tid; i < 64 * (AP_KS / 4); i += AP_THREADS) {
+            for (int i = tid; i < RP * (AP_KS / 4); i += AP_THREADS) {
                 const int r = i / (AP_KS / 4), k = (i % (AP_KS / 4)) * 4;
                 const bool ok = r0 + r < ch.n && k0 + k < K;
                 cp_async16_zfill(Rs + r * (AP_KS + 4) + k, ok ? R + (int64_t)ids[r0 + r] * K + k0 + k : R, ok);
             }
         } else {
-            for (int i = tid; i < 64 * AP_KS; i += AP_THREADS) {
+            for (int i = tid; i < RP * AP_KS; i += AP_THREADS) {
                 const int r = i / AP_KS, k = i % AP_KS;
                 const bool ok = r0 + r < ch.n && k0 + k < K;
                 cp_async4_zfill(Rs + r * (AP_KS + 4) + k, ok ? R + (int64_t)ids[r0 + r] * K + k0 + k : R, ok);
@@ -366,8 +374,8 @@ moe_apply_kernel(const float *__restrict__ Zin, int ldzin, const float *__restri
         }
         cp_async_commit();
     };
-    for (int r0 = 0; r0 < ch.n; r0 += 64) {
-        for (int c0 = 0; c0 < d; c0 += 64) {
+    for (int r0 = 0; r0 < ch.n; r0 += RP) {
+        for (int c0 = 0; c0 < d; c0 += TCN * 4) {
             float acc[4][4];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -393,7 +401,7 @@ moe_apply_kernel(const float *__restrict__ Zin, int ldzin, const float *__restri
                         const float4 w = *reinterpret_cast<const float4 *>(Ws + (k0 + k) * DP + cb);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            const float r = Rs[(tr + 16 * i) * (AP_KS + 4) + k];
+                            const float r = Rs[(tr + TRN * i) * (AP_KS + 4) + k];
                             acc[i][0] = fmaf(r, w.x, acc[i][0]);
                             acc[i][1] = fmaf(r, w.y, acc[i][1]);
                             acc[i][2] = fmaf(r, w.z, acc[i][2]);
@@ -405,7 +413,7 @@ moe_apply_kernel(const float *__restrict__ Zin, int ldzin, const float *__restri
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int r = r0 + tr + 16 * i;
+                const int r = r0 + tr + TRN * i;
                 if (r >= ch.n) continue;
                 const int64_t n = ids[r];
 #pragma unroll
@@ -459,13 +467,19 @@ extern "C" int sym_moe_stats(const float *Z, int32_t ldz, const float *R, int64_
     const int KP = (K + 7) & ~7, DP = ((d + 1) + 3) & ~3;
     const size_t smem = 2 * (size_t)(ST_SUB * KP + ST_SUB * DP) * sizeof(float) + MOE_CH * sizeof(int32_t);
     SYM_REQUIRE(smem <= 200 * 1024, SYM_ERR_UNSUPPORTED_SHAPE, "sym_moe_stats: K=%d too large", K);
-    SYM_CUDA(cudaFuncSetAttribute(moe_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool narrow = d + 1 <= 32;
+    SYM_CUDA(cudaFuncSetAttribute(narrow ? moe_stats_kernel<true> : moe_stats_kernel<false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SYM_REQUIRE(V <= MOE_MAX_VARS, SYM_ERR_UNSUPPORTED_SHAPE, "sym_moe_stats: more than %d batch variables", MOE_MAX_VARS);
     VarOffsets vo;
     for (int i = 0; i < MOE_MAX_VARS; ++i) vo.off[i] = i < V ? var_offset[i] : 0;
     const int64_t grid = ceil_div(N, MOE_CH) + (perm ? n_levels_v : 0);
-    moe_stats_kernel<<<(unsigned)grid, ST_THREADS, smem, (cudaStream_t)stream>>>(
-        Z, ldz, R, N, d, K, codes, V, vo, v, n_levels_v, perm, seg, chunk_start, B1, gram, cross);
+    if (narrow)
+        moe_stats_kernel<true><<<(unsigned)grid, ST_THREADS, smem, (cudaStream_t)stream>>>(
+            Z, ldz, R, N, d, K, codes, V, vo, v, n_levels_v, perm, seg, chunk_start, B1, gram, cross);
+    else
+        moe_stats_kernel<false><<<(unsigned)grid, ST_THREADS, smem, (cudaStream_t)stream>>>(
+            Z, ldz, R, N, d, K, codes, V, vo, v, n_levels_v, perm, seg, chunk_start, B1, gram, cross);
     SYM_LAUNCH_CHECK("moe_stats_kernel");
     return SYM_OK;
 }
@@ -500,12 +514,18 @@ extern "C" int sym_moe_apply(const float *Zin, int32_t ldzin, const float *R, in
                 "sym_moe_apply: a variable with several levels needs sym_batch_order output");
     if (N == 0) return SYM_OK;
     const int DP = (d + 3) & ~3, KP = (K + 3) & ~3;
-    const size_t smem = ((size_t)KP * DP + 2 * 64 * (AP_KS + 4)) * sizeof(float) + MOE_CH * sizeof(int32_t);
+    const bool narrow = d <= 32;
+    const size_t smem = ((size_t)KP * DP + 2 * (narrow ? 128 : 64) * (AP_KS + 4)) * sizeof(float) + MOE_CH * sizeof(int32_t);
     SYM_REQUIRE(smem <= 200 * 1024, SYM_ERR_UNSUPPORTED_SHAPE, "sym_moe_apply: K=%d d=%d too large", K, d);
-    SYM_CUDA(cudaFuncSetAttribute(moe_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SYM_CUDA(cudaFuncSetAttribute(narrow ? moe_apply_kernel<true> : moe_apply_kernel<false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t grid = ceil_div(N, MOE_CH) + (perm ? n_levels_v : 0);
-    moe_apply_kernel<<<(unsigned)grid, AP_THREADS, smem, (cudaStream_t)stream>>>(
-        Zin, ldzin, R, N, d, K, var_offset, n_levels_v, perm, seg, chunk_start, W, B1, Zout, ldzout);
+    if (narrow)
+        moe_apply_kernel<true><<<(unsigned)grid, AP_THREADS, smem, (cudaStream_t)stream>>>(
+            Zin, ldzin, R, N, d, K, var_offset, n_levels_v, perm, seg, chunk_start, W, B1, Zout, ldzout);
+    else
+        moe_apply_kernel<false><<<(unsigned)grid, AP_THREADS, smem, (cudaStream_t)stream>>>(
+            Zin, ldzin, R, N, d, K, var_offset, n_levels_v, perm, seg, chunk_start, W, B1, Zout, ldzout);
     SYM_LAUNCH_CHECK("moe_apply_kernel");
     return SYM_OK;
 }
