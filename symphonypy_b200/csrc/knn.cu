@@ -494,7 +494,11 @@ knn_rerank_groups_kernel(const float *__restrict__ Q, int ldq, int64_t N, const 
         const int64_t pos = (int64_t)(uint32_t)(key & 0xffffffffull) + (e & 7);
         const bool valid = gvalid && pos < M;
         float sc = INFINITY;
-        if (gvalid) {   // (padding positions of the last tile hold +inf norms: their score is +inf)
+        // A group whose recorded minimum is already above the bar cannot hold a survivor (members score >= the group's
+        // minimum): its tiles are not even read.  With one split every candidate group is below its split's threshold;
+        // with many (few query rows, e.g. the repair passes: up to 28 splits x kc groups per row) almost all are skipped.
+        const bool wanted = gvalid && knn_key_score(key) <= keep_below;
+        if (wanted) {   // (padding positions of the last tile hold +inf norms: their score is +inf)
             const unsigned char *t = rtiles + (size_t)(pos >> 7) * tile_bytes + ((pos & 127) >> 3) * 128 + (pos & 7) * 16;
             float a0 = 0.f, a1 = 0.f;
 #pragma unroll 4
@@ -524,7 +528,7 @@ knn_rerank_groups_kernel(const float *__restrict__ Q, int ldq, int64_t N, const 
         float gmin = sc;
 #pragma unroll
         for (int o = 1; o < 8; o <<= 1) gmin = fminf(gmin, __shfl_xor_sync(0xffffffffu, gmin, o));
-        if (gvalid && (e & 7) == 0) {
+        if (wanted && (e & 7) == 0) {
             const float rec = knn_key_score(key);
             bad |= !(fabs((double)rec - (double)gmin) * unscale <= eps);
         }
