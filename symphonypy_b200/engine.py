@@ -394,7 +394,7 @@ def knn_search(index: KnnIndex, Q: torch.Tensor, k: int, method: int = KNN_AUTO,
 
 
 def knn_search_certified(index: KnnIndex, Q: torch.Tensor, k: int, method: int = KNN_AUTO, events: list | None = None,
-                         prune: bool = False):
+                         prune: bool = False, after_launch=None):
     """`knn_search` plus the repair passes.  Rows whose over-selection margin could not be certified (possible
     with the reduced-precision tensor-core scans, or with many exactly tied neighbours) are re-run with the next
     more accurate scan: single-FP16 tcgen05 -> BF16x3 tcgen05 -> FP32 FFMA.
@@ -418,6 +418,8 @@ def knn_search_certified(index: KnnIndex, Q: torch.Tensor, k: int, method: int =
     else:
         first = method
     idx, dist2, unsafe = knn_search(index, Q, k, first, events=events, prune=prune)
+    if after_launch is not None:
+        after_launch()   # host work of the caller that can run while the first-tier scan is on the GPU
     n_first = n_bad = int(unsafe.sum().item())
     if n_bad and os.environ.get("SYM_KNN_NO_REPAIR") != "1":  # (the switch exists for kernel timing experiments only)
         rows = torch.nonzero(unsafe, as_tuple=False).flatten()
