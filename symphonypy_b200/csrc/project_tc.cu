@@ -423,8 +423,11 @@ project_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t N, int G, c
         int s = 0, t = 0;
         uint32_t ph_raw = 0, ph_op = 0;
         for (int c = 0; c < nchunks; ++c) {
-            const float m[8] = {ms[0].x, ms[0].y, ms[0].z, ms[0].w, ms[1].x, ms[1].y, ms[1].z, ms[1].w};
+            // t = clip(x * inv_sd - mu * inv_sd): one FMA per value.  Genes with inv_sd == 0 (zero std; absent genes cannot
+            // occur on this path, the genes are in reference order) give x * 0 - 0 = 0 exactly for every finite x.
             const float is[8] = {ms[2].x, ms[2].y, ms[2].z, ms[2].w, ms[3].x, ms[3].y, ms[3].z, ms[3].w};
+            const float m[8] = {-ms[0].x * is[0], -ms[0].y * is[1], -ms[0].z * is[2], -ms[0].w * is[3],
+                                -ms[1].x * is[4], -ms[1].y * is[5], -ms[1].z * is[6], -ms[1].w * is[7]};
             if (c + 1 < nchunks) load_ms(c + 1);
             mbar_wait(&raw_full[s], ph_raw);
             const unsigned char *raw = raw_s + (size_t)s * PT_RAW_TILE;
@@ -446,8 +449,7 @@ project_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t N, int G, c
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int q = 2 * e + h;
-                        // genes with inv_sd == 0 (absent from the query or zero std) contribute exactly 0
-                        tt[h] = is[q] != 0.f ? fminf(fmaxf((x[q] - m[q]) * is[q], -clip), clip) : 0.f;
+                        tt[h] = fminf(fmaxf(fmaf(x[q], is[q], m[q]), -clip), clip);
                     }
                     pt_split(tt[0], tt[1], hi[j][e], lo[j][e]);
                 }
