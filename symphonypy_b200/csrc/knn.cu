@@ -297,7 +297,11 @@ constexpr int RR_THREADS = 256;
 constexpr int RR_MAXC = 512;   // candidates per row the scan may hand over, and members per row that can be ranked
 constexpr int RR_DMAX = 128;
 constexpr size_t RR_SMEM = (size_t)(RR_THREADS / 32) * (RR_MAXC * (sizeof(double) + sizeof(int32_t)) + RR_DMAX * sizeof(float));
-constexpr size_t RR_SMEM_GROUPS = RR_SMEM + (size_t)(RR_THREADS / 32) * 512;   // + the packed operand row of each warp's query
+// groups kernel: 256 survivors per row are plenty (~kc survive pass A; a row with more — hundreds of references tied at
+// its threshold — is flagged and goes to the next tier, whose last one ranks up to RR_MAXC single references); the
+// smaller lists let 5 instead of 4 blocks share an SM, which is what this latency-bound kernel needs
+constexpr int RG_MAXC = 256;
+constexpr size_t RR_SMEM_GROUPS = (size_t)(RR_THREADS / 32) * (RG_MAXC * (sizeof(double) + sizeof(int32_t)) + RR_DMAX * sizeof(float) + 256 * sizeof(float));
 
 __global__ void __launch_bounds__(RR_THREADS)
 knn_rerank_kernel(const float *__restrict__ Q, int ldq, int64_t N, const float *__restrict__ Ref, int ldr,
@@ -445,19 +449,31 @@ knn_rerank_groups_kernel(const float *__restrict__ Q, int ldq, int64_t N, const 
     extern __shared__ __align__(16) unsigned char rr_smem[];
     constexpr int W = RR_THREADS / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // per warp: survivors (double distance | int32 id, RR_MAXC each), the float32 query row, its packed operand row
-    double *wd = reinterpret_cast<double *>(rr_smem) + (size_t)warp * RR_MAXC;
-    int32_t *wi = reinterpret_cast<int32_t *>(rr_smem + (size_t)W * RR_MAXC * sizeof(double)) + (size_t)warp * RR_MAXC;
-    float *wq = reinterpret_cast<float *>(rr_smem + (size_t)W * RR_MAXC * (sizeof(double) + sizeof(int32_t))) + (size_t)warp * RR_DMAX;
-    uint4 *wo = reinterpret_cast<uint4 *>(rr_smem + (size_t)W * (RR_MAXC * (sizeof(double) + sizeof(int32_t)) + RR_DMAX * sizeof(float))) +
-                (size_t)warp * (256 / 8);   // kp <= 256 operand values = 32 uint4
+    // per warp: survivors (double distance | int32 id, RG_MAXC each), the float32 query row, its packed operand row
+    double *wd = reinterpret_cast<double *>(rr_smem) + (size_t)warp * RG_MAXC;
+    int32_t *wi = reinterpret_cast<int32_t *>(rr_smem + (size_t)W * RG_MAXC * sizeof(double)) + (size_t)warp * RG_MAXC;
+    float *wq = reinterpret_cast<float *>(rr_smem + (size_t)W * RG_MAXC * (sizeof(double) + sizeof(int32_t))) + (size_t)warp * RR_DMAX;
+    // the query's packed operand row, converted to float once per row (kp <= 256 values): pass A then spends its
+    // conversions on the reference side only
+    float *wo = reinterpret_cast<float *>(rr_smem + (size_t)W * (RG_MAXC * (sizeof(double) + sizeof(int32_t)) + RR_DMAX * sizeof(float))) +
+                (size_t)warp * 256;
     const int64_t row = (int64_t)blockIdx.x * W + warp;   // row of the scan (locality order)
     if (row >= N) return;
     const int64_t n = q_perm ? q_perm[row] : row;         // the query it stands for
     const float *q = Q + n * ldq;
     for (int c = lane; c < d; c += 32) wq[c] = q[c];
     const int nunits = kp / 8;
-    for (int j = lane; j < nunits; j += 32) wo[j] = __ldg(reinterpret_cast<const uint4 *>(qrows + (size_t)row * kp * 2) + j);
+    for (int j = lane; j < kp / 2; j += 32) {   // two operand values per 32-bit word
+        const uint32_t w2 = __ldg(reinterpret_cast<const uint32_t *>(qrows + (size_t)row * kp * 2) + j);
+        if (PREC == 1) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&w2));
+            wo[2 * j] = f.x;
+            wo[2 * j + 1] = f.y;
+        } else {
+            wo[2 * j] = __uint_as_float(w2 << 16);
+            wo[2 * j + 1] = __uint_as_float(w2 & 0xffff0000u);
+        }
+    }
     __syncwarp();
     double qn = 0.0;
     for (int c = 0; c < d; ++c) {
@@ -504,21 +520,20 @@ knn_rerank_groups_kernel(const float *__restrict__ Q, int ldq, int64_t N, const 
 #pragma unroll 4
             for (int j = 0; j < nunits; ++j) {
                 const uint4 rv = __ldg(reinterpret_cast<const uint4 *>(t + (size_t)j * 2048));
-                const uint4 qv = wo[j];
-                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w}, qw[4] = {qv.x, qv.y, qv.z, qv.w};
+                const float4 qa = *reinterpret_cast<const float4 *>(wo + 8 * j), qb = *reinterpret_cast<const float4 *>(wo + 8 * j + 4);
+                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+                const float qf[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    float r0, r1, q0, q1;
+                    float r0, r1;
                     if (PREC == 1) {
                         const float2 rf = __half22float2(*reinterpret_cast<const __half2 *>(&rw[u]));
-                        const float2 qf = __half22float2(*reinterpret_cast<const __half2 *>(&qw[u]));
-                        r0 = rf.x; r1 = rf.y; q0 = qf.x; q1 = qf.y;
+                        r0 = rf.x; r1 = rf.y;
                     } else {
                         r0 = __uint_as_float(rw[u] << 16); r1 = __uint_as_float(rw[u] & 0xffff0000u);
-                        q0 = __uint_as_float(qw[u] << 16); q1 = __uint_as_float(qw[u] & 0xffff0000u);
                     }
-                    a0 = fmaf(q0, r0, a0);
-                    a1 = fmaf(q1, r1, a1);
+                    a0 = fmaf(qf[2 * u], r0, a0);
+                    a1 = fmaf(qf[2 * u + 1], r1, a1);
                 }
             }
             sc = a0 + a1;
@@ -535,15 +550,15 @@ knn_rerank_groups_kernel(const float *__restrict__ Q, int ldq, int64_t N, const 
         const bool keep = valid && sc <= keep_below;
         const unsigned m = __ballot_sync(0xffffffffu, keep);
         const int off = nsurv + __popc(m & ((1u << lane) - 1u));
-        if (keep && off < RR_MAXC) {
+        if (keep && off < RG_MAXC) {
             ws[2 * off] = sc;
             wi[off] = (int32_t)pos;
         }
         nsurv += __popc(m);
     }
     bad = __any_sync(0xffffffffu, bad);
-    if (nsurv > RR_MAXC) {   // cannot rank them all: rank what fits, flag the row
-        nsurv = RR_MAXC;
+    if (nsurv > RG_MAXC) {   // cannot rank them all: rank what fits, flag the row
+        nsurv = RG_MAXC;
         bad = 1;
     }
     __syncwarp();
