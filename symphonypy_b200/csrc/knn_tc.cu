@@ -20,12 +20,17 @@
 //
 // Warp roles (384 threads for two query tiles):  warp 0 = bulk-copy producer; warps 1-2 = MMA issuers, one per
 // query tile (warp 1 owns the TMEM allocation); warps 4-11 = selection, thread <-> query row <-> TMEM lane.  A
-// selection thread pulls the 128 scores of its row with four tcgen05.ld, hands the accumulator back, folds the
-// scores with 3-input min against its row's kc-th best (one straight-line block), and only on a hit locates the
-// candidate groups and appends them to the row's buffer in shared memory (compacted to the kc best when full).
-// The scan over-selects (kc = k + 8); the float64 re-rank in knn.cu certifies the margin with the scores recorded
-// here (error bound per row: measured FP16 rounding residuals, or 6e-5 relative for BF16x3) and flags the rows
-// that have to be re-run with the next tier.
+// selection thread pulls the 128 scores of its row with four tcgen05.ld, hands the accumulator back and folds the
+// scores with 3-input min into the minima of 16 GROUPS of 8 references, compared with its row's threshold in one
+// straight-line block.  What is selected are groups (minimum score, first position).  On a hit the thread only PARKS
+// the tile (its 16 group minima + first position, five stores) in its row's small FIFO; at the same tiles for every
+// warp of the CTA each row then moves one parked tile into its 4-ary max-heap of the kc best groups in shared
+// memory (root = threshold), lanes in lock-step — so the four warps that share an accumulator are slow together
+// instead of one after the other.
+// The scan over-selects (kc = k + 8 groups, k + 16 for k >= 40); the re-rank in knn.cu expands the groups, certifies
+// the margin with the scores recorded here (error bound per row: measured FP16 rounding residuals, or 6e-5 relative
+// for BF16x3) and flags the rows that have to be re-run with the next tier.  Opt-in: exact tile pruning (bounding
+// balls of the reference tiles against the rows' published thresholds; tile numbers through a ring in shared memory).
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
