@@ -242,8 +242,8 @@ __device__ unsigned long long tc_prof[16];
 // per query tile; otherwise 2-3, rotated through both query tiles in global issue order.
 //
 // Selection per tile: four tcgen05.ld (128 scores per row), the accumulator handed back, 16 independent
-// 3-input-min chains over groups of 8, one compare against the row's kc-th best; only on a hit are the groups
-// located and appended to the row's candidate buffer.
+// 3-input-min chains over groups of 8, one compare against the row's threshold; on a hit the tile is parked (see
+// below) and drained into the row's heap later.
 
 __device__ __forceinline__ float tc_min8(const uint32_t *v) {
     float m = fmin3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
