@@ -339,6 +339,18 @@ def _project_host_dense(Xh: torch.Tensor, ld: engine.Loadings, gene_col, Z: torc
         free[b].record(compute)
 
 
+def csr_row_chunks(indptr: np.ndarray, per_chunk: int) -> list:
+    """Row boundaries [0, r1, r2, ..., N] of a CSR matrix such that every chunk of rows holds about `per_chunk`
+    non-zeros (never more, unless a single row does) and at least one row."""
+    N = len(indptr) - 1
+    bounds = [0]
+    while bounds[-1] < N:
+        target = indptr[bounds[-1]] + per_chunk
+        nxt = int(np.searchsorted(indptr, target, side="right")) - 1
+        bounds.append(min(N, max(nxt, bounds[-1] + 1)))
+    return bounds
+
+
 def _project_host_csr(Xc, col_gene: np.ndarray, ld: engine.Loadings, Z: torch.Tensor, after_chunk=None):
     """Stream a scipy CSR matrix through the GPU in row chunks (its `data` / `indices` slices are contiguous): the
     values and column indices of chunk i+1 are staged and sent while chunk i is projected; `after_chunk(Z, s, e)`
@@ -359,11 +371,7 @@ def _project_host_csr(Xc, col_gene: np.ndarray, ld: engine.Loadings, Z: torch.Te
         return flag
     stager = _Stager(dev)
     per_chunk = max(1, _STAGE_CHUNK // 8)                          # non-zeros per chunk (4 B value + 4 B index)
-    bounds = [0]
-    while bounds[-1] < N:                                          # row boundaries: ~per_chunk non-zeros each
-        target = indptr_h[bounds[-1]] + per_chunk
-        nxt = int(np.searchsorted(indptr_h, target, side="right")) - 1
-        bounds.append(min(N, max(nxt, bounds[-1] + 1)))
+    bounds = csr_row_chunks(indptr_h, per_chunk)
     d_h, i_h = Xc.data, Xc.indices
     # values / indices that are page-locked (by the caller, or in place on their second visit) and already 32-bit
     # skip the staging copy

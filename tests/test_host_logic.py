@@ -389,3 +389,20 @@ def test_pad_runs_pads_every_run_by_repeating_its_last_row():
     assert out.numel() % 32 == 0 and set(out.tolist()) == set(range(1000))
     groups = code[out.long()].reshape(-1, 32)
     assert bool((groups == groups[:, :1]).all())                    # no group of 32 mixes two runs
+
+
+def test_csr_row_chunks_cover_all_rows_within_the_byte_budget():
+    """Host logic of the CSR streaming (`tl.csr_row_chunks`): consecutive row ranges that cover every row once, hold at
+    most the budgeted number of non-zeros unless a single row exceeds it, and never an empty range."""
+    from symphonypy_b200 import tl
+
+    rng = np.random.default_rng(3)
+    for nnz_per_row, budget in (((rng.poisson(20, 500)), 300), (np.array([0, 0, 5, 1000, 0, 3, 0]), 10), (np.zeros(7, int), 4),
+                                (np.array([9]), 100), (np.array([], dtype=int), 5)):
+        indptr = np.concatenate([[0], np.cumsum(nnz_per_row)]).astype(np.int64)
+        b = tl.csr_row_chunks(indptr, budget)
+        N = len(nnz_per_row)
+        assert b[0] == 0 and b[-1] == N and all(x < y for x, y in zip(b[:-1], b[1:])) or N == 0 and b == [0]
+        for s0, e0 in zip(b[:-1], b[1:]):
+            n = indptr[e0] - indptr[s0]
+            assert n <= budget or e0 - s0 == 1
