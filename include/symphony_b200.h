@@ -41,6 +41,12 @@ int sym_version(void);
 const char *sym_last_error(void);
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
 int64_t sym_launch_count(void);
+/* 64-bit digest of `nbytes` of HOST memory, computed on up to `threads` host threads (the value does not depend on
+ * `threads`).  Synchronous, no GPU work.  The host layer keys its device-side caches of reference objects (loadings,
+ * packed kNN index) by the content of the arrays they were built from — the reference rebuilds them on every call
+ * (symphonypy/tl.py:425-426 fits the classifier each time) — and re-hashes the arrays on every call: a foreign-function
+ * call releases the interpreter lock, so the hashing overlaps the caller's other host work.  Not cryptographic. */
+uint64_t sym_host_digest64(const void *data, uint64_t nbytes, int32_t threads);
 /* Compute capability (major*10+minor) the kernels were compiled for: 100. */
 int sym_compiled_arch(void);
 

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int32, c_int64, c_size_t, c_void_p
+from ctypes import c_char_p, c_float, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # SYM_B200_LIB: experiments only (an instrumented / tuning build made by `python -m symphonypy_b200.build --variant`)
@@ -20,6 +20,7 @@ SIGNATURES = {
     "sym_last_error": (c_char_p, []),
     "sym_launch_count": (c_int64, []),
     "sym_compiled_arch": (c_int32, []),
+    "sym_host_digest64": (c_uint64, [_P, c_uint64, c_int32]),
     "sym_project_dense": (c_int32, [_P, c_int64, c_int64, _P, c_int32, _P, _P, _P, c_int32, c_int32, c_float, _P,
                                     c_int32, _P]),
     "sym_project_pack_bytes": (c_size_t, [c_int32, c_int32]),

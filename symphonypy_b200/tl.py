@@ -25,7 +25,6 @@ import numbers
 import os
 import warnings
 import weakref
-import zlib
 from collections import OrderedDict
 from concurrent.futures import ThreadPoolExecutor
 
@@ -34,7 +33,7 @@ import pandas as pd
 import torch
 from scipy.sparse import issparse
 
-from . import _design, _dist, engine, pipeline
+from . import _design, _dist, _lib, engine, pipeline
 
 logger = logging.getLogger("symphonypy")
 
@@ -78,23 +77,19 @@ _REF_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
 # the index searched speculatively while the digest of the array is recomputed (see transfer_labels_kNN)
 _KNN_SPEC: "OrderedDict[tuple, tuple]" = OrderedDict()
 
-try:
-    import xxhash as _xxhash
-except ImportError:  # pragma: no cover - the image has it; zlib is the stand-in
-    _xxhash = None
-_HASH_CHUNK = 16 << 20
-_HASH_POOL: list = []
 _DIGEST_POOL: list = []
 
 
-def _hash_bytes(mv) -> int:
-    if _xxhash is not None:
-        return _xxhash.xxh3_64_intdigest(mv)
-    return (zlib.crc32(mv) << 32) | zlib.adler32(mv)
+def _hash_threads() -> int:
+    """Host threads one digest may use (one process per GPU on one host: the ranks share its cores)."""
+    ranks = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1) if _dist.active() else 1
+    return max(1, min(8, (os.cpu_count() or 1) // max(1, ranks)))
 
 
 def content_digest(*arrays) -> str:
-    """64-bit digests of the full contents (plus dtype and shape) of host arrays, as one string."""
+    """64-bit digests of the full contents (plus dtype and shape) of host arrays, as one string.  The bytes are
+    hashed by `sym_host_digest64` of the C-ABI library on a few threads: the call releases the interpreter lock, so a
+    digest computed on a worker thread does not hold up the thread that is launching GPU work."""
     out = []
     for a in arrays:
         if a is None:
@@ -108,17 +103,7 @@ def content_digest(*arrays) -> str:
             a = np.asarray(pd.util.hash_pandas_object(pd.Series(a), index=False))
         if not a.flags.c_contiguous:
             a = np.ascontiguousarray(a)
-        mv = memoryview(a).cast("B") if a.size else memoryview(b"")
-        n = len(mv)
-        if n <= _HASH_CHUNK:
-            h = _hash_bytes(mv)
-        else:
-            if not _HASH_POOL:
-                # (one process per GPU on one host: the ranks share its cores)
-                ranks = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1) if _dist.active() else 1
-                _HASH_POOL.append(ThreadPoolExecutor(max_workers=max(1, min(8, (os.cpu_count() or 1) // max(1, ranks)))))
-            parts = list(_HASH_POOL[0].map(lambda o: _hash_bytes(mv[o:o + _HASH_CHUNK]), range(0, n, _HASH_CHUNK)))
-            h = _hash_bytes(np.asarray(parts, dtype=np.uint64).tobytes())
+        h = int(_lib.load().sym_host_digest64(a.ctypes.data if a.size else None, a.nbytes, _hash_threads()))
         out.append(f"{a.dtype.str}{a.shape}{h:x}")
     return "|".join(out)
 
@@ -141,11 +126,12 @@ def _device_copy(arr, dev) -> torch.Tensor:
         if hit is not None and hit[0]() is arr and hit[1].device == dev:
             return hit[1]
     a = np.ascontiguousarray(np.asarray(arr))
-    if not a.flags.writeable:
-        with warnings.catch_warnings():
-            warnings.simplefilter("ignore")
-            return torch.from_numpy(a).to(dev).float()
-    return torch.from_numpy(a).to(dev).float()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")   # (read-only arrays: torch warns that it could write through the view)
+        t = torch.from_numpy(a)
+    # a page-locked source (the result buffers `map_embedding` hands out are) is copied asynchronously: the array stays
+    # referenced by the caller's AnnData, and everything that reads the copy is ordered behind it on the stream
+    return t.to(dev, non_blocking=t.is_pinned()).float()
 
 
 def _cached(key, build):
@@ -687,6 +673,8 @@ def _map_embedding_once(adata_query, adata_ref, key, lamb, sigma, use_genes_colu
         assert Yd.shape == (Kc, d), "harmony C must be [K, n_components]"
 
         # 3. mixture-of-experts correction
+        # (these small synchronous uploads wait for the last chunk's projection, which step 3 needs anyway; issuing
+        # them before the query streams in was measured 1 ms slower: they then delay the first chunk instead)
         codes_h, levels = _design.batch_codes(adata_query, key)
         n_levels = [len(lv) for lv in levels]
         lam = _design.ridge_diagonal(lamb, n_levels)
@@ -897,6 +885,10 @@ def _encode_labels(col: pd.Series, dev):
     return classes, torch.from_numpy(np.ascontiguousarray(inv, dtype=np.int32)).to(dev)
 
 
+_DECODE_CHUNK = 1 << 18
+_DECODE_POOL: list = []
+
+
 def _decode_labels(classes: np.ndarray, lab: np.ndarray, index: pd.Index):
     """`classes[lab]` as the column pandas builds from sklearn's object array of predictions.  When pandas infers
     its Arrow-backed `str` dtype for such an array (pandas >= 3), the same column is produced by an Arrow
@@ -906,8 +898,17 @@ def _decode_labels(classes: np.ndarray, lab: np.ndarray, index: pd.Index):
         dt = pd.Series(classes).dtype
         if isinstance(dt, pd.StringDtype) and getattr(dt, "storage", None) == "pyarrow":
             import pyarrow as pa
-            arr = pa.DictionaryArray.from_arrays(pa.array(np.ascontiguousarray(lab, dtype=np.int32)),
-                                                 pa.array(list(classes), type=pa.large_string())).dictionary_decode()
+            import pyarrow.compute as pc
+            names = pa.array(list(classes), type=pa.large_string())
+            codes = np.ascontiguousarray(lab, dtype=np.int32)
+            if codes.shape[0] < 2 * _DECODE_CHUNK:
+                arr = pc.take(names, pa.array(codes))
+            else:   # Arrow releases the interpreter lock: the gather of a few hundred thousand strings per thread
+                if not _DECODE_POOL:
+                    _DECODE_POOL.append(ThreadPoolExecutor(max_workers=4))
+                parts = _DECODE_POOL[0].map(lambda o: pc.take(names, pa.array(codes[o:o + _DECODE_CHUNK])),
+                                            range(0, codes.shape[0], _DECODE_CHUNK))
+                arr = pa.chunked_array(list(parts), type=pa.large_string())
             return pd.Series(pd.array(arr, dtype=dt), index=index)
     return classes[lab]
 
@@ -950,9 +951,9 @@ def transfer_labels_kNN(
     with torch.cuda.device(dev):
         # the packed index is found again by the CONTENT of the reference embedding (a replaced or edited obsm array
         # gets a new index)
-        # (the digest of the reference embedding — 13 ms for 120 MB — runs on a worker thread, the hash releases the
-        # GIL, while this thread uploads the query and encodes the label columns)
-        if not _DIGEST_POOL:   # (its own thread: content_digest fans out over _HASH_POOL and waits for it)
+        # (the digest of the reference embedding runs on a worker thread — a foreign call, no interpreter lock held —
+        # while this thread uploads the query, launches the scan and encodes the label columns)
+        if not _DIGEST_POOL:
             _DIGEST_POOL.append(ThreadPoolExecutor(max_workers=1))
         digest = _DIGEST_POOL[0].submit(content_digest, ref_emb)
         Q = _device_copy(adata_query.obsm[query_basis], dev)

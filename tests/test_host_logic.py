@@ -346,6 +346,47 @@ def test_content_digest_notices_in_place_edits():
     assert tl.content_digest(lab) != e0
 
 
+def test_host_digest_is_thread_count_independent_and_sees_every_byte(built_library):
+    """`sym_host_digest64` (host code of the C-ABI library, no GPU): the same value on 1, 3 and 8 threads, a different
+    one after flipping any single bit (block interior, the zero-padded tail, a chunk boundary) or appending a zero."""
+    from symphonypy_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.default_rng(1)
+    buf = rng.integers(0, 256, (20 << 20) + 37, dtype=np.uint8)             # three 8 MiB chunks, ragged tail
+
+    def dig(b, threads=4):
+        return int(lib.sym_host_digest64(b.ctypes.data if b.size else None, b.nbytes, threads))
+
+    base = dig(buf)
+    assert {dig(buf, t) for t in (1, 3, 8, 0)} == {base}
+    for pos in (0, 63, 64, (8 << 20) - 1, 8 << 20, (16 << 20) + 5, buf.size - 1):
+        buf[pos] ^= 0x10
+        assert dig(buf) != base, pos
+        buf[pos] ^= 0x10
+    assert dig(buf) == base
+    small = np.zeros(70, dtype=np.uint8)
+    seen = {dig(small[:n]) for n in range(0, 71)}                           # all-zero inputs of every length differ
+    assert len(seen) == 71
+    assert dig(np.zeros((8 << 20) + 1, np.uint8)) != dig(np.zeros(8 << 20, np.uint8))
+
+
+def test_decode_labels_in_chunks(monkeypatch):
+    """Long label columns are gathered on a few threads; the column equals the single-call one."""
+    import pandas as pd
+
+    rng = np.random.default_rng(3)
+    classes = np.array([f"type {i}" for i in range(37)], dtype=object)
+    lab = rng.integers(0, 37, 5003).astype(np.int32)
+    idx = pd.RangeIndex(5003).astype(str)
+    whole = tl._decode_labels(classes, lab, idx)
+    monkeypatch.setattr(tl, "_DECODE_CHUNK", 512)
+    parts = tl._decode_labels(classes, lab, idx)
+    obs = pd.DataFrame(index=idx)
+    obs["parts"], obs["whole"], obs["plain"] = parts, whole, classes[lab]
+    assert obs["parts"].dtype == obs["plain"].dtype and obs["parts"].equals(obs["plain"]) and obs["whole"].equals(obs["plain"])
+
+
 @pytest.mark.parametrize("kind", ["category", "str", "object", "int", "category_unused", "bool"])
 def test_encode_labels_equals_numpy_unique(kind):
     rng = np.random.default_rng(1)

@@ -10,12 +10,16 @@ N, M, G, d, K, k = int(os.environ.get("N", 1_000_000)), 500_000, 2000, 30, 100, 
 model = synth.make_model(G, d, 20, 0, dev)
 Zref, comp, C, Nr = synth.make_reference(model, M, K, 0)
 X, codes, _ = synth.make_query(model, N, [1], 1000)
-FMT = os.environ.get("FMT", "pinned")   # pinned | pageable | csr
+FMT = os.environ.get("FMT", "pinned")   # pinned | pageable | csr | csr_pinned
 Xh = torch.empty((N, G), dtype=torch.float32, pin_memory=(FMT == "pinned")); Xh.copy_(X); del X
 Xq = Xh.numpy()
-if FMT == "csr":
+if FMT in ("csr", "csr_pinned"):
     import scipy.sparse as sp
     Xq = sp.csr_matrix(Xq)
+    if FMT == "csr_pinned":
+        dh = torch.empty(Xq.nnz, dtype=torch.float32, pin_memory=True); dh.copy_(torch.from_numpy(Xq.data))
+        ih = torch.empty(Xq.nnz, dtype=torch.int32, pin_memory=True); ih.copy_(torch.from_numpy(Xq.indices))
+        Xq = sp.csr_matrix((dh.numpy(), ih.numpy(), Xq.indptr), shape=Xq.shape)
 q = AnnDataLite(Xq, obs=pd.DataFrame(index=pd.RangeIndex(N).astype(str)),
                 var=pd.DataFrame(index=pd.Index([f"g{i}" for i in range(G)])), uns={"log1p": {}})
 _, ref = synth.to_anndata(model, Zref, comp, C, Nr, Xh[:8].to(dev), codes[:, :8], K, seed=0)
