@@ -83,7 +83,8 @@ _DIGEST_POOL: list = []
 def _hash_threads() -> int:
     """Host threads one digest may use (one process per GPU on one host: the ranks share its cores)."""
     ranks = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1) if _dist.active() else 1
-    return max(1, min(8, (os.cpu_count() or 1) // max(1, ranks)))
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    return max(1, min(8, cores // max(1, ranks)))
 
 
 def content_digest(*arrays) -> str:
