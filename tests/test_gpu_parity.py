@@ -830,6 +830,35 @@ def test_knn_tile_pruning_is_exact(cuda_device, method, N, M, d, k, sep):
     assert (i1.cpu().numpy() == want).mean() > 0.9999   # (float32 inputs: exact ties aside)
 
 
+@pytest.mark.parametrize("method", [engine.KNN_TC16, engine.KNN_TC])
+@pytest.mark.parametrize("N,M,d,k", [(20000, 50000, 30, 10), (6000, 40000, 50, 50)])
+def test_knn_scan_is_bit_reproducible(cuda_device, method, N, M, d, k):
+    """The same scan on the same inputs returns the same bits every time — neighbour lists, distances and the rows it
+    could not certify — also on a fresh workspace full of junk.  (What a racecheck would look for in the per-row
+    heaps, the parked-hit queues and the pair locks; compute-sanitizer is not available on the GPU pool.)"""
+    rng = np.random.default_rng(M + k)
+    cent = rng.normal(size=(8, d)) * 4
+    ref = (cent[rng.integers(0, 8, M)] + rng.normal(size=(M, d))).astype(np.float32)
+    qry = (cent[rng.integers(0, 8, N)] + rng.normal(size=(N, d))).astype(np.float32)
+    qry[:3] *= 1e4                                               # rows the FP16 tier cannot certify
+    index = engine.knn_fit(torch.from_numpy(ref).to(cuda_device))
+    Q = torch.from_numpy(qry).to(cuda_device)
+    first = None
+    for rep in range(4):
+        if rep == 2:
+            index.workspace.clear()
+            junk = torch.full((300_000_000,), 0x7F, dtype=torch.uint8, device=cuda_device)
+            del junk
+        idx, dist2, unsafe = engine.knn_search(index, Q, k, method)
+        ok = ~unsafe.bool()
+        cur = (unsafe.clone(), idx[ok].clone(), dist2[ok].clone())
+        if first is None:
+            first = cur
+            continue
+        assert torch.equal(first[0], cur[0]), f"rep {rep}: {int((first[0] != cur[0]).sum())} rows changed their flag"
+        assert torch.equal(first[1], cur[1]) and torch.equal(first[2], cur[2]), f"rep {rep}: results changed"
+
+
 @pytest.mark.parametrize("N,d,K", [(5000, 20, 30), (70000, 30, 100), (1500, 8, 200), (257, 3, 1)])
 def test_kmeanspp_kernel_matches_sklearn_restatement(cuda_device, N, d, K):
     """`sym_kmeanspp` (sampling, trial potentials, selection and D^2 update on the device) picks the rows that
