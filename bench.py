@@ -488,15 +488,24 @@ def roofline_of(st, ctx, res, name):
         hbm = peaks.get("hbm_gbs", 6650.0)
         sm = res["stage_ms"]
         other = []
-        for stage, kern, bytes_cell in (
-                ("project", "project_tma_kernel (tcgen05 FP16x3, X tiles by TMA)", 4.0 * G + 4.0 * d),
-                ("assign", "assign_kernel", 4.0 * d + 4.0 * K),
-                ("moe_stats", "moe_stats_kernel (+ counting sort)", 4.0 * d + 4.0 * K + 4.0 * V),
-                ("moe_solve_apply", "moe_solve_kernel + moe_apply_kernel", 8.0 * d + 4.0 * K + 4.0 * V)):
+        # FP32 FFMA peak (nominal: 148 SMs x 128 lanes x 2 flop x the SM clock; no measured figure in MEASURED_PEAKS.json):
+        # the three K x d products per cell sit at the ridge of the two rooflines (11.5 flop/B at d=30, K=100), so the
+        # FP32 fraction is reported next to the HBM one
+        fp32_tf = 148 * 128 * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
+        for stage, kern, bytes_cell, flops_cell in (
+                ("project", "project_tma_kernel (tcgen05 FP16x3, X tiles by TMA)", 4.0 * G + 4.0 * d, None),
+                ("assign", "assign_kernel", 4.0 * d + 4.0 * K, 2.0 * K * d),
+                ("moe_stats", "moe_stats_kernel (+ counting sort)", 4.0 * d + 4.0 * K + 4.0 * V, 2.0 * K * (d + 1)),
+                ("moe_solve_apply", "moe_solve_kernel + moe_apply_kernel", 8.0 * d + 4.0 * K + 4.0 * V, 2.0 * K * d)):
             if stage in sm and sm[stage] > 0:
                 gbs = N * bytes_cell / (sm[stage] / 1000.0) / 1e9
-                other.append({"stage": stage, "kernel": kern, "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s",
-                              "frac": gbs / hbm, "ms": sm[stage], "algorithmic_bytes_per_cell": bytes_cell})
+                row = {"stage": stage, "kernel": kern, "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s",
+                       "frac": gbs / hbm, "ms": sm[stage], "algorithmic_bytes_per_cell": bytes_cell}
+                if flops_cell:
+                    tf = N * flops_cell / (sm[stage] / 1000.0) / 1e12
+                    row["fp32"] = {"achieved_tflops": tf, "peak_tflops_nominal": fp32_tf, "frac": tf / fp32_tf,
+                                   "algorithmic_flops_per_cell": flops_cell}
+                other.append(row)
         roof["other_kernels"] = other
     return roof
 

@@ -301,7 +301,7 @@ constexpr size_t RR_SMEM = (size_t)(RR_THREADS / 32) * (RR_MAXC * (sizeof(double
 // its threshold — is flagged and goes to the next tier, whose last one ranks up to RR_MAXC single references); the
 // smaller lists let 5 instead of 4 blocks share an SM, which is what this latency-bound kernel needs
 constexpr int RG_MAXC = 256;
-constexpr size_t RR_SMEM_GROUPS = (size_t)(RR_THREADS / 32) * (RG_MAXC * (sizeof(double) + sizeof(int32_t)) + RR_DMAX * sizeof(float) + 256 * sizeof(float));
+constexpr size_t RR_SMEM_GROUPS = (size_t)(RR_THREADS / 32) * (RG_MAXC * (sizeof(double) + sizeof(int32_t)) + RR_DMAX * sizeof(double) + 256 * 2);
 
 __global__ void __launch_bounds__(RR_THREADS)
 knn_rerank_kernel(const float *__restrict__ Q, int ldq, int64_t N, const float *__restrict__ Ref, int ldr,
@@ -438,6 +438,21 @@ knn_rerank_kernel(const float *__restrict__ Q, int ldq, int64_t N, const float *
 // bytes, fully coalesced) in FP32; only the members that can still be among the k nearest if the row certifies —
 // score below the row's threshold plus the error margin, ~kc of them — get the exact float64 distance from their
 // reference row.  One warp per query row; lane <-> member in pass A, lane <-> survivor in pass B.
+// a0 += lo(q) * lo(r), a1 += hi(q) * hi(r): FP32 accumulation of 16-bit operand pairs without converting them first
+// (sm_100 mixed-precision FMA, `FHFMA`; the product of two 11-bit — or 8-bit — significands is exact in FP32, so this is
+// bit for bit the FFMA of the converted values)
+template <int PREC>
+__device__ __forceinline__ void fma_pair16(float &a0, float &a1, uint32_t q, uint32_t r) {
+    if (PREC == 1)
+        asm("{\n .reg .b16 ql, qh, rl, rh;\n mov.b32 {ql, qh}, %2;\n mov.b32 {rl, rh}, %3;\n"
+            " fma.rn.f32.f16 %0, ql, rl, %0;\n fma.rn.f32.f16 %1, qh, rh, %1;\n}\n"
+            : "+f"(a0), "+f"(a1) : "r"(q), "r"(r));
+    else
+        asm("{\n .reg .b16 ql, qh, rl, rh;\n mov.b32 {ql, qh}, %2;\n mov.b32 {rl, rh}, %3;\n"
+            " fma.rn.f32.bf16 %0, ql, rl, %0;\n fma.rn.f32.bf16 %1, qh, rh, %1;\n}\n"
+            : "+f"(a0), "+f"(a1) : "r"(q), "r"(r));
+}
+
 template <int PREC>   // 0: BF16x3 operands, 1: single FP16
 __global__ void __launch_bounds__(RR_THREADS)
 knn_rerank_groups_kernel(const float *__restrict__ Q, int ldq, int64_t N, const float *__restrict__ Ref, int ldr, int64_t M,
@@ -449,37 +464,29 @@ knn_rerank_groups_kernel(const float *__restrict__ Q, int ldq, int64_t N, const 
     extern __shared__ __align__(16) unsigned char rr_smem[];
     constexpr int W = RR_THREADS / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // per warp: survivors (double distance | int32 id, RG_MAXC each), the float32 query row, its packed operand row
+    // per warp: survivors (double distance | int32 id, RG_MAXC each), the query row, its packed operand row
     double *wd = reinterpret_cast<double *>(rr_smem) + (size_t)warp * RG_MAXC;
     int32_t *wi = reinterpret_cast<int32_t *>(rr_smem + (size_t)W * RG_MAXC * sizeof(double)) + (size_t)warp * RG_MAXC;
-    float *wq = reinterpret_cast<float *>(rr_smem + (size_t)W * RG_MAXC * (sizeof(double) + sizeof(int32_t))) + (size_t)warp * RR_DMAX;
-    // the query's packed operand row, converted to float once per row (kp <= 256 values): pass A then spends its
-    // conversions on the reference side only
-    float *wo = reinterpret_cast<float *>(rr_smem + (size_t)W * (RG_MAXC * (sizeof(double) + sizeof(int32_t)) + RR_DMAX * sizeof(float))) +
-                (size_t)warp * 256;
+    // the query row in float64 (pass B multiplies it with every survivor) and its packed 16-bit operand row (kp <= 256
+    // values) as the scan saw it (pass A)
+    double *wq = reinterpret_cast<double *>(rr_smem + (size_t)W * RG_MAXC * (sizeof(double) + sizeof(int32_t))) + (size_t)warp * RR_DMAX;
+    uint4 *wo = reinterpret_cast<uint4 *>(rr_smem + (size_t)W * (RG_MAXC * (sizeof(double) + sizeof(int32_t)) + RR_DMAX * sizeof(double))) +
+                (size_t)warp * 32;
     const int64_t row = (int64_t)blockIdx.x * W + warp;   // row of the scan (locality order)
     if (row >= N) return;
     const int64_t n = q_perm ? q_perm[row] : row;         // the query it stands for
     const float *q = Q + n * ldq;
-    for (int c = lane; c < d; c += 32) wq[c] = q[c];
     const int nunits = kp / 8;
-    for (int j = lane; j < kp / 2; j += 32) {   // two operand values per 32-bit word
-        const uint32_t w2 = __ldg(reinterpret_cast<const uint32_t *>(qrows + (size_t)row * kp * 2) + j);
-        if (PREC == 1) {
-            const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&w2));
-            wo[2 * j] = f.x;
-            wo[2 * j + 1] = f.y;
-        } else {
-            wo[2 * j] = __uint_as_float(w2 << 16);
-            wo[2 * j + 1] = __uint_as_float(w2 & 0xffff0000u);
-        }
-    }
-    __syncwarp();
     double qn = 0.0;
-    for (int c = 0; c < d; ++c) {
-        const double v = (double)wq[c];
+    for (int c = lane; c < d; c += 32) {
+        const double v = (double)q[c];
+        wq[c] = v;
         qn = fma(v, v, qn);
     }
+    for (int j = lane; j < nunits; j += 32) wo[j] = __ldg(reinterpret_cast<const uint4 *>(qrows + (size_t)row * kp * 2) + j);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) qn += __shfl_xor_sync(0xffffffffu, qn, o);   // (the same bits in every lane)
+    __syncwarp();
     const double rmax2 = (double)hdr->rmax2;
     double eps = eps_rel * (2.0 * sqrt(qn) * sqrt(rmax2) + rmax2);
     double unscale = 1.0;   // scan scores and thresholds are in units of scale16^2 when the operands were single FP16
@@ -520,21 +527,11 @@ knn_rerank_groups_kernel(const float *__restrict__ Q, int ldq, int64_t N, const 
 #pragma unroll 4
             for (int j = 0; j < nunits; ++j) {
                 const uint4 rv = __ldg(reinterpret_cast<const uint4 *>(t + (size_t)j * 2048));
-                const float4 qa = *reinterpret_cast<const float4 *>(wo + 8 * j), qb = *reinterpret_cast<const float4 *>(wo + 8 * j + 4);
-                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-                const float qf[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    float r0, r1;
-                    if (PREC == 1) {
-                        const float2 rf = __half22float2(*reinterpret_cast<const __half2 *>(&rw[u]));
-                        r0 = rf.x; r1 = rf.y;
-                    } else {
-                        r0 = __uint_as_float(rw[u] << 16); r1 = __uint_as_float(rw[u] & 0xffff0000u);
-                    }
-                    a0 = fmaf(qf[2 * u], r0, a0);
-                    a1 = fmaf(qf[2 * u + 1], r1, a1);
-                }
+                const uint4 qv = wo[j];
+                fma_pair16<PREC>(a0, a1, qv.x, rv.x);
+                fma_pair16<PREC>(a0, a1, qv.y, rv.y);
+                fma_pair16<PREC>(a0, a1, qv.z, rv.z);
+                fma_pair16<PREC>(a0, a1, qv.w, rv.w);
             }
             sc = a0 + a1;
         }
@@ -563,6 +560,7 @@ knn_rerank_groups_kernel(const float *__restrict__ Q, int ldq, int64_t N, const 
     }
     __syncwarp();
     // ---- pass B: exact float64 distance of the survivors (sklearn's formula), from their reference rows
+    const bool ref_pairs = (ldr & 1) == 0 && (reinterpret_cast<uintptr_t>(Ref) & 7) == 0;
     int nkeep = 0;
     for (int base = 0; base < nsurv; base += 32) {
         const int e = base + lane;
@@ -574,10 +572,22 @@ knn_rerank_groups_kernel(const float *__restrict__ Q, int ldq, int64_t N, const 
             id = order[wi[e]];
             const float *r = Ref + (int64_t)id * ldr;
             double rn = 0.0, dot = 0.0;
-            for (int c = 0; c < d; ++c) {
+            int c = 0;
+            if (ref_pairs) {   // rows start on 8-byte boundaries: two components per load
+                for (; c + 1 < d; c += 2) {
+                    const float2 rv2 = __ldg(reinterpret_cast<const float2 *>(r + c));
+                    const double2 qv = *reinterpret_cast<const double2 *>(wq + c);
+                    const double r0 = (double)rv2.x, r1 = (double)rv2.y;
+                    rn = fma(r0, r0, rn);
+                    dot = fma(qv.x, r0, dot);
+                    rn = fma(r1, r1, rn);
+                    dot = fma(qv.y, r1, dot);
+                }
+            }
+            for (; c < d; ++c) {
                 const double rv = (double)__ldg(r + c);
                 rn = fma(rv, rv, rn);
-                dot = fma((double)wq[c], rv, dot);
+                dot = fma(wq[c], rv, dot);
             }
             s_exact = rn - 2.0 * dot;
             bad |= !(fabs((double)sA * unscale - s_exact) <= eps);   // the error bound holds on the members that matter
