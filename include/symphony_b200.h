@@ -203,6 +203,18 @@ int sym_knn(const float *Q, int32_t ldq, int64_t N, const float *Ref, int32_t ld
             const void *packed, int32_t d, int32_t k, int32_t method, const int32_t *q_perm, const int32_t *q_code,
             const int32_t *cl_tile, int32_t *idx, float *dist2, uint8_t *unsafe, void *workspace,
             size_t workspace_bytes, sym_stream_t stream);
+/* Exact float64 brute force for a FEW query rows (n_rows <= sym_knn_exact_rows_max() = 64), the cheap way to finish
+ * the rows sym_knn flagged `unsafe` when there are only a handful of them (a scan launched for 4 rows costs ~0.8 ms, a
+ * reading of the reference ~0.03 ms).  rows [n_rows] int64: indices into Q.  ub [n_rows] f32: an upper bound on each
+ * row's k-th squared distance — e.g. the k-th distance sym_knn returned for that row (uncertified results are still exact
+ * distances of real reference rows), nudged up; +inf is allowed but useless.  idx_out / dist2_out [n_rows,k] as sym_knn
+ * (same formula, same tie rule).  overflow [n_rows] uint8 = 1 for rows whose bound admitted more than 1024 reference rows
+ * (or fewer than k: not a bound): nothing usable was written, send them through sym_knn with the next method. */
+int32_t sym_knn_exact_rows_max(void);
+size_t sym_knn_exact_rows_workspace(int32_t n_rows);
+int sym_knn_exact_rows(const float *Q, int32_t ldq, const int64_t *rows, int32_t n_rows, const float *Ref, int32_t ldr,
+                       int64_t M, int32_t d, int32_t k, const float *ub, int32_t *idx_out, float *dist2_out,
+                       uint8_t *overflow, void *workspace, size_t workspace_bytes, sym_stream_t stream);
 int sym_vote(const int32_t *idx, const float *dist2, int64_t N, int32_t k, const int32_t *ref_codes, int64_t M,
              int32_t *label, float *conf, sym_stream_t stream);
 

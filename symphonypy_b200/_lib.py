@@ -48,6 +48,10 @@ SIGNATURES = {
     "sym_knn_method_supported": (c_int32, [c_int64, c_int64, c_int32, c_int32, c_int32]),
     "sym_knn": (c_int32, [_P, c_int32, c_int64, _P, c_int32, c_int64, _P, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P,
                           _P, _P, c_size_t, _P]),
+    "sym_knn_exact_rows_max": (c_int32, []),
+    "sym_knn_exact_rows_workspace": (c_size_t, [c_int32]),
+    "sym_knn_exact_rows": (c_int32, [_P, c_int32, _P, c_int32, _P, c_int32, c_int64, c_int32, c_int32, _P, _P, _P, _P, _P,
+                                     c_size_t, _P]),
     "sym_vote": (c_int32, [_P, _P, c_int64, c_int32, _P, c_int64, _P, _P, _P]),
     "sym_cluster_moments": (c_int32, [_P, c_int32, c_int64, c_int32, _P, c_int32, _P, _P]),
     "sym_cluster_cov": (c_int32, [_P, c_int32, c_int64, c_int32, _P, c_int32, _P, _P, _P]),

@@ -627,6 +627,109 @@ knn_rerank_groups_kernel(const float *__restrict__ Q, int ldq, int64_t N, const 
     }
 }
 
+// ------------------------------------------------------------------------------------------ exact search of a few rows
+// The handful of rows per pass whose first-tier result could not be certified used to go through a second scan and
+// re-rank launched for them alone: two small-grid launches that spend ~0.8 ms on 4 rows.  For a few rows brute force
+// in float64 is cheaper than any scan — 2 R M d flop at R <= 64 is a reading of the reference — and needs no
+// certificate, given an upper bound on each row's k-th distance: the first tier's own k-th result is one (they are exact
+// distances of real reference rows).  Kernel 1 lists, per row, every reference row within the bound (normally k plus
+// a few); kernel 2 ranks the list by (distance, index) and writes the first k.
+constexpr int XR_MAX_ROWS = 64;
+constexpr int XR_CAP = 1024;     // listed reference rows per query row; more (a useless bound) -> the row is flagged
+constexpr int XR_THREADS = 256;
+constexpr int XR_RJ = 4;         // query rows per pass over a reference row
+
+__global__ void __launch_bounds__(XR_THREADS)
+knn_exact_collect_kernel(const float *__restrict__ Q, int ldq, const int64_t *__restrict__ rows, int n_rows,
+                         const float *__restrict__ Ref, int ldr, int64_t M, int d, const float *__restrict__ ub,
+                         int32_t *__restrict__ counts, double *__restrict__ ldist, int32_t *__restrict__ lid) {
+    extern __shared__ __align__(16) unsigned char xr_smem[];
+    double *qd = reinterpret_cast<double *>(xr_smem);          // [n_rows][d]
+    double *qn = qd + (size_t)n_rows * d;                      // [n_rows]
+    double *bound = qn + n_rows;                               // [n_rows]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int j = warp; j < n_rows; j += XR_THREADS / 32) {
+        const float *q = Q + rows[j] * ldq;
+        double s = 0.0;
+        for (int c = lane; c < d; c += 32) {      // (||q||^2 summed exactly as the re-rank kernels sum it)
+            const double v = (double)q[c];
+            qd[(size_t)j * d + c] = v;
+            s = fma(v, v, s);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) {
+            qn[j] = s;
+            bound[j] = (double)ub[j];
+        }
+    }
+    __syncthreads();
+    for (int64_t m = (int64_t)blockIdx.x * XR_THREADS + threadIdx.x; m < M; m += (int64_t)gridDim.x * XR_THREADS) {
+        const float *r = Ref + m * ldr;
+        double rn = 0.0;
+        for (int c = 0; c < d; ++c) {
+            const double rv = (double)__ldg(r + c);
+            rn = fma(rv, rv, rn);
+        }
+        for (int j0 = 0; j0 < n_rows; j0 += XR_RJ) {
+            double dot[XR_RJ];
+#pragma unroll
+            for (int j = 0; j < XR_RJ; ++j) dot[j] = 0.0;
+            for (int c = 0; c < d; ++c) {
+                const double rv = (double)__ldg(r + c);
+#pragma unroll
+                for (int j = 0; j < XR_RJ; ++j)
+                    if (j0 + j < n_rows) dot[j] = fma(qd[(size_t)(j0 + j) * d + c], rv, dot[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < XR_RJ; ++j) {
+                if (j0 + j >= n_rows) break;
+                const double dist = fmax(qn[j0 + j] + (rn - 2.0 * dot[j]), 0.0);   // sklearn's formula, as in the re-rank
+                if (dist <= bound[j0 + j]) {
+                    const int pos = atomicAdd(&counts[j0 + j], 1);
+                    if (pos < XR_CAP) {
+                        ldist[(size_t)(j0 + j) * XR_CAP + pos] = dist;
+                        lid[(size_t)(j0 + j) * XR_CAP + pos] = (int32_t)m;
+                    }
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(XR_THREADS)
+knn_exact_select_kernel(int k, const int32_t *__restrict__ counts, const double *__restrict__ ldist,
+                        const int32_t *__restrict__ lid, int32_t *__restrict__ idx_out, float *__restrict__ dist_out,
+                        uint8_t *__restrict__ overflow) {
+    __shared__ double sd[XR_CAP];
+    __shared__ int32_t si[XR_CAP];
+    const int j = blockIdx.x, n = counts[j];
+    if (n > XR_CAP || n < k) {   // the bound was useless (or not a bound at all): the caller takes the scan tiers
+        if (threadIdx.x == 0) overflow[j] = 1;
+        for (int e = threadIdx.x; e < k; e += XR_THREADS) {
+            idx_out[(size_t)j * k + e] = -1;
+            dist_out[(size_t)j * k + e] = INFINITY;
+        }
+        return;
+    }
+    if (threadIdx.x == 0) overflow[j] = 0;
+    for (int e = threadIdx.x; e < n; e += XR_THREADS) {
+        sd[e] = ldist[(size_t)j * XR_CAP + e];
+        si[e] = lid[(size_t)j * XR_CAP + e];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < n; e += XR_THREADS) {
+        const double de = sd[e];
+        const int32_t ie = si[e];
+        int rank = 0;
+        for (int f = 0; f < n; ++f) rank += (sd[f] < de) || (sd[f] == de && si[f] < ie);
+        if (rank < k) {
+            idx_out[(size_t)j * k + rank] = ie;
+            dist_out[(size_t)j * k + rank] = (float)de;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ nearest centroid
 // code[n] = argmin_c ||x_n - cent_c||^2 (lowest c on ties).  Used to put queries and reference rows into the
 // same coarse spatial order, so that a query tile meets its likely neighbours in the first reference tiles
@@ -907,5 +1010,39 @@ extern "C" int sym_vote(const int32_t *idx, const float *dist2, int64_t N, int32
     knn_vote_kernel<<<(unsigned)ceil_div(N, 128), 128, 0, (cudaStream_t)stream>>>(idx, dist2, N, k, ref_codes, M, label,
                                                                                     conf);
     SYM_LAUNCH_CHECK("knn_vote_kernel");
+    return SYM_OK;
+}
+
+// ---- exact search of a few rows (see knn_exact_collect_kernel)
+extern "C" int32_t sym_knn_exact_rows_max(void) { return sym::XR_MAX_ROWS; }
+extern "C" size_t sym_knn_exact_rows_workspace(int32_t n_rows) {
+    const size_t n = n_rows > 0 ? (size_t)n_rows : 0;
+    return 256 + ((n * sizeof(int32_t) + 255) & ~(size_t)255) + n * sym::XR_CAP * (sizeof(double) + sizeof(int32_t));
+}
+extern "C" int sym_knn_exact_rows(const float *Q, int32_t ldq, const int64_t *rows, int32_t n_rows, const float *Ref,
+                                  int32_t ldr, int64_t M, int32_t d, int32_t k, const float *ub, int32_t *idx_out,
+                                  float *dist2_out, uint8_t *overflow, void *workspace, size_t workspace_bytes,
+                                  sym_stream_t stream) {
+    using namespace sym;
+    SYM_REQUIRE(n_rows >= 0 && n_rows <= XR_MAX_ROWS && M >= 1 && d >= 1 && d <= 128 && k >= 1 && k <= M && ldq >= d && ldr >= d,
+                SYM_ERR_INVALID_ARGUMENT, "sym_knn_exact_rows: bad sizes (n_rows <= %d, d <= 128, k <= M)", XR_MAX_ROWS);
+    SYM_REQUIRE(k <= XR_CAP, SYM_ERR_UNSUPPORTED_SHAPE, "sym_knn_exact_rows: k=%d (<= %d)", k, XR_CAP);
+    if (n_rows == 0) return SYM_OK;
+    SYM_REQUIRE(workspace_bytes >= sym_knn_exact_rows_workspace(n_rows), SYM_ERR_WORKSPACE_TOO_SMALL,
+                "sym_knn_exact_rows: workspace of %zu B, %zu needed", workspace_bytes, sym_knn_exact_rows_workspace(n_rows));
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char *w = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+    int32_t *counts = reinterpret_cast<int32_t *>(w);
+    double *ldist = reinterpret_cast<double *>(w + (((size_t)n_rows * sizeof(int32_t) + 255) & ~(size_t)255));
+    int32_t *lid = reinterpret_cast<int32_t *>(ldist + (size_t)n_rows * XR_CAP);
+    SYM_CUDA(cudaMemsetAsync(counts, 0, (size_t)n_rows * sizeof(int32_t), st));
+    const size_t smem = ((size_t)n_rows * d + 2 * (size_t)n_rows) * sizeof(double);
+    SYM_CUDA(cudaFuncSetAttribute(knn_exact_collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t grid = ceil_div(M, XR_THREADS);
+    if (grid > 8 * kNumSMs) grid = 8 * kNumSMs;
+    knn_exact_collect_kernel<<<(unsigned)grid, XR_THREADS, smem, st>>>(Q, ldq, rows, n_rows, Ref, ldr, M, d, ub, counts, ldist, lid);
+    SYM_LAUNCH_CHECK("knn_exact_collect_kernel");
+    knn_exact_select_kernel<<<(unsigned)n_rows, XR_THREADS, 0, st>>>(k, counts, ldist, lid, idx_out, dist2_out, overflow);
+    SYM_LAUNCH_CHECK("knn_exact_select_kernel");
     return SYM_OK;
 }

@@ -393,11 +393,40 @@ def knn_search(index: KnnIndex, Q: torch.Tensor, k: int, method: int = KNN_AUTO,
     return idx, dist2, unsafe
 
 
+EXACT_ROWS_MAX = 64      # = sym_knn_exact_rows_max()
+
+
+def knn_exact_rows(index: KnnIndex, Q: torch.Tensor, rows: torch.Tensor, k: int, ub: torch.Tensor):
+    """Exact float64 brute force for the few query rows `rows` (int64 indices into Q) given upper bounds `ub` [n] f32 on
+    their k-th squared distances: (idx [n,k] int32, dist2 [n,k] f32, overflow [n] uint8 — rows the bound did not help)."""
+    lib = _lib.load()
+    Q = _f32c(Q)
+    n = int(rows.numel())
+    dev = Q.device
+    idx = torch.empty((n, k), device=dev, dtype=torch.int32)
+    dist2 = torch.empty((n, k), device=dev, dtype=torch.float32)
+    over = torch.empty(n, device=dev, dtype=torch.uint8)
+    ws_bytes = int(lib.sym_knn_exact_rows_workspace(n))
+    ws = index.workspace.get("exact")
+    if ws is None or ws.numel() < ws_bytes or ws.device != dev:
+        ws = torch.empty(max(ws_bytes, int(lib.sym_knn_exact_rows_workspace(8))), device=dev, dtype=torch.uint8)
+        index.workspace["exact"] = ws
+    rows = rows.to(torch.int64).contiguous()
+    ub = ub.to(torch.float32).contiguous()
+    _lib.check(lib.sym_knn_exact_rows(Q.data_ptr(), Q.stride(0), rows.data_ptr(), n, index.ref.data_ptr(),
+                                      index.ref.stride(0), index.M, index.d, k, ub.data_ptr(), idx.data_ptr(),
+                                      dist2.data_ptr(), over.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)),
+               "sym_knn_exact_rows")
+    return idx, dist2, over
+
+
 def knn_search_certified(index: KnnIndex, Q: torch.Tensor, k: int, method: int = KNN_AUTO, events: list | None = None,
                          prune: bool = False, after_launch=None):
     """`knn_search` plus the repair passes.  Rows whose over-selection margin could not be certified (possible
     with the reduced-precision tensor-core scans, or with many exactly tied neighbours) are re-run with the next
-    more accurate scan: single-FP16 tcgen05 -> BF16x3 tcgen05 -> FP32 FFMA.
+    more accurate scan: single-FP16 tcgen05 -> BF16x3 tcgen05 -> FP32 FFMA.  When only a handful of rows (<= 64) are
+    left after the first tier they are finished by exact float64 brute force instead (`knn_exact_rows`, bounded by
+    the k-th distance the first tier found for them): a reading of the reference instead of two small-grid launches.
 
     With `method=KNN_AUTO` the first tier is the single-FP16 scan (a third of the MMAs) unless this index has
     shown, for this k, that more than 8 % of the rows then need the BF16x3 scan anyway (dense neighbourhoods:
@@ -423,6 +452,16 @@ def knn_search_certified(index: KnnIndex, Q: torch.Tensor, k: int, method: int =
     n_first = n_bad = int(unsafe.sum().item())
     if n_bad and os.environ.get("SYM_KNN_NO_REPAIR") != "1":  # (the switch exists for kernel timing experiments only)
         rows = torch.nonzero(unsafe, as_tuple=False).flatten()
+        if n_bad <= EXACT_ROWS_MAX and os.environ.get("SYM_KNN_EXACT_ROWS", "1") != "0":
+            # a handful of rows: exact brute force within the k-th distance the first tier found for them (an upper
+            # bound on the true one: uncertified results are still exact distances of real reference rows)
+            ub = torch.nextafter(dist2[rows, k - 1] * (1.0 + 1e-6), torch.full((), float("inf"), device=dist2.device))
+            i2, d2, over = knn_exact_rows(index, Q, rows, k, ub)
+            done = over == 0
+            idx[rows[done]] = i2[done]
+            dist2[rows[done]] = d2[done]
+            rows = rows[~done]                      # (bound useless, e.g. fewer than k survivors: scan tiers below)
+            n_bad = int(rows.numel())
         tier = first
         while n_bad and tier != KNN_FFMA:
             tier = KNN_TC if tier == KNN_TC16 and supported(KNN_TC, n_bad) else KNN_FFMA

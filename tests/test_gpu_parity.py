@@ -859,6 +859,74 @@ def test_knn_scan_is_bit_reproducible(cuda_device, method, N, M, d, k):
         assert torch.equal(first[1], cur[1]) and torch.equal(first[2], cur[2]), f"rep {rep}: results changed"
 
 
+@pytest.mark.parametrize("n_rows,M,d,k", [(4, 50000, 30, 10), (64, 20000, 50, 50), (1, 300, 3, 300), (7, 5000, 128, 1)])
+def test_knn_exact_rows_kernel(cuda_device, n_rows, M, d, k):
+    """`sym_knn_exact_rows`: float64 brute force of a few rows inside a given bound — duplicates and exact ties
+    included (lower index first) — equals the oracle's kneighbors; a useless bound is reported, not answered."""
+    rng = np.random.default_rng(M + k)
+    ref = rng.normal(size=(M, d)).astype(np.float32)
+    ref[M // 2: M // 2 + 5] = ref[3]                       # duplicated reference rows: exact distance ties
+    qry = rng.normal(size=(200, d)).astype(np.float32)
+    qry[17] = ref[3]                                       # a query on top of them: distance 0 five + 1 times
+    rows = np.sort(rng.choice(200, n_rows, replace=False))
+    if n_rows >= 4:
+        rows[0] = 17
+        rows = np.unique(rows)
+    want_i, want_d = so.knn_indices(ref.astype(np.float64), qry[rows].astype(np.float64), k)
+    index = engine.knn_fit(torch.from_numpy(ref).to(cuda_device))
+    Q = torch.from_numpy(qry).to(cuda_device)
+    kth = torch.from_numpy(want_d[:, k - 1].astype(np.float32)).to(cuda_device)      # (squared distances)
+    ub = torch.nextafter(kth * (1 + 1e-6), torch.full((), float("inf"), device=cuda_device))
+    r = torch.from_numpy(rows).to(cuda_device)
+    idx, dist2, over = engine.knn_exact_rows(index, Q, r, k, ub)
+    assert int(over.sum()) == 0
+    got = idx.cpu().numpy()
+    same = got == want_i
+    if 17 in rows:   # the six references at distance 0 from query 17 come in index order here, in heap order in sklearn
+        j17 = int(np.where(rows == 17)[0][0])
+        assert set(got[j17, :min(k, 6)]) <= set(want_i[j17, :6]) | set([3] + list(range(M // 2, M // 2 + 5)))
+        same[j17, :6] = True
+    # float32 inputs: the oracle's float64 distances can tie where ours differ in the last bit only for the duplicates,
+    # which the kernel orders by index like sklearn
+    assert same.mean() > 0.999, f"{(~same).sum()} of {same.size} neighbours differ"
+    if 17 in rows and k >= 6:
+        j = int(np.where(rows == 17)[0][0])
+        assert got[j, :6].tolist() == sorted([3] + list(range(M // 2, M // 2 + 5)))
+    np.testing.assert_allclose(dist2.cpu().numpy(), want_d, rtol=2e-5, atol=2e-4)
+    # loose bound within the list capacity: same answer; no bound at all: reported
+    if M > 2000:
+        idx2, _, over2 = engine.knn_exact_rows(index, Q, r, k, ub * 1.02)
+        assert int(over2.sum()) == 0 and torch.equal(idx2, idx)
+        _, _, over3 = engine.knn_exact_rows(index, Q, r, k, torch.full_like(ub, float("inf")))
+        assert int(over3.sum()) == len(rows)
+    if k > 1:   # half the k-th distance holds fewer than k rows (the query sitting on duplicates aside): not a bound
+        _, _, over4 = engine.knn_exact_rows(index, Q, r, k, ub * 0.5)
+        assert int(over4.sum()) >= len(rows) - 1
+
+
+def test_few_uncertified_rows_take_the_exact_path(cuda_device, monkeypatch):
+    """A search that leaves a handful of rows uncertified finishes them with `knn_exact_rows` (no second scan) and
+    returns what the tiered repair returns."""
+    rng = np.random.default_rng(5)
+    M, N, d, k = 60000, 9000, 30, 10
+    ref = rng.normal(size=(M, d)).astype(np.float32)
+    qry = rng.normal(size=(N, d)).astype(np.float32)
+    qry[:5] *= 300.0                                        # far outside the reference: FP16 scores cannot certify them
+    index = engine.knn_fit(torch.from_numpy(ref).to(cuda_device))
+    Q = torch.from_numpy(qry).to(cuda_device)
+    used = []
+    real = engine.knn_exact_rows
+    monkeypatch.setattr(engine, "knn_exact_rows", lambda *a: used.append(int(a[2].numel())) or real(*a))
+    i1, d1, n1 = engine.knn_search_certified(index, Q, k)
+    assert 0 < n1 <= engine.EXACT_ROWS_MAX and used == [n1]
+    monkeypatch.setenv("SYM_KNN_EXACT_ROWS", "0")
+    i0, d0, n0 = engine.knn_search_certified(index, Q, k)
+    assert n0 == n1 and len(used) == 1
+    assert torch.equal(i0, i1) and torch.allclose(d0, d1, rtol=1e-6)
+    want, _ = so.knn_indices(ref.astype(np.float64), qry[:50].astype(np.float64), k)
+    assert (i1[:50].cpu().numpy() == want).mean() > 0.999
+
+
 @pytest.mark.parametrize("N,d,K", [(5000, 20, 30), (70000, 30, 100), (1500, 8, 200), (257, 3, 1)])
 def test_kmeanspp_kernel_matches_sklearn_restatement(cuda_device, N, d, K):
     """`sym_kmeanspp` (sampling, trial potentials, selection and D^2 update on the device) picks the rows that

@@ -218,6 +218,28 @@ def test_knn_tier_logic_with_a_fake_scan(monkeypatch):
     engine.knn_search_certified(index, Q, k, engine.KNN_TC16)
     assert calls[0] == (engine.KNN_TC16, N)
 
+    # a handful of uncertified rows: exact brute force first (bounded by the first tier's k-th distance), and only the
+    # rows it could not finish go on to the scan tiers
+    exact_calls = []
+
+    def fake_exact(index, Q, rows, k, ub):
+        exact_calls.append((rows.tolist(), ub.tolist()))
+        tag = Q[rows, 0].long()
+        over = (tag % 200 == 0).to(torch.uint8)   # "bound useless" for these
+        return (tag[:, None] * 10 + 9).int().repeat(1, k), torch.ones((len(rows), k)), over
+
+    monkeypatch.setattr(engine, "knn_exact_rows", fake_exact)
+    calls.clear()
+    index2 = engine.KnnIndex(ref=torch.zeros((10, 4)), packed=torch.zeros(1, dtype=torch.uint8), M=10, d=4)
+    index2.fail16 = 100                           # 50 rows fail
+    idx, dist2, n_rep = engine.knn_search_certified(index2, Q, k)
+    assert n_rep == 50 and len(exact_calls) == 1 and exact_calls[0][0] == list(range(0, N, 100))
+    assert all(u > 0 for u in exact_calls[0][1])  # the k-th distance (0 here) nudged up
+    assert calls == [(engine.KNN_TC16, N), (engine.KNN_TC, 25), (engine.KNN_FFMA, 25)]
+    tier = idx[:, 0] % 10
+    assert (tier[(rows % 100 == 0) & (rows % 200 != 0)] == 9).all() and (tier[rows % 200 == 0] == engine.KNN_FFMA).all()
+    assert (idx[:, 0] // 10 == rows).all()
+
 
 def test_cluster_maha_dists_matches_oracle():
     """Host half of `per_cluster_confidence`: from exact per-cluster moments it reproduces the oracle's
