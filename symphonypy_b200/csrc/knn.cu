@@ -663,12 +663,26 @@ knn_exact_collect_kernel(const float *__restrict__ Q, int ldq, const int64_t *__
             bound[j] = (double)ub[j];
         }
     }
-    __syncthreads();
-    for (int64_t m = (int64_t)blockIdx.x * XR_THREADS + threadIdx.x; m < M; m += (int64_t)gridDim.x * XR_THREADS) {
-        const float *r = Ref + m * ldr;
+    // 256 reference rows at a time are staged in shared memory with coalesced loads (row stride odd: thread t then
+    // reads row t without bank conflicts; straight from global memory every load of a warp touched 32 lines)
+    float *rs = reinterpret_cast<float *>(bound + n_rows);     // [XR_THREADS][DS]
+    const int DS = d | 1;
+    for (int64_t m0 = (int64_t)blockIdx.x * XR_THREADS; m0 < M; m0 += (int64_t)gridDim.x * XR_THREADS) {
+        __syncthreads();
+        const int nr = M - m0 < XR_THREADS ? (int)(M - m0) : XR_THREADS;
+        if (ldr == d) {
+            const float *src = Ref + m0 * ldr;
+            for (int i = threadIdx.x; i < nr * d; i += XR_THREADS) rs[(i / d) * DS + (i % d)] = __ldg(src + i);
+        } else {
+            for (int i = threadIdx.x; i < nr * d; i += XR_THREADS) rs[(i / d) * DS + (i % d)] = __ldg(Ref + (m0 + i / d) * ldr + (i % d));
+        }
+        __syncthreads();
+        if ((int)threadIdx.x >= nr) continue;
+        const int64_t m = m0 + threadIdx.x;
+        const float *r = rs + threadIdx.x * DS;
         double rn = 0.0;
         for (int c = 0; c < d; ++c) {
-            const double rv = (double)__ldg(r + c);
+            const double rv = (double)r[c];
             rn = fma(rv, rv, rn);
         }
         for (int j0 = 0; j0 < n_rows; j0 += XR_RJ) {
@@ -676,7 +690,7 @@ knn_exact_collect_kernel(const float *__restrict__ Q, int ldq, const int64_t *__
 #pragma unroll
             for (int j = 0; j < XR_RJ; ++j) dot[j] = 0.0;
             for (int c = 0; c < d; ++c) {
-                const double rv = (double)__ldg(r + c);
+                const double rv = (double)r[c];
 #pragma unroll
                 for (int j = 0; j < XR_RJ; ++j)
                     if (j0 + j < n_rows) dot[j] = fma(qd[(size_t)(j0 + j) * d + c], rv, dot[j]);
@@ -1036,10 +1050,11 @@ extern "C" int sym_knn_exact_rows(const float *Q, int32_t ldq, const int64_t *ro
     double *ldist = reinterpret_cast<double *>(w + (((size_t)n_rows * sizeof(int32_t) + 255) & ~(size_t)255));
     int32_t *lid = reinterpret_cast<int32_t *>(ldist + (size_t)n_rows * XR_CAP);
     SYM_CUDA(cudaMemsetAsync(counts, 0, (size_t)n_rows * sizeof(int32_t), st));
-    const size_t smem = ((size_t)n_rows * d + 2 * (size_t)n_rows) * sizeof(double);
+    const size_t smem = ((size_t)n_rows * d + 2 * (size_t)n_rows) * sizeof(double) + (size_t)XR_THREADS * (d | 1) * sizeof(float);
     SYM_CUDA(cudaFuncSetAttribute(knn_exact_collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t grid = ceil_div(M, XR_THREADS);
-    if (grid > 8 * kNumSMs) grid = 8 * kNumSMs;
+    const int per_sm = smem > 100 * 1024 ? 1 : (smem > 48 * 1024 ? 2 : 4);
+    if (grid > (int64_t)per_sm * kNumSMs) grid = (int64_t)per_sm * kNumSMs;
     knn_exact_collect_kernel<<<(unsigned)grid, XR_THREADS, smem, st>>>(Q, ldq, rows, n_rows, Ref, ldr, M, d, ub, counts, ldist, lid);
     SYM_LAUNCH_CHECK("knn_exact_collect_kernel");
     knn_exact_select_kernel<<<(unsigned)n_rows, XR_THREADS, 0, st>>>(k, counts, ldist, lid, idx_out, dist2_out, overflow);
