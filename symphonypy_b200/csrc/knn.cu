@@ -477,16 +477,16 @@ knn_rerank_groups_kernel(const float *__restrict__ Q, int ldq, int64_t N, const 
     const int64_t n = q_perm ? q_perm[row] : row;         // the query it stands for
     const float *q = Q + n * ldq;
     const int nunits = kp / 8;
+    for (int c = lane; c < d; c += 32) wq[c] = (double)q[c];
+    for (int j = lane; j < nunits; j += 32) wo[j] = __ldg(reinterpret_cast<const uint4 *>(qrows + (size_t)row * kp * 2) + j);
+    __syncwarp();
+    // ||q||^2 summed in the order pass B sums ||r||^2 and q.r: a query that IS a reference row then gets the distance
+    // qn - 2 dot + rn = 0 exactly (every lane computes the same bits)
     double qn = 0.0;
-    for (int c = lane; c < d; c += 32) {
-        const double v = (double)q[c];
-        wq[c] = v;
+    for (int c = 0; c < d; ++c) {
+        const double v = wq[c];
         qn = fma(v, v, qn);
     }
-    for (int j = lane; j < nunits; j += 32) wo[j] = __ldg(reinterpret_cast<const uint4 *>(qrows + (size_t)row * kp * 2) + j);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) qn += __shfl_xor_sync(0xffffffffu, qn, o);   // (the same bits in every lane)
-    __syncwarp();
     const double rmax2 = (double)hdr->rmax2;
     double eps = eps_rel * (2.0 * sqrt(qn) * sqrt(rmax2) + rmax2);
     double unscale = 1.0;   // scan scores and thresholds are in units of scale16^2 when the operands were single FP16
@@ -650,15 +650,11 @@ knn_exact_collect_kernel(const float *__restrict__ Q, int ldq, const int64_t *__
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int j = warp; j < n_rows; j += XR_THREADS / 32) {
         const float *q = Q + rows[j] * ldq;
-        double s = 0.0;
-        for (int c = lane; c < d; c += 32) {      // (||q||^2 summed exactly as the re-rank kernels sum it)
-            const double v = (double)q[c];
-            qd[(size_t)j * d + c] = v;
-            s = fma(v, v, s);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) {
+        for (int c = lane; c < d; c += 32) qd[(size_t)j * d + c] = (double)q[c];
+        __syncwarp();
+        if (lane == 0) {   // ||q||^2 in the order ||r||^2 and q.r are summed below (a row's distance to itself is exactly 0)
+            double s = 0.0;
+            for (int c = 0; c < d; ++c) s = fma(qd[(size_t)j * d + c], qd[(size_t)j * d + c], s);
             qn[j] = s;
             bound[j] = (double)ub[j];
         }

@@ -437,8 +437,6 @@ project_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t N, int G, c
                 xv[j][0] = *reinterpret_cast<const float4 *>(raw + rl[j] * 128 + off0);
                 xv[j][1] = *reinterpret_cast<const float4 *>(raw + rl[j] * 128 + off1);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&raw_empty[s]);   // this warp's part of the raw tile is in registers
             uint32_t hi[2][4], lo[2][4];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -454,6 +452,17 @@ project_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t N, int G, c
                     pt_split(tt[0], tt[1], hi[j][e], lo[j][e]);
                 }
             }
+            // Release the raw stage only now, after the values have been USED: the loads above are merely issued when
+            // the next instruction runs, and the TMA write that refills the stage goes through the async proxy, which is
+            // not ordered behind generic-proxy loads still in flight.  Arriving right after the loads (with or without a
+            // membar.cta) let ~0.3 % of the tiles read one 32-byte unit of the NEXT use of the stage: one cell per ~300
+            // tiles off by a few per cent, differently on every launch (found by repeated launches on the same input —
+            // `tests: test_project_tensor_core_large_launches`).  Either measure fixes it alone: the arrive after the uses, or
+            // a generic -> async proxy fence before it; both are kept (the compiler may sink register arithmetic below
+            // the barrier instructions, the fence does not depend on instruction placement).
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&raw_empty[s]);
             mbar_wait(&op_empty[t], ph_op ^ 1);   // the MMAs that read this operand stage last time are done
             unsigned char *stage = op_s + (size_t)t * OP_STAGE;
             if (tid == 0) {   // this chunk's loadings: [hi | lo] in one bulk copy

@@ -144,6 +144,35 @@ def test_project_csr_kernel(cuda_device):
     assert row_rel_err(Z.cpu().numpy(), want) < 2e-5
 
 
+@pytest.mark.parametrize("d", [30, 50, 100])
+def test_project_tensor_core_large_launches(cuda_device, d):
+    """A launch of many waves of CTAs (200k cells: 1563 tiles on 296 CTA slots) is as accurate as a small one and
+    returns the same bits every time.  (A shared-memory stage released to the TMA unit too early once corrupted one
+    cell in ~300 tiles, differently on every launch; launches of a few dozen tiles — all the other tests — rarely showed it.)"""
+    N, G = 200_000, 2000
+    g = torch.Generator(device=cuda_device)
+    g.manual_seed(d)
+    X = (torch.rand((N, G), device=cuda_device, generator=g) < 0.1) * torch.rand((N, G), device=cuda_device, generator=g) * 6
+    mu = torch.rand(G, device=cuda_device, generator=g) * 0.5
+    sd = torch.rand(G, device=cuda_device, generator=g) + 0.3
+    U = torch.randn((G, d), device=cuda_device, generator=g) / 40
+    pad = (-d) % 4
+    ld = engine.Loadings(mu=mu, inv_sd=1.0 / sd, U=torch.nn.functional.pad(U, (0, pad)).contiguous(), d=d)
+    Z0 = engine.project_dense(X, ld).clone()
+    want = torch.empty((N, d), device=cuda_device, dtype=torch.float64)
+    for s in range(0, N, 50_000):   # float64 reference in slices (a float64 copy of X would be 3.2 GB)
+        t = ((X[s:s + 50_000].double() - mu.double()) * (1.0 / sd).double()).clamp(-10, 10)
+        want[s:s + 50_000] = t @ U.double()
+    rel = ((Z0.double() - want).norm(dim=1) / want.norm(dim=1)).max().item()
+    assert rel < 2e-5, rel
+    junk = torch.empty(32 << 20, device=cuda_device)
+    for i in range(25):
+        if i % 3 == 0:
+            junk.normal_()       # other work between the launches: different timing, different cache contents
+        Z = engine.project_dense(X, ld)
+        assert torch.equal(Z, Z0), f"launch {i}: {int((Z != Z0).any(1).sum())} rows differ"
+
+
 # ------------------------------------------------------------------------------ kernel level: assign
 @pytest.mark.parametrize("N,d,K", [(1, 20, 100), (1001, 30, 100), (513, 50, 200), (77, 20, 7), (300, 24, 300),
                                    (64, 20, 600)])

@@ -33,5 +33,10 @@ def step():
 step()
 t0 = time.perf_counter(); t1 = step(); t2 = time.perf_counter()
 print(f"map_embedding {1e3*(t1-t0):.1f} ms, transfer {1e3*(t2-t1):.1f} ms")
+if os.environ.get("COLD") == "1":   # what the `cold` variant of bench.py times: every cache and staging buffer dropped first
+    tl.clear_caches(); torch.cuda.synchronize()
+    t0 = time.perf_counter(); t1 = step(); t2 = time.perf_counter()
+    print(f"cold: map_embedding {1e3*(t1-t0):.1f} ms, transfer {1e3*(t2-t1):.1f} ms")
+    tl.clear_caches(); torch.cuda.synchronize()
 pr = cProfile.Profile(); pr.enable(); step(); pr.disable()
 pstats.Stats(pr).sort_stats("cumulative").print_stats(int(os.environ.get("TOP", 28)))
