@@ -934,26 +934,37 @@ def test_knn_exact_rows_kernel(cuda_device, n_rows, M, d, k):
 
 
 def test_few_uncertified_rows_take_the_exact_path(cuda_device, monkeypatch):
-    """A search that leaves a handful of rows uncertified finishes them with `knn_exact_rows` (no second scan) and
-    returns what the tiered repair returns."""
+    """A search that leaves a handful of rows uncertified finishes them with `knn_exact_rows` (no second scan), and
+    what it returns for them is the float64 brute-force answer.  The rows: queries inside a knot of 400 reference
+    cells 1e-4 apart — FP32 tells them apart, FP16 operands (1e-3) cannot, and the knot is wider than the k + 8
+    candidate groups of 8 a row keeps, so the first tier cannot certify them."""
     rng = np.random.default_rng(5)
     M, N, d, k = 60000, 9000, 30, 10
     ref = rng.normal(size=(M, d)).astype(np.float32)
     qry = rng.normal(size=(N, d)).astype(np.float32)
-    qry[:5] *= 300.0                                        # far outside the reference: FP16 scores cannot certify them
+    base = rng.normal(size=d)
+    ref[:400] = (base + 1e-4 * rng.normal(size=(400, d))).astype(np.float32)
+    qry[:5] = (base + 1e-4 * rng.normal(size=(5, d))).astype(np.float32)
     index = engine.knn_fit(torch.from_numpy(ref).to(cuda_device))
     Q = torch.from_numpy(qry).to(cuda_device)
     used = []
     real = engine.knn_exact_rows
-    monkeypatch.setattr(engine, "knn_exact_rows", lambda *a: used.append(int(a[2].numel())) or real(*a))
+
+    def spy(index, Q, rows, k, ub):
+        out = real(index, Q, rows, k, ub)
+        used.append((rows.tolist(), out[2].tolist()))
+        return out
+
+    monkeypatch.setattr(engine, "knn_exact_rows", spy)
     i1, d1, n1 = engine.knn_search_certified(index, Q, k)
-    assert 0 < n1 <= engine.EXACT_ROWS_MAX and used == [n1]
-    monkeypatch.setenv("SYM_KNN_EXACT_ROWS", "0")
-    i0, d0, n0 = engine.knn_search_certified(index, Q, k)
-    assert n0 == n1 and len(used) == 1
-    assert torch.equal(i0, i1) and torch.allclose(d0, d1, rtol=1e-6)
-    want, _ = so.knn_indices(ref.astype(np.float64), qry[:50].astype(np.float64), k)
-    assert (i1[:50].cpu().numpy() == want).mean() > 0.999
+    assert 5 <= n1 <= engine.EXACT_ROWS_MAX, n1
+    assert len(used) == 1 and len(used[0][0]) == n1 and set(range(5)) <= set(used[0][0]), used
+    assert sum(used[0][1]) == 0, f"bound useless for rows {used}"       # (every row was finished by the exact path)
+    want, want_d = so.knn_indices(ref.astype(np.float64), qry[:50].astype(np.float64), k)
+    got = i1[:50].cpu().numpy()
+    assert (got[:5] == want[:5]).all(), (got[:5], want[:5])
+    assert (got == want).mean() > 0.999
+    np.testing.assert_allclose(d1[:50].cpu().numpy(), want_d, rtol=1e-4, atol=1e-9)
 
 
 @pytest.mark.parametrize("N,d,K", [(5000, 20, 30), (70000, 30, 100), (1500, 8, 200), (257, 3, 1)])
