@@ -47,6 +47,10 @@ int64_t sym_launch_count(void);
  * (symphonypy/tl.py:425-426 fits the classifier each time) — and re-hashes the arrays on every call: a foreign-function
  * call releases the interpreter lock, so the hashing overlaps the caller's other host work.  Not cryptographic. */
 uint64_t sym_host_digest64(const void *data, uint64_t nbytes, int32_t threads);
+/* memcpy of HOST memory on up to `threads` host threads (dst and src must not overlap).  Synchronous, no GPU work.  The
+ * host layer stages pageable input arrays into page-locked memory with it when the process has been left a single
+ * intra-op thread (torchrun exports OMP_NUM_THREADS=1): the staging copy is what bounds a pageable input then. */
+void sym_host_copy(void *dst, const void *src, uint64_t nbytes, int32_t threads);
 /* Compute capability (major*10+minor) the kernels were compiled for: 100. */
 int sym_compiled_arch(void);
 

@@ -21,6 +21,7 @@ SIGNATURES = {
     "sym_launch_count": (c_int64, []),
     "sym_compiled_arch": (c_int32, []),
     "sym_host_digest64": (c_uint64, [_P, c_uint64, c_int32]),
+    "sym_host_copy": (None, [_P, _P, c_uint64, c_int32]),
     "sym_project_dense": (c_int32, [_P, c_int64, c_int64, _P, c_int32, _P, _P, _P, c_int32, c_int32, c_float, _P,
                                     c_int32, _P]),
     "sym_project_pack_bytes": (c_size_t, [c_int32, c_int32]),

@@ -57,6 +57,29 @@ constexpr uint64_t DIGEST_CHUNK = 8ull << 20;   // fixed, so the digest does not
 }  // namespace sym
 
 extern "C" {
+void sym_host_copy(void *dst, const void *src, uint64_t nbytes, int32_t threads) {
+    // memcpy on a few threads: 4 MiB pieces handed out round-robin.  Staging a pageable input into page-locked memory is
+    // bound by how many cores copy; torch's CPU copy does this with its intra-op threads, which a launcher may have
+    // limited to one per process (torchrun sets OMP_NUM_THREADS=1).
+    constexpr uint64_t PIECE = 4ull << 20;
+    const uint64_t pieces = (nbytes + PIECE - 1) / PIECE;
+    uint64_t nt = threads < 1 ? 1 : (uint64_t)threads;
+    if (nt > pieces) nt = pieces;
+    auto work = [&](uint64_t first, uint64_t step) {
+        for (uint64_t i = first; i < pieces; i += step) {
+            const uint64_t off = i * PIECE, len = nbytes - off < PIECE ? nbytes - off : PIECE;
+            memcpy((unsigned char *)dst + off, (const unsigned char *)src + off, len);
+        }
+    };
+    if (nt <= 1) {
+        if (nbytes) memcpy(dst, src, nbytes);
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (uint64_t t = 1; t < nt; ++t) pool.emplace_back(work, t, nt);
+    work(0, nt);
+    for (auto &t : pool) t.join();
+}
 uint64_t sym_host_digest64(const void *data, uint64_t nbytes, int32_t threads) {
     using namespace sym;
     const unsigned char *p = (const unsigned char *)data;

@@ -180,9 +180,21 @@ def _pinned_stage(nbytes: int, slot: int) -> torch.Tensor:
 _STAGE_CHUNK = 48 << 20      # bytes per staged chunk
 
 
+_TORCH_NP = {torch.float32: np.float32, torch.int32: np.int32, torch.int64: np.int64, torch.float64: np.float64,
+             torch.uint8: np.uint8}
+
+
 def _stage_copy(dst: torch.Tensor, src: np.ndarray) -> None:
     """dst[...] = src for host arrays (1-D, same length; converts the dtype on the way).  torch's CPU copy is
-    parallel over its intra-op threads and runs at memory speed (a thread pool of numpy copies measured half of it)."""
+    parallel over its intra-op threads and runs at memory speed (a thread pool of numpy copies measured half of it).
+    When the process has been left fewer intra-op threads than its share of the cores (torchrun exports
+    OMP_NUM_THREADS=1: one staging thread per rank, 4x slower end to end) a same-dtype copy goes through the library's
+    own threads instead (`sym_host_copy`)."""
+    want = _hash_threads()
+    if (want > torch.get_num_threads() and src.nbytes >= (1 << 20) and src.flags.c_contiguous and dst.is_contiguous()
+            and _TORCH_NP.get(dst.dtype) == src.dtype.type and dst.numel() == src.size):
+        _lib.load().sym_host_copy(dst.data_ptr(), src.ctypes.data, src.nbytes, want)
+        return
     if not src.flags.writeable:
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")

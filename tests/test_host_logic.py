@@ -393,6 +393,55 @@ def test_host_digest_is_thread_count_independent_and_sees_every_byte(built_libra
     assert dig(np.zeros((8 << 20) + 1, np.uint8)) != dig(np.zeros(8 << 20, np.uint8))
 
 
+def test_host_copy_and_staging_with_one_intra_op_thread(built_library, monkeypatch):
+    """`sym_host_copy` (threaded memcpy of the C-ABI library, host only) copies exactly the bytes it is given, and
+    `tl._stage_copy` takes it for same-dtype copies when the process has fewer torch intra-op threads than its share of
+    the cores (torchrun's OMP_NUM_THREADS=1) — dtype conversions still go through torch."""
+    import torch
+
+    from symphonypy_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.default_rng(2)
+    for n in (0, 1, 4093, (4 << 20) - 1, 4 << 20, (9 << 20) + 5):
+        src = rng.integers(0, 256, n, dtype=np.uint8)
+        for threads in (1, 3, 8):
+            dst = np.full(n + 16, 7, dtype=np.uint8)
+            lib.sym_host_copy(dst.ctypes.data + 8, src.ctypes.data, n, threads)
+            assert (dst[8:8 + n] == src).all() and (dst[:8] == 7).all() and (dst[8 + n:] == 7).all(), (n, threads)
+
+    calls = []
+    real = lib.sym_host_copy
+
+    class Spy:
+        def __getattr__(self, name):
+            return getattr(lib, name)
+
+        def sym_host_copy(self, *a):
+            calls.append(a[2])
+            return real(*a)
+
+    monkeypatch.setattr(tl._lib, "load", lambda: Spy())
+    monkeypatch.setattr(tl, "_hash_threads", lambda: 4)
+    monkeypatch.setattr(torch, "get_num_threads", lambda: 1)
+    src = rng.standard_normal(600_000).astype(np.float32)
+    dst = torch.zeros(600_000, dtype=torch.float32)
+    tl._stage_copy(dst, src)
+    assert calls == [src.nbytes] and np.array_equal(dst.numpy(), src)
+    idx = rng.integers(0, 2000, 500_000).astype(np.int32)
+    dsti = torch.zeros(500_000, dtype=torch.int32)
+    tl._stage_copy(dsti, idx)
+    assert len(calls) == 2 and np.array_equal(dsti.numpy(), idx)
+    src64 = rng.standard_normal(400_000)                                  # float64 -> float32: torch converts
+    tl._stage_copy(dst[:400_000], src64)
+    assert len(calls) == 2 and np.array_equal(dst[:400_000].numpy(), src64.astype(np.float32))
+    tl._stage_copy(dst[:1000], src[:1000])                                # small: not worth threads
+    assert len(calls) == 2
+    monkeypatch.setattr(torch, "get_num_threads", lambda: 16)             # torch has the cores: its own copy
+    tl._stage_copy(dst, src)
+    assert len(calls) == 2 and np.array_equal(dst.numpy(), src)
+
+
 def test_decode_labels_in_chunks(monkeypatch):
     """Long label columns are gathered on a few threads; the column equals the single-call one."""
     import pandas as pd
